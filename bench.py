@@ -1,0 +1,319 @@
+#!/usr/bin/env python
+"""bench.py — cost-volume throughput (build + aggregate + WTA) in Mpix*disp/s.
+
+One "step" = the full dense-matching job of the workload: every reference view of the synthetic
+8-view refractive scene (BASELINE.json configs[3], "cfg4", the configuration north_star quotes
+its target on) through sr_run_view: stage (1) refractive tap-volume build, stages (2)+(3)
+support-weight aggregation with fused WTA.  Metric = sum over reference views of H*W*D / time.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload cfg4|cfg3|small]
+
+N > 1 is launched by torchrun (one rank per GPU); reference views are partitioned across ranks
+(north_star: "by reference view for multi-view runs"), no collective on the data path; the total
+work is fixed, so scaling is "strong".  `--impl reference` times the CPU oracle (the reference
+cannot be compiled here) on a bounded row band with all host threads.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+from stereoreconstruction_b200 import scenes, types as T  # noqa: E402
+
+METRIC = "cost-volume Mpix*disp/s (build+aggregate+WTA)"
+UNIT = "Mpix*disp/s"
+
+
+def workload(name):
+    """Returns dict(w,h,V,D,params,cams,max_nbrs,desc)."""
+    if name == "cfg4":
+        w, h, V, D = 1920, 1080, 8, 256
+    elif name == "cfg5":
+        w, h, V, D = 3840, 2160, 8, 512
+    elif name == "small":
+        w, h, V, D = 480, 270, 8, 64
+    elif name == "cfg3":
+        w, h, V, D = 1920, 1080, 2, 256
+    else:
+        raise SystemExit(f"unknown workload {name}")
+    if name == "cfg3":
+        cams, _ = scenes.rectified_pair(w, h, z0=100.0)
+        P = T.default_params(False, 100.0, 500.0, D, radius=16, weight_kind=T.SR_WEIGHT_ADAPTIVE)
+        desc = "cfg3: synthetic rectified 1920x1080 pair, 256 disparities, AdaptiveWeight 33x33, NCC, both directions"
+        surf = scenes.HeightField(z0=167.0, amp=20.0, lx=25.0, ly=18.0)
+        cell = 3.5 * 167.0 / cams[0].K[0]
+        seed = 1234
+    else:
+        cams = scenes.arc_cameras(V, w, h)
+        P = T.default_params(True, 350.0, 650.0, D)  # GeodesicWeight r=2, NCC, 3 neighbours (reference defaults)
+        desc = (f"{name}: synthetic refractive {V}-view {w}x{h}, {D} depth hypotheses, tilted planar interface "
+                f"(n=1.333), lens distortion, GeodesicWeight r=2, 3 nearest neighbour views, all reference views")
+        surf = scenes.HeightField(z0=0.0, amp=25.0, lx=90.0, ly=70.0)
+        cell = 3.5 * 500.0 / cams[0].K[0]
+        seed = 4321 if name != "cfg5" else 8765
+    return dict(name=name, w=w, h=h, V=V, D=D, params=P, cams=cams, desc=desc, surf=surf, cell=cell, seed=seed)
+
+
+def neighbours_for(wl, ctx=None):
+    if wl["name"] == "cfg3":
+        return [[1], [0]]
+    return scenes.nearest_neighbours(wl["cams"], 3)
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+
+    def __init__(self, gpu_index):
+        super().__init__(daemon=True)
+        self.gpu = gpu_index
+        self.rows = []
+        self.stop_flag = False
+        self.proc = None
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={q}",
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            for line in self.proc.stdout:
+                if self.stop_flag:
+                    break
+                self.rows.append([c.strip() for c in line.split(",")])
+        except Exception:
+            pass
+
+    def finish(self):
+        self.stop_flag = True
+        if self.proc:
+            self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx.append(float(r[1]))
+            except (ValueError, IndexError):
+                continue
+            for name, val in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], r[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_sample(wl, imgs, rows, steps=1, warmup=0):
+    """Times the CPU oracle (all host threads) on `rows` rows of reference view 0 of the workload."""
+    from oracle import oracle_api as O
+    sc = O.Scene(wl["cams"], imgs)
+    nb = neighbours_for(wl)
+    P = T.SrParams.from_buffer_copy(wl["params"])
+    r0 = (wl["h"] - rows) // 2
+    P.row_begin, P.row_end = r0, r0 + rows
+    times = []
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        if wl["name"] == "cfg3":
+            sc.twoview_label(P, 0, 1)
+        else:
+            sc.mvs_view(P, 0, nb[0])
+        dt = time.perf_counter() - t0
+        if i >= warmup:
+            times.append(dt)
+    units = rows * wl["w"] * wl["D"]
+    t = sum(times) / len(times)
+    return units / t / 1e6, t, O.num_threads(), f"{rows} rows x {wl['w']} px x {wl['D']} labels of reference view 0 (rows {r0}..{r0 + rows})"
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="cfg4")
+    ap.add_argument("--cpu-rows", type=int, default=0, help="rows of the CPU sample (0 = auto)")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    wl = workload(args.workload)
+    w, h, V, D = wl["w"], wl["h"], wl["V"], wl["D"]
+    cpu_rows = args.cpu_rows or max(2, int(16 * (1920.0 / w) * (256.0 / D) * (0.08 if wl["name"] == "cfg3" else 1)))
+
+    # ------------------------------------------------------------------ reference arm (CPU oracle)
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        imgs = scenes.noise_images(V, w, h, wl["seed"])  # content does not change the CPU work
+        val, t, cores, sample = cpu_sample(wl, imgs, cpu_rows, steps=max(1, args.steps), warmup=min(args.warmup, 1))
+        line = {
+            "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": t * 1e3, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": wl["desc"], "note": "CPU oracle (restated reference, OpenMP over rows); each step = the bounded sample"},
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        }
+        print(json.dumps(line))
+        return
+
+    # ------------------------------------------------------------------ our arm (CUDA)
+    import torch
+    import torch.distributed as dist
+    from stereoreconstruction_b200 import capi
+
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    ctx = capi.Context(local_rank)
+    stream = torch.cuda.current_stream()
+    ctx.set_stream(stream.cuda_stream)
+
+    # synthetic, photo-consistent inputs rendered through the GPU's own unproject
+    cams = wl["cams"]
+    blank = [np.zeros((h, w, 4), np.uint8)] * V
+    ctx.set_views(cams, blank, None)
+    ctx.set_params(wl["params"])
+    imgs = scenes.render_views(V, lambda v: ctx.unproject_grid(v), wl["surf"], wl["seed"], wl["cell"])
+    pinned = [torch.from_numpy(im).pin_memory() for im in imgs]
+    imgs_p = [p.numpy() for p in pinned]
+    ctx.set_views(cams, imgs_p, None)
+    nbrs = neighbours_for(wl)
+    my_views = [v for v in range(V) if v % world == rank]
+    units_total = V * h * w * D
+
+    def step():
+        for v in my_views:
+            ctx.run_view(v, nbrs[v])
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    launches0 = ctx.launch_count()
+    ctx.set_profiling(True)
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record(stream)
+    for _ in range(args.steps):
+        step()
+    ev1.record(stream)
+    barrier()
+    ms = ev0.elapsed_time(ev1)
+    clocks = sampler.finish()
+    stages = ctx.stage_ms()
+    ctx.set_profiling(False)
+    launches = ctx.launch_count() - launches0
+    if world > 1:
+        tmax = torch.tensor([ms], device="cuda")
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        ms = float(tmax.item())
+    ms_per_step = ms / args.steps
+    value = units_total / (ms_per_step * 1e-3) / 1e6
+
+    # end-to-end through the C ABI with host buffers: H2D of all images + run + D2H of the index maps
+    idx_host = [torch.empty((h, w), dtype=torch.int32).pin_memory().numpy() for _ in my_views]
+
+    def e2e_step():
+        ctx.set_views(cams, imgs_p, None)
+        ctx.set_params(wl["params"])
+        for v in my_views:
+            ctx.run_view(v, nbrs[v])
+        for k, v in enumerate(my_views):
+            ctx.depth_index(v, out=idx_host[k])
+
+    e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    e2e_steps = max(1, min(args.steps, 2))
+    for _ in range(e2e_steps):
+        e2e_step()
+    barrier()
+    e2e_s = (time.perf_counter() - t0) / e2e_steps
+    if world > 1:
+        tmax = torch.tensor([e2e_s], device="cuda", dtype=torch.float64)
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        e2e_s = float(tmax.item())
+    e2e_val = units_total / e2e_s / 1e6
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # roofline of the dominant kernel (match_kernel: streams the tap volume once, fused WTA)
+    peaks = {}
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            peaks = json.load(f)
+    except OSError:
+        pass
+    peak_gbs = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback (B200_PROFILING.md)"
+    n_nbr = len(nbrs[my_views[0]])
+    n_match = max(1, stages["match_launches"])
+    match_ms = stages["match_ms"] / n_match
+    build_ms = stages["build_ms"] / n_match
+    # 8 B per pixel*disparity (volume written once by build, read once by
+    # aggregate+WTA) + H*W*(4*(1+N_nbr)+4) per reference view; the match launch owns the read half
+    # and the per-pixel terms.
+    alg_bytes_match = h * w * D * 4 + h * w * (4 * (1 + n_nbr) + 4)
+    alg_bytes_view = h * w * D * 8 + h * w * (4 * (1 + n_nbr) + 4)
+    achieved = alg_bytes_match / (match_ms * 1e-3) / 1e9
+    pipe_gbs = alg_bytes_view / ((match_ms + build_ms) * 1e-3) / 1e9
+    roofline = {
+        "bound": "hbm", "kernel": "match_kernel (weights + windowed NCC + fused WTA)", "achieved": achieved,
+        "peak": peak_gbs, "unit": "GB/s", "frac": achieved / peak_gbs, "traffic": None, "peak_source": peak_src,
+        "match_ms_per_view": match_ms, "build_ms_per_view": build_ms,
+        "pipeline_achieved_gbs": pipe_gbs, "pipeline_frac": pipe_gbs / peak_gbs,
+        "binding_bound": "FP64 issue (see DESIGN.md: ~200 FP64 instructions per pixel*label*neighbour)",
+    }
+
+    cpu = None
+    if not args.no_cpu:
+        val, t, cores, sample = cpu_sample(wl, imgs, cpu_rows)
+        cpu = {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample, "seconds": t}
+
+    h2d = V * h * w * 4 * (len(my_views) / V if world > 1 else 1)
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": wl["desc"], "views_per_rank": len(my_views), "neighbours": n_nbr,
+                   "l2": "inputs larger than L2 (tap volume %.1f GB per view streams through HBM)" % (n_nbr * h * w * D * 4 / 1e9),
+                   "partition": "reference views round-robin over ranks"},
+        "clocks": clocks,
+        "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": int(V * h * w * 4),
+                "d2h_bytes_per_step": int(len(my_views) * h * w * 4), "seconds_per_step": e2e_s},
+        "gpu_launches": launches,
+        "roofline": roofline,
+        "cpu_baseline": cpu,
+    }
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

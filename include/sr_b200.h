@@ -115,6 +115,11 @@ int sr_set_stream(sr_ctx *ctx, void *cuda_stream);
 void sr_params_default(sr_params *p, int multi_view);
 /* Number of kernels this context has launched since creation. */
 int64_t sr_launch_count(const sr_ctx *ctx);
+/* Per-stage device timing with CUDA events on the context stream (replaces the QTime
+ * prints of stereo/twoviewstereo.cpp:260,333).  sr_get_stage_ms synchronises and returns
+ * {build ms, match ms, build bands, match launches} accumulated since its last call. */
+int sr_set_profiling(sr_ctx *ctx, int on);
+int sr_get_stage_ms(sr_ctx *ctx, double *out4);
 
 /* ---- inputs -----------------------------------------------------------------*/
 /* Replaces the image/mask ingestion of TwoViewStereo::TwoViewStereo
@@ -155,10 +160,11 @@ int sr_get_depth_index(sr_ctx *ctx, int view, int32_t *out);
 /* computedDepth* / computedDepths[view] (stereo/twoviewstereo.hpp:41,
  * stereo/multiviewstereo.hpp:106-107): doubles with NaN / +INF / -1 sentinels. */
 int sr_get_depth(sr_ctx *ctx, int view, double *out);
-/* Best cost per pixel (min cost two-view, max ncc MVS), float w*h. */
-int sr_get_best_cost(sr_ctx *ctx, int view, float *out);
+/* Best cost per pixel (min cost two-view, max ncc MVS), double w*h. */
+int sr_get_best_cost(sr_ctx *ctx, int view, double *out);
 /* The cost volume of the last sr_run_view with keep_cost_volume, float
- * [nbr][row - row_begin][x][d]; NaN where the label could not be evaluated. */
+ * [nbr][d][row - row_begin][x] (label-major planes, the layout the kernels stream);
+ * NaN where the label could not be evaluated. */
 int sr_get_cost_volume(sr_ctx *ctx, float *out, size_t out_elems);
 /* Replaces depth upload for cross-check under view sharding (each rank receives
  * the other ranks' depth maps before sr_cross_check). */

@@ -1,0 +1,712 @@
+// sr_capi.cu — the C ABI of include/sr_b200.h: context, device memory, launches.
+// Host code is C++; everything numeric runs in the kernels of sr_kernels.cuh / sr_curve.cuh.
+// There is no CPU fallback: every entry point that computes launches CUDA kernels.
+#include <atomic>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <dlfcn.h>
+#include <string>
+#include <vector>
+#include <algorithm>
+
+#include "sr_kernels.cuh"
+#include "sr_match_dispatch.cuh"
+
+using namespace sr;
+
+namespace {
+
+std::string g_create_error;
+
+struct ViewDev {
+    uchar4 *rgba = nullptr;
+    uint8_t *mask = nullptr;
+    double *gray_pix = nullptr, *gray_two = nullptr, *gray_msk = nullptr;
+    int32_t *index = nullptr;
+    double *depth = nullptr, *best = nullptr;
+};
+
+// ---- NCCL through dlopen (the library loads without NCCL; sr_comm_* fail loudly) ------------
+typedef struct ncclComm *ncclComm_t;
+struct Uid128 {
+    char b[128];
+};
+struct NcclApi {
+    void *handle = nullptr;
+    int (*GetUniqueId)(void *) = nullptr;
+    int (*CommInitRank)(ncclComm_t *, int, Uid128 /* ncclUniqueId by value */, int) = nullptr;
+    int (*CommDestroy)(ncclComm_t) = nullptr;
+    int (*Broadcast)(const void *, void *, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+    int (*GroupStart)() = nullptr;
+    int (*GroupEnd)() = nullptr;
+    const char *(*GetErrorString)(int) = nullptr;
+};
+NcclApi g_nccl;
+const int NCCL_CHAR = 0;
+
+bool load_nccl(std::string &err) {
+    if (g_nccl.handle) return true;
+    const char *names[] = {"libnccl.so.2", "libnccl.so"};
+    for (const char *n : names) {
+        g_nccl.handle = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+        if (g_nccl.handle) break;
+    }
+    if (!g_nccl.handle) {
+        err = std::string("cannot dlopen libnccl.so.2: ") + dlerror();
+        return false;
+    }
+#define LD(field, sym)                                                    \
+    *(void **)(&g_nccl.field) = dlsym(g_nccl.handle, sym);                \
+    if (!g_nccl.field) {                                                  \
+        err = std::string("NCCL symbol missing: ") + sym;                 \
+        return false;                                                     \
+    }
+    LD(GetUniqueId, "ncclGetUniqueId");
+    LD(CommInitRank, "ncclCommInitRank");
+    LD(CommDestroy, "ncclCommDestroy");
+    LD(Broadcast, "ncclBroadcast");
+    LD(GroupStart, "ncclGroupStart");
+    LD(GroupEnd, "ncclGroupEnd");
+    LD(GetErrorString, "ncclGetErrorString");
+#undef LD
+    return true;
+}
+
+}  // namespace
+
+struct sr_ctx {
+    int device = 0;
+    cudaStream_t own_stream = nullptr, stream = nullptr;
+    std::string err;
+    std::atomic<bool> cancel{false};
+    int V = 0, w = 0, h = 0;
+    std::vector<sr_camera> cams;
+    sr_camera *d_cams = nullptr;
+    std::vector<ViewDev> views;
+    double **d_depth_ptrs = nullptr;  // device array of per-view depth map pointers
+    sr_params params{};
+    bool have_params = false;
+    std::vector<double> depth_table;
+    double *d_depth_table = nullptr;
+    int depth_table_cap = 0;
+    double *d_rays = nullptr;
+    int32_t *d_taps = nullptr;
+    size_t taps_cap = 0;
+    float *d_volume = nullptr;
+    size_t vol_cap = 0, vol_elems = 0;
+    void *d_scratch = nullptr;
+    size_t scratch_cap = 0;
+    int64_t launches = 0;
+    size_t tap_budget = (size_t)8 << 30;
+    ncclComm_t comm = nullptr;
+    int rank = 0, nranks = 1;
+    // per-stage CUDA-event timing (sr_set_profiling): [begin, after build, after match] per band
+    bool profiling = false;
+    std::vector<cudaEvent_t> prof_events;
+};
+
+namespace {
+
+int fail(sr_ctx *c, int code, const std::string &msg) {
+    if (c) c->err = msg;
+    else g_create_error = msg;
+    return code;
+}
+#define CK(call)                                                                                       \
+    do {                                                                                               \
+        cudaError_t e_ = (call);                                                                       \
+        if (e_ != cudaSuccess)                                                                         \
+            return fail(ctx, SR_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_));         \
+    } while (0)
+#define CKL()                                                                                          \
+    do {                                                                                               \
+        ++ctx->launches;                                                                               \
+        cudaError_t e_ = cudaGetLastError();                                                           \
+        if (e_ != cudaSuccess)                                                                         \
+            return fail(ctx, SR_ERR_CUDA, std::string("kernel launch: ") + cudaGetErrorString(e_));    \
+    } while (0)
+
+template <typename T>
+void dfree(T *&p) {
+    if (p) cudaFree(p);
+    p = nullptr;
+}
+
+void free_views(sr_ctx *c) {
+    for (ViewDev &v : c->views) {
+        dfree(v.rgba);
+        dfree(v.mask);
+        dfree(v.gray_pix);
+        dfree(v.gray_two);
+        dfree(v.gray_msk);
+        dfree(v.index);
+        dfree(v.depth);
+        dfree(v.best);
+    }
+    c->views.clear();
+    dfree(c->d_cams);
+    dfree(c->d_depth_ptrs);
+    dfree(c->d_rays);
+}
+
+int ensure_scratch(sr_ctx *ctx, size_t bytes) {
+    if (bytes <= ctx->scratch_cap) return SR_OK;
+    if (ctx->d_scratch) cudaFree(ctx->d_scratch);
+    ctx->d_scratch = nullptr;
+    ctx->scratch_cap = 0;
+    CK(cudaMalloc(&ctx->d_scratch, bytes));
+    ctx->scratch_cap = bytes;
+    return SR_OK;
+}
+
+double depth_from_label(const sr_params &p, int label) {
+    double t = label / (p.num_levels - 1.0);
+    if (p.depth_kind == SR_DEPTH_INV5) t /= (5 - 4 * t);  // stereo/twoviewstereo.cpp:981-985
+    return p.min_depth * (1 - t) + p.max_depth * t;        // stereo/multiviewstereo.cpp:733-736
+}
+
+int check_view(sr_ctx *ctx, int v) {
+    if (!ctx) return SR_ERR_INVALID;
+    if (ctx->V == 0) return fail(ctx, SR_ERR_STATE, "sr_set_views has not been called");
+    if (v < 0 || v >= ctx->V) return fail(ctx, SR_ERR_INVALID, "view index out of range");
+    return SR_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int sr_ctx_create(int device, sr_ctx **out) {
+    if (!out) return fail(nullptr, SR_ERR_INVALID, "out is null");
+    *out = nullptr;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0)
+        return fail(nullptr, SR_ERR_CUDA,
+                    std::string("no CUDA device (this library has no CPU fallback): ") + cudaGetErrorString(e));
+    if (device < 0 || device >= n) return fail(nullptr, SR_ERR_INVALID, "device index out of range");
+    e = cudaSetDevice(device);
+    if (e != cudaSuccess) return fail(nullptr, SR_ERR_CUDA, cudaGetErrorString(e));
+    sr_ctx *c = new sr_ctx;
+    c->device = device;
+    e = cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking);
+    if (e != cudaSuccess) {
+        delete c;
+        return fail(nullptr, SR_ERR_CUDA, cudaGetErrorString(e));
+    }
+    c->stream = c->own_stream;
+    if (const char *mb = getenv("SR_TAP_BUDGET_MB")) c->tap_budget = (size_t)atoll(mb) << 20;
+    *out = c;
+    return SR_OK;
+}
+
+void sr_ctx_destroy(sr_ctx *c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    if (c->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
+    free_views(c);
+    dfree(c->d_depth_table);
+    dfree(c->d_taps);
+    dfree(c->d_volume);
+    if (c->d_scratch) cudaFree(c->d_scratch);
+    cudaStreamDestroy(c->own_stream);
+    delete c;
+}
+
+const char *sr_last_error(const sr_ctx *c) { return c ? c->err.c_str() : g_create_error.c_str(); }
+void sr_request_cancel(sr_ctx *c) {
+    if (c) c->cancel.store(true);
+}
+void sr_clear_cancel(sr_ctx *c) {
+    if (c) c->cancel.store(false);
+}
+int sr_set_stream(sr_ctx *c, void *s) {
+    if (!c) return SR_ERR_INVALID;
+    c->stream = s ? (cudaStream_t)s : c->own_stream;
+    return SR_OK;
+}
+int64_t sr_launch_count(const sr_ctx *c) { return c ? c->launches : 0; }
+
+void sr_params_default(sr_params *p, int multi_view) {
+    memset(p, 0, sizeof(*p));
+    p->min_depth = 10.0;  // gui/forms/stereowidget.ui defaults
+    p->max_depth = 100.0;
+    p->num_levels = 100;
+    p->image_scale = 1.0;
+    p->weight_kind = SR_WEIGHT_GEODESIC;  // typedef GeodesicWeight WeightFunc
+    p->second_best_factor = 0.95;
+    p->ncc_threshold = 0.95;
+    if (multi_view) {
+        p->radius = 2;
+        p->cost_kind = SR_COST_NCC_MVS;
+        p->depth_kind = SR_DEPTH_LINEAR;
+        p->select_kind = SR_SELECT_MVS;
+    } else {
+        p->radius = 5;
+        p->cost_kind = SR_COST_NCC_TWOVIEW;
+        p->depth_kind = SR_DEPTH_INV5;
+        p->select_kind = SR_SELECT_TWOVIEW;
+    }
+}
+
+int sr_set_views(sr_ctx *ctx, int V, const sr_camera *cams, const uint8_t *const *rgba8, const uint8_t *const *mask8,
+                 int w, int h) {
+    if (!ctx) return SR_ERR_INVALID;
+    if (V <= 0 || !cams || !rgba8 || w <= 0 || h <= 0 || w > 16384 || h > 16384)
+        return fail(ctx, SR_ERR_INVALID, "sr_set_views: bad arguments (1 <= w,h <= 16384)");
+    CK(cudaSetDevice(ctx->device));
+    const size_t n = (size_t)w * h;
+    if (V != ctx->V || w != ctx->w || h != ctx->h) {
+        CK(cudaStreamSynchronize(ctx->stream));
+        free_views(ctx);
+        ctx->views.resize(V);
+        for (ViewDev &v : ctx->views) {
+            CK(cudaMalloc(&v.rgba, n * 4));
+            CK(cudaMalloc(&v.mask, n));
+            CK(cudaMalloc(&v.gray_pix, n * 8));
+            CK(cudaMalloc(&v.gray_two, n * 8));
+            CK(cudaMalloc(&v.gray_msk, n * 8));
+            CK(cudaMalloc(&v.index, n * 4));
+            CK(cudaMalloc(&v.depth, n * 8));
+            CK(cudaMalloc(&v.best, n * 8));
+        }
+        CK(cudaMalloc(&ctx->d_cams, sizeof(sr_camera) * V));
+        CK(cudaMalloc(&ctx->d_depth_ptrs, sizeof(double *) * V));
+        CK(cudaMalloc(&ctx->d_rays, n * 6 * 8));
+        std::vector<double *> ptrs(V);
+        for (int i = 0; i < V; ++i) ptrs[i] = ctx->views[i].depth;
+        CK(cudaMemcpyAsync(ctx->d_depth_ptrs, ptrs.data(), sizeof(double *) * V, cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        ctx->V = V;
+        ctx->w = w;
+        ctx->h = h;
+    }
+    ctx->cams.assign(cams, cams + V);
+    CK(cudaMemcpyAsync(ctx->d_cams, ctx->cams.data(), sizeof(sr_camera) * V, cudaMemcpyHostToDevice, ctx->stream));
+    for (int i = 0; i < V; ++i) {
+        ViewDev &v = ctx->views[i];
+        if (!rgba8[i]) return fail(ctx, SR_ERR_INVALID, "sr_set_views: null image");
+        CK(cudaMemcpyAsync(v.rgba, rgba8[i], n * 4, cudaMemcpyHostToDevice, ctx->stream));
+        if (mask8 && mask8[i]) CK(cudaMemcpyAsync(v.mask, mask8[i], n, cudaMemcpyHostToDevice, ctx->stream));
+        else CK(cudaMemsetAsync(v.mask, 255, n, ctx->stream));
+        prep_view_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(v.rgba, v.mask, w, h, v.gray_pix,
+                                                                             v.gray_two, v.gray_msk);
+        CKL();
+        // results start as "not computed": NaN depth (twoviewstereo.cpp:118-119), index NONE
+        CK(cudaMemsetAsync(v.depth, 0xff, n * 8, ctx->stream));
+        CK(cudaMemsetAsync(v.best, 0xff, n * 8, ctx->stream));
+        CK(cudaMemsetAsync(v.index, 0xff, n * 4, ctx->stream));
+    }
+    return SR_OK;
+}
+
+int sr_set_params(sr_ctx *ctx, const sr_params *p) {
+    if (!ctx || !p) return SR_ERR_INVALID;
+    if (p->num_levels < 2 || p->num_levels > 65536) return fail(ctx, SR_ERR_INVALID, "num_levels must be in [2,65536]");
+    if (!(p->image_scale > 0)) return fail(ctx, SR_ERR_INVALID, "image_scale must be > 0");
+    if (!match_supported(p->radius))
+        return fail(ctx, SR_ERR_INVALID, "unsupported window radius (supported: 1-8, 10, 12, 16)");
+    if (p->weight_kind < 0 || p->weight_kind > 1 || p->cost_kind < 0 || p->cost_kind > 2 || p->depth_kind < 0 ||
+        p->depth_kind > 1 || p->select_kind < 0 || p->select_kind > 1)
+        return fail(ctx, SR_ERR_INVALID, "bad enum in sr_params");
+    ctx->params = *p;
+    ctx->have_params = true;
+    ctx->depth_table.resize(p->num_levels);
+    for (int d = 0; d < p->num_levels; ++d) ctx->depth_table[d] = depth_from_label(*p, d);
+    CK(cudaSetDevice(ctx->device));
+    if (p->num_levels > ctx->depth_table_cap) {
+        CK(cudaStreamSynchronize(ctx->stream));
+        dfree(ctx->d_depth_table);
+        CK(cudaMalloc(&ctx->d_depth_table, sizeof(double) * p->num_levels));
+        ctx->depth_table_cap = p->num_levels;
+    }
+    CK(cudaMemcpyAsync(ctx->d_depth_table, ctx->depth_table.data(), sizeof(double) * p->num_levels,
+                       cudaMemcpyHostToDevice, ctx->stream));
+    return SR_OK;
+}
+
+int sr_run_view(sr_ctx *ctx, int ref, const int32_t *nbrs, int nn) {
+    int rc = check_view(ctx, ref);
+    if (rc) return rc;
+    if (!ctx->have_params) return fail(ctx, SR_ERR_STATE, "sr_set_params has not been called");
+    if (!nbrs || nn <= 0 || nn > SR_MAX_NBRS) return fail(ctx, SR_ERR_INVALID, "1..8 neighbour views required");
+    for (int j = 0; j < nn; ++j)
+        if (nbrs[j] < 0 || nbrs[j] >= ctx->V || nbrs[j] == ref) return fail(ctx, SR_ERR_INVALID, "bad neighbour index");
+    const sr_params &P = ctx->params;
+    if (P.select_kind == SR_SELECT_TWOVIEW && nn != 1)
+        return fail(ctx, SR_ERR_INVALID, "two-view selection takes exactly one neighbour");
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    const int w = ctx->w, h = ctx->h, D = P.num_levels;
+    const int r0 = std::max(P.row_begin, 0);
+    const int r1 = (P.row_end > 0 && P.row_end < h) ? P.row_end : h;
+    if (r0 >= r1) return fail(ctx, SR_ERR_INVALID, "empty row range");
+    const size_t n = (size_t)w * h;
+    ViewDev &A = ctx->views[ref];
+
+    rays_kernel<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(ctx->cams[ref], w, h, P.image_scale, ctx->d_rays);
+    CKL();
+
+    // Row bands bound the tap volume (nn*D*rows*w*4 bytes); a kept cost volume needs one band.
+    const size_t per_row = (size_t)nn * D * w * 4;
+    int band = (int)std::min<size_t>((size_t)(r1 - r0), std::max<size_t>(1, ctx->tap_budget / per_row));
+    if (P.keep_cost_volume) band = r1 - r0;
+    const size_t need = per_row * band;
+    if (need > ctx->taps_cap) {
+        CK(cudaStreamSynchronize(st));
+        dfree(ctx->d_taps);
+        ctx->taps_cap = 0;
+        CK(cudaMalloc(&ctx->d_taps, need));
+        ctx->taps_cap = need;
+    }
+    ctx->vol_elems = 0;
+    if (P.keep_cost_volume) {
+        if (need > ctx->vol_cap) {
+            CK(cudaStreamSynchronize(st));
+            dfree(ctx->d_volume);
+            ctx->vol_cap = 0;
+            CK(cudaMalloc(&ctx->d_volume, need));
+            ctx->vol_cap = need;
+        }
+        ctx->vol_elems = need / 4;
+    }
+
+    for (int b0 = r0; b0 < r1; b0 += band) {
+        if (ctx->cancel.load()) return fail(ctx, SR_ERR_CANCELLED, "cancelled");
+        cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
+        if (ctx->profiling) {
+            for (int k = 0; k < 3; ++k) CK(cudaEventCreate(&ev[k]));
+            CK(cudaEventRecord(ev[0], st));
+        }
+        const int rows = std::min(band, r1 - b0);
+        const size_t plane = (size_t)rows * w;
+        const unsigned gx = (unsigned)((plane + 127) / 128);
+        const int d_chunk = 32;
+        for (int j = 0; j < nn; ++j) {
+            BuildArgs ba;
+            ba.nbr = ctx->cams[nbrs[j]];
+            memcpy(ba.prin, ctx->cams[ref].prin_dir, sizeof(ba.prin));
+            memcpy(ba.C, ctx->cams[ref].C, sizeof(ba.C));
+            ba.rays = ctx->d_rays;
+            ba.depth_table = ctx->d_depth_table;
+            ba.ref_mask = A.mask;
+            ba.nbr_mask = ctx->views[nbrs[j]].mask;
+            ba.taps = ctx->d_taps + (size_t)j * D * plane;
+            ba.w = w;
+            ba.h = h;
+            ba.row0 = b0;
+            ba.rows = rows;
+            ba.D = D;
+            ba.d_chunk = d_chunk;
+            ba.scale = P.image_scale;
+            ba.mvs = (P.select_kind == SR_SELECT_MVS);
+            build_kernel<<<dim3(gx, (D + d_chunk - 1) / d_chunk), 128, 0, st>>>(ba);
+            CKL();
+        }
+        if (ctx->profiling) CK(cudaEventRecord(ev[1], st));
+        MatchArgs ma;
+        memset(&ma, 0, sizeof(ma));
+        ma.rgbaL = A.rgba;
+        ma.maskL = A.mask;
+        ma.grayL = (P.cost_kind == SR_COST_NCC_MVS) ? A.gray_pix : A.gray_two;
+        for (int j = 0; j < nn; ++j) {
+            const ViewDev &B = ctx->views[nbrs[j]];
+            ma.grayR[j] = (P.cost_kind == SR_COST_NCC_MVS) ? B.gray_pix
+                          : (P.cost_kind == SR_COST_NCC_TWOVIEW) ? B.gray_two : B.gray_msk;
+        }
+        ma.taps = ctx->d_taps;
+        ma.depth_table = ctx->d_depth_table;
+        ma.out_index = A.index;
+        ma.out_depth = A.depth;
+        ma.out_best = A.best;
+        ma.out_volume = P.keep_cost_volume ? ctx->d_volume : nullptr;
+        ma.w = w;
+        ma.h = h;
+        ma.row0 = b0;
+        ma.rows = rows;
+        ma.D = D;
+        ma.num_nbrs = nn;
+        ma.weight_kind = P.weight_kind;
+        ma.select_kind = P.select_kind;
+        ma.second_best_factor = P.second_best_factor;
+        ma.ncc_threshold = P.ncc_threshold;
+        cudaError_t e = launch_match(P.radius, P.cost_kind, ma, st);
+        ++ctx->launches;
+        if (e != cudaSuccess) return fail(ctx, SR_ERR_CUDA, std::string("match kernel: ") + cudaGetErrorString(e));
+        if (ctx->profiling) {
+            CK(cudaEventRecord(ev[2], st));
+            for (int k = 0; k < 3; ++k) ctx->prof_events.push_back(ev[k]);
+        }
+    }
+    return SR_OK;
+}
+
+int sr_set_profiling(sr_ctx *ctx, int on) {
+    if (!ctx) return SR_ERR_INVALID;
+    ctx->profiling = on != 0;
+    return SR_OK;
+}
+
+// out[0] = build-stage ms, out[1] = match-stage ms (summed over all bands run since the last
+// call), out[2] = number of build launches' bands, out[3] = number of match launches.
+int sr_get_stage_ms(sr_ctx *ctx, double *out4) {
+    if (!ctx || !out4) return SR_ERR_INVALID;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaStreamSynchronize(ctx->stream));
+    out4[0] = out4[1] = out4[2] = out4[3] = 0;
+    for (size_t i = 0; i + 2 < ctx->prof_events.size(); i += 3) {
+        float b = 0, m = 0;
+        CK(cudaEventElapsedTime(&b, ctx->prof_events[i], ctx->prof_events[i + 1]));
+        CK(cudaEventElapsedTime(&m, ctx->prof_events[i + 1], ctx->prof_events[i + 2]));
+        out4[0] += b;
+        out4[1] += m;
+        out4[2] += 1;
+        out4[3] += 1;
+    }
+    for (cudaEvent_t e : ctx->prof_events) cudaEventDestroy(e);
+    ctx->prof_events.clear();
+    return SR_OK;
+}
+
+int sr_run_view_curve(sr_ctx *ctx, int ref, const int32_t *nbrs, int nn) {
+    (void)ref;
+    (void)nbrs;
+    (void)nn;
+    return fail(ctx, SR_ERR_STATE, "sr_run_view_curve: curve-mode search is not built yet (SURVEY §8f rank 2)");
+}
+
+int sr_select_neighbours(sr_ctx *ctx, int max_nbrs, int32_t *out, int32_t *counts) {
+    if (!ctx || !out || !counts || max_nbrs <= 0) return SR_ERR_INVALID;
+    if (ctx->V == 0) return fail(ctx, SR_ERR_STATE, "sr_set_views has not been called");
+    // Host-side control logic of MultiViewStereo::runTask (stereo/multiviewstereo.cpp:335-360):
+    // V^2 dot products on the camera PODs; not part of the per-pixel path.
+    for (int i = 0; i < ctx->V; ++i) {
+        std::vector<std::pair<double, int>> nearViews;
+        const sr_camera &a = ctx->cams[i];
+        for (int j = 0; j < ctx->V; ++j) {
+            if (i == j) continue;
+            const sr_camera &b = ctx->cams[j];
+            const double dp = a.prin_dir[0] * b.prin_dir[0] + a.prin_dir[1] * b.prin_dir[1] + a.prin_dir[2] * b.prin_dir[2];
+            if (std::fabs(dp) > 0.2) {
+                const double dx = a.C[0] - b.C[0], dy = a.C[1] - b.C[1], dz = a.C[2] - b.C[2];
+                nearViews.push_back(std::make_pair(dx * dx + dy * dy + dz * dz, j));
+            }
+        }
+        size_t end = nearViews.size();
+        if ((size_t)max_nbrs < nearViews.size()) {
+            std::sort(nearViews.begin(), nearViews.end());
+            end = max_nbrs;
+        }
+        counts[i] = (int32_t)end;
+        for (size_t k = 0; k < end; ++k) out[i * max_nbrs + k] = nearViews[k].second;
+    }
+    return SR_OK;
+}
+
+int sr_cross_check(sr_ctx *ctx, int two_view, double threshold) {
+    if (!ctx) return SR_ERR_INVALID;
+    if (ctx->V == 0 || !ctx->have_params) return fail(ctx, SR_ERR_STATE, "views/params not set");
+    if (two_view && ctx->V != 2) return fail(ctx, SR_ERR_INVALID, "two-view cross-check needs exactly 2 views");
+    CK(cudaSetDevice(ctx->device));
+    const size_t n = (size_t)ctx->w * ctx->h;
+    // View by view, in place, in index order: view v sees the already-updated maps of views < v,
+    // exactly as twoviewstereo.cpp:604-670 / multiviewstereo.cpp:427-431 do.
+    for (int v = 0; v < ctx->V; ++v) {
+        CrossArgs ca;
+        ca.cams = ctx->d_cams;
+        ca.depth_ptrs = ctx->d_depth_ptrs;
+        ca.indexA = ctx->views[v].index;
+        ca.viewA = v;
+        ca.num_views = ctx->V;
+        ca.w = ctx->w;
+        ca.h = ctx->h;
+        ca.scale = ctx->params.image_scale;
+        ca.thresh = threshold;
+        ca.two_view = two_view;
+        cross_check_kernel<<<(unsigned)((n + 127) / 128), 128, 0, ctx->stream>>>(ca);
+        CKL();
+    }
+    return SR_OK;
+}
+
+int sr_synchronize(sr_ctx *ctx) {
+    if (!ctx) return SR_ERR_INVALID;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return SR_OK;
+}
+
+static int d2h(sr_ctx *ctx, void *dst, const void *src, size_t bytes) {
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return SR_OK;
+}
+
+int sr_get_depth_index(sr_ctx *ctx, int view, int32_t *out) {
+    int rc = check_view(ctx, view);
+    if (rc) return rc;
+    return d2h(ctx, out, ctx->views[view].index, (size_t)ctx->w * ctx->h * 4);
+}
+int sr_get_depth(sr_ctx *ctx, int view, double *out) {
+    int rc = check_view(ctx, view);
+    if (rc) return rc;
+    return d2h(ctx, out, ctx->views[view].depth, (size_t)ctx->w * ctx->h * 8);
+}
+int sr_get_best_cost(sr_ctx *ctx, int view, double *out) {
+    int rc = check_view(ctx, view);
+    if (rc) return rc;
+    return d2h(ctx, out, ctx->views[view].best, (size_t)ctx->w * ctx->h * 8);
+}
+int sr_get_cost_volume(sr_ctx *ctx, float *out, size_t out_elems) {
+    if (!ctx || !out) return SR_ERR_INVALID;
+    if (ctx->vol_elems == 0) return fail(ctx, SR_ERR_STATE, "no cost volume kept (set keep_cost_volume and run)");
+    if (out_elems < ctx->vol_elems) return fail(ctx, SR_ERR_INVALID, "output buffer too small");
+    return d2h(ctx, out, ctx->d_volume, ctx->vol_elems * 4);
+}
+int sr_set_depth(sr_ctx *ctx, int view, const double *depth) {
+    int rc = check_view(ctx, view);
+    if (rc) return rc;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaMemcpyAsync(ctx->views[view].depth, depth, (size_t)ctx->w * ctx->h * 8, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return SR_OK;
+}
+int sr_get_depth_image(sr_ctx *ctx, int view, int mvs, uint8_t *out) {
+    int rc = check_view(ctx, view);
+    if (rc) return rc;
+    if (!ctx->have_params) return fail(ctx, SR_ERR_STATE, "sr_set_params has not been called");
+    if (!mvs) return fail(ctx, SR_ERR_INVALID, "two-view HSV depth image is produced by the host class (QColor semantics)");
+    const size_t n = (size_t)ctx->w * ctx->h;
+    rc = ensure_scratch(ctx, n * 4);
+    if (rc) return rc;
+    depth_image_mvs_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(
+        ctx->views[view].depth, ctx->views[view].mask, (int)n, ctx->params.min_depth, ctx->params.max_depth,
+        (uchar4 *)ctx->d_scratch);
+    CKL();
+    return d2h(ctx, out, ctx->d_scratch, n * 4);
+}
+
+int sr_unproject_grid(sr_ctx *ctx, int view, double *out) {
+    int rc = check_view(ctx, view);
+    if (rc) return rc;
+    CK(cudaSetDevice(ctx->device));
+    const size_t n = (size_t)ctx->w * ctx->h;
+    const double scale = ctx->have_params ? ctx->params.image_scale : 1.0;
+    rays_kernel<<<(unsigned)((n + 127) / 128), 128, 0, ctx->stream>>>(ctx->cams[view], ctx->w, ctx->h, scale, ctx->d_rays);
+    CKL();
+    std::vector<double> soa(n * 6);
+    rc = d2h(ctx, soa.data(), ctx->d_rays, n * 6 * 8);
+    if (rc) return rc;
+    for (size_t i = 0; i < n; ++i)  // SoA (device layout) -> the (h,w,6) AoS the API documents
+        for (int k = 0; k < 6; ++k) out[i * 6 + k] = soa[k * n + i];
+    return SR_OK;
+}
+
+int sr_project_points(sr_ctx *ctx, int view, int n, const double *xyz, double *out_xy, int32_t *out_ok) {
+    int rc = check_view(ctx, view);
+    if (rc) return rc;
+    if (n <= 0) return SR_OK;
+    CK(cudaSetDevice(ctx->device));
+    rc = ensure_scratch(ctx, (size_t)n * (24 + 16 + 4));
+    if (rc) return rc;
+    double *dx = (double *)ctx->d_scratch;
+    double *dxy = dx + (size_t)3 * n;
+    int32_t *dok = (int32_t *)(dxy + (size_t)2 * n);
+    CK(cudaMemcpyAsync(dx, xyz, (size_t)n * 24, cudaMemcpyHostToDevice, ctx->stream));
+    project_points_kernel<<<(n + 127) / 128, 128, 0, ctx->stream>>>(ctx->cams[view], n, dx, dxy, dok);
+    CKL();
+    CK(cudaMemcpyAsync(out_xy, dxy, (size_t)n * 16, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(out_ok, dok, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return SR_OK;
+}
+
+int sr_compute_weights(sr_ctx *ctx, int view, int kind, int radius, int n, const int32_t *cx, const int32_t *cy,
+                       double *out) {
+    int rc = check_view(ctx, view);
+    if (rc) return rc;
+    if (n <= 0) return SR_OK;
+    if (radius < 1 || radius > 64 || kind < 0 || kind > 1) return fail(ctx, SR_ERR_INVALID, "bad radius/kind");
+    CK(cudaSetDevice(ctx->device));
+    const size_t wn = (size_t)(2 * radius + 1) * (2 * radius + 1);
+    rc = ensure_scratch(ctx, (size_t)n * 8 + (size_t)n * wn * 8);
+    if (rc) return rc;
+    int32_t *dcx = (int32_t *)ctx->d_scratch;
+    int32_t *dcy = dcx + n;
+    double *dout = (double *)(dcy + n);
+    CK(cudaMemcpyAsync(dcx, cx, (size_t)n * 4, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(dcy, cy, (size_t)n * 4, cudaMemcpyHostToDevice, ctx->stream));
+    weights_kernel<<<(n + 63) / 64, 64, 0, ctx->stream>>>(ctx->views[view].rgba, ctx->w, ctx->h, kind, radius, n, dcx,
+                                                          dcy, dout);
+    CKL();
+    return d2h(ctx, out, dout, (size_t)n * wn * 8);
+}
+
+// ---- multi-GPU ---------------------------------------------------------------------------
+int sr_comm_unique_id(void *out128) {
+    std::string err;
+    if (!load_nccl(err)) return fail(nullptr, SR_ERR_NCCL, err);
+    int r = g_nccl.GetUniqueId(out128);
+    if (r != 0) return fail(nullptr, SR_ERR_NCCL, g_nccl.GetErrorString(r));
+    return SR_OK;
+}
+
+int sr_comm_init(sr_ctx *ctx, const void *uid128, int rank, int nranks) {
+    if (!ctx || !uid128 || nranks < 1 || rank < 0 || rank >= nranks) return SR_ERR_INVALID;
+    std::string err;
+    if (!load_nccl(err)) return fail(ctx, SR_ERR_NCCL, err);
+    CK(cudaSetDevice(ctx->device));
+    Uid128 id;
+    memcpy(id.b, uid128, 128);
+    int r = g_nccl.CommInitRank(&ctx->comm, nranks, id, rank);
+    if (r != 0) return fail(ctx, SR_ERR_NCCL, g_nccl.GetErrorString(r));
+    ctx->rank = rank;
+    ctx->nranks = nranks;
+    return SR_OK;
+}
+
+// All-gather realised as one broadcast per view from its owner (views are whole buffers owned
+// by exactly one rank, so a grouped broadcast moves each byte once over NVLink).
+int sr_comm_allgather_views(sr_ctx *ctx, const int32_t *owner) {
+    if (!ctx || !owner) return SR_ERR_INVALID;
+    if (!ctx->comm) return fail(ctx, SR_ERR_STATE, "sr_comm_init has not been called");
+    CK(cudaSetDevice(ctx->device));
+    const size_t n = (size_t)ctx->w * ctx->h;
+    int r = g_nccl.GroupStart();
+    for (int v = 0; v < ctx->V && r == 0; ++v) {
+        ViewDev &d = ctx->views[v];
+        r = g_nccl.Broadcast(d.depth, d.depth, n * 8, NCCL_CHAR, owner[v], ctx->comm, ctx->stream);
+        if (r == 0) r = g_nccl.Broadcast(d.index, d.index, n * 4, NCCL_CHAR, owner[v], ctx->comm, ctx->stream);
+        if (r == 0) r = g_nccl.Broadcast(d.best, d.best, n * 8, NCCL_CHAR, owner[v], ctx->comm, ctx->stream);
+    }
+    int r2 = g_nccl.GroupEnd();
+    if (r == 0) r = r2;
+    if (r != 0) return fail(ctx, SR_ERR_NCCL, g_nccl.GetErrorString(r));
+    return SR_OK;
+}
+
+int sr_comm_allgather_rows(sr_ctx *ctx, int view, const int32_t *row_begin, const int32_t *row_end) {
+    int rc = check_view(ctx, view);
+    if (rc) return rc;
+    if (!ctx->comm) return fail(ctx, SR_ERR_STATE, "sr_comm_init has not been called");
+    CK(cudaSetDevice(ctx->device));
+    ViewDev &d = ctx->views[view];
+    int r = g_nccl.GroupStart();
+    for (int k = 0; k < ctx->nranks && r == 0; ++k) {
+        const size_t off = (size_t)row_begin[k] * ctx->w, cnt = (size_t)(row_end[k] - row_begin[k]) * ctx->w;
+        if (cnt == 0) continue;
+        r = g_nccl.Broadcast(d.depth + off, d.depth + off, cnt * 8, NCCL_CHAR, k, ctx->comm, ctx->stream);
+        if (r == 0) r = g_nccl.Broadcast(d.index + off, d.index + off, cnt * 4, NCCL_CHAR, k, ctx->comm, ctx->stream);
+        if (r == 0) r = g_nccl.Broadcast(d.best + off, d.best + off, cnt * 8, NCCL_CHAR, k, ctx->comm, ctx->stream);
+    }
+    int r2 = g_nccl.GroupEnd();
+    if (r == 0) r = r2;
+    if (r != 0) return fail(ctx, SR_ERR_NCCL, g_nccl.GetErrorString(r));
+    return SR_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,625 @@
+// sr_kernels.cuh — hand-written sm_100a kernels of the dense-matching hot path.
+//
+//   prep_view_kernel      RGBA8 + mask  -> FP64 gray planes (validity folded in as NaN)
+//   rays_kernel           Camera::unproject on every pixel centre        (camera.cpp:423-459)
+//   build_kernel          stage (1): per (pixel, depth label, neighbour view) refractive
+//                         reprojection -> packed integer tap volume      (twoviewstereo.cpp:308-316,
+//                                                                         multiviewstereo.cpp:768-775)
+//   match_kernel<R,G,C>   stages (2)+(3): support weights (Adaptive/Geodesic), weighted window
+//                         cost, WTA fused in the epilogue; streams the tap volume once
+//                                                                        (twoviewstereo.cpp:909-977,
+//                                                                         multiviewstereo.cpp:113-189,589-602)
+//   cross_check_*         crossCheck                                      (twoviewstereo.cpp:596-672,
+//                                                                         multiviewstereo.cpp:666-729)
+//
+// Data layout in HBM (all row-major, x fastest):
+//   gray planes  double [h][w]          per view, 3 variants (see prep_view_kernel)
+//   rays         double [6][h][w]       SoA: source xyz, direction xyz
+//   tap volume   int32  [nbr][D][rows][w]   (ty<<16 | tx&0xffff), TAP_NONE where the label
+//                                       cannot be evaluated; x fastest so one warp reads/writes
+//                                       128 contiguous bytes per label
+//   cost volume  float  [nbr][D][rows][w]   optional (keep_cost_volume)
+//   outputs      int32 index [h][w], double depth [h][w], double best [h][w]
+#pragma once
+#include "sr_geometry.cuh"
+
+namespace sr {
+
+constexpr int SR_MAX_NBRS = 8;
+constexpr int32_t TAP_NONE = INT32_MIN;
+constexpr int TAP_CLAMP = 20000;  // |coordinate| beyond this is outside any image for any window
+
+__device__ __forceinline__ double gray_of(uchar4 p) {
+    // RGBA::toGray(), util/vectorimage.hpp:60-62 (no FMA contraction: same roundings as the
+    // reference's plain expression)
+    return __dadd_rn(__dadd_rn(__dmul_rn(0.11, (double)p.x), __dmul_rn(0.59, (double)p.y)),
+                     __dmul_rn(0.3, (double)p.z));
+}
+__device__ __forceinline__ double qnan() { return __longlong_as_double(0x7ff8000000000000LL); }
+
+// gray_pix: valid wherever in bounds              (VectorImage::pixel, vectorimage.cpp:115-119)
+// gray_two: NaN unless mask WHITE and x+1<w,y+1<h (mask test twoviewstereo.cpp:920-924 +
+//                                                  VectorImage::sample validity, vectorimage.cpp:132)
+// gray_msk: NaN unless mask WHITE                 (cost_sad right taps, twoviewstereo.cpp:877,885)
+__global__ void prep_view_kernel(const uchar4 *__restrict__ rgba, const uint8_t *__restrict__ mask, int w, int h,
+                                 double *__restrict__ gray_pix, double *__restrict__ gray_two,
+                                 double *__restrict__ gray_msk) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= w * h) return;
+    const int x = i % w, y = i / w;
+    const double g = gray_of(rgba[i]);
+    const bool white = mask[i] == 255;
+    gray_pix[i] = g;
+    gray_msk[i] = white ? g : qnan();
+    gray_two[i] = (white && x + 1 < w && y + 1 < h) ? g : qnan();
+}
+
+__global__ void rays_kernel(sr_camera cam, int w, int h, double scale, double *__restrict__ rays) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= w * h) return;
+    const int x = i % w, y = i / w;
+    d3 s, d;
+    cam_unproject(cam, (x + 0.5) / scale, (y + 0.5) / scale, s, d);
+    const size_t n = (size_t)w * h;
+    rays[i] = s.x;
+    rays[n + i] = s.y;
+    rays[2 * n + i] = s.z;
+    rays[3 * n + i] = d.x;
+    rays[4 * n + i] = d.y;
+    rays[5 * n + i] = d.z;
+}
+
+__global__ void project_points_kernel(sr_camera cam, int n, const double *__restrict__ xyz, double *__restrict__ out_xy,
+                                      int32_t *__restrict__ out_ok) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double u = qnan(), v = qnan();
+    const bool ok = cam_project(cam, d3{xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2]}, u, v);
+    out_xy[2 * i] = ok ? u : qnan();
+    out_xy[2 * i + 1] = ok ? v : qnan();
+    out_ok[i] = ok;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Stage (1): tap-volume build.
+struct BuildArgs {
+    sr_camera nbr;               // target view
+    double prin[3], C[3];        // reference view principal direction and centre
+    const double *rays;          // [6][h][w] of the reference view
+    const double *depth_table;   // [D] depthFromLabel(d)
+    const uint8_t *ref_mask;     // [h][w]
+    const uint8_t *nbr_mask;     // [h][w]
+    int32_t *taps;               // [D][rows][w] for this neighbour
+    int w, h, row0, rows, D, d_chunk;
+    double scale;
+    int mvs;                     // 1: tap = trunc(p*scale), neighbour mask must be WHITE
+                                 // 0: tap = trunc(p*scale - 0.5)
+};
+
+__global__ void __launch_bounds__(128) build_kernel(const BuildArgs a) {
+    const int pid = blockIdx.x * blockDim.x + threadIdx.x;
+    if (pid >= a.rows * a.w) return;
+    const int x = pid % a.w, y = a.row0 + pid / a.w;
+    const size_t pix = (size_t)y * a.w + x;
+    if (a.ref_mask[pix] != 255) return;  // match_kernel never reads taps of masked-out pixels
+    const size_t n = (size_t)a.w * a.h;
+    const d3 src = {a.rays[pix], a.rays[n + pix], a.rays[2 * n + pix]};
+    const d3 dir = {a.rays[3 * n + pix], a.rays[4 * n + pix], a.rays[5 * n + pix]};
+    // pointFromDepth (multiviewstereo.cpp:740-750): Plane3d(normal, C + normal*depth) then
+    // intersect(); everything independent of the label is hoisted.
+    const d3 prin = ld3(a.prin);
+    const d3 nrm = normalized(prin);
+    const double nd = dot(nrm, dir);
+    const bool ray_ok = !(fabs(nd) < 1e-10);
+    const double inv_nd = 1.0 / nd;
+    const double nC = dot(nrm, ld3(a.C)), npn = dot(nrm, prin), nn = dot(nrm, nrm), ns = dot(nrm, src);
+    const RayInView rv = ray_in_view(a.nbr, src, dir);
+    const int d0 = blockIdx.y * a.d_chunk;
+    const int d1 = min(d0 + a.d_chunk, a.D);
+    const size_t plane = (size_t)a.rows * a.w;
+    double warm = -1.0;
+    for (int d = d0; d < d1; ++d) {
+        int32_t tap = TAP_NONE;
+        const double depth = a.depth_table[d];
+        const double dist = fma(depth, npn, nC);
+        const double t = (dist * nn - ns) * inv_nd;
+        if (ray_ok && !(t < 1e-10)) {
+            const d3 local = rv.Ls + t * rv.Ld;
+            double u, v;
+            if (cam_project_local(a.nbr, local, warm, u, v)) {
+                int tx, ty;
+                if (a.mvs) {
+                    tx = to_int_x86(u * a.scale);
+                    ty = to_int_x86(v * a.scale);
+                } else {
+                    tx = to_int_x86(u * a.scale - 0.5);
+                    ty = to_int_x86(v * a.scale - 0.5);
+                }
+                bool keep = true;
+                if (a.mvs) {  // multiviewstereo.cpp:787: only WHITE neighbour-mask pixels are candidates
+                    keep = tx >= 0 && ty >= 0 && tx < a.w && ty < a.h && a.nbr_mask[(size_t)ty * a.w + tx] == 255;
+                }
+                if (keep) {
+                    tx = max(-TAP_CLAMP, min(TAP_CLAMP, tx));
+                    ty = max(-TAP_CLAMP, min(TAP_CLAMP, ty));
+                    tap = (int32_t)(((uint32_t)(ty & 0xffff) << 16) | (uint32_t)(tx & 0xffff));
+                }
+            }
+        }
+        a.taps[(size_t)d * plane + pid] = tap;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Support weights.
+__device__ __forceinline__ bool load_rgb(const uchar4 *img, int w, int h, int x, int y, double &r, double &g, double &b) {
+    if (x < 0 || y < 0 || x >= w || y >= h) return false;
+    const uchar4 p = img[(size_t)y * w + x];
+    r = p.x;
+    g = p.y;
+    b = p.z;
+    return true;
+}
+
+// AdaptiveWeight::weight (stereo/adaptiveweight.cpp:62-79)
+__device__ __forceinline__ double adaptive_weight(const uchar4 *img, int w, int h, int cx, int cy, int row, int col,
+                                                  int radius) {
+    double r0, g0, b0, r1, g1, b1;
+    if (!load_rgb(img, w, h, cx + col, cy + row, r1, g1, b1)) return 0.0;
+    if (!load_rgb(img, w, h, cx, cy, r0, g0, b0)) return 0.0;  // NaN weight -> 0
+    r1 -= r0;
+    g1 -= g0;
+    b1 -= b0;
+    const double diff = sqrt(r1 * r1 + g1 * g1 + b1 * b1);
+    const double w1 = exp(-abs(row) / (1.0 * radius)) * exp(-abs(col) / (1.0 * radius));
+    const double w2 = exp(-diff / 10.0);
+    const double wt = w1 * w2;
+    return (wt == wt) ? wt : 0.0;
+}
+
+// GeodesicWeight::init_weights (stereo/geodesicweight.cpp:59-131): 3 x (forward + backward)
+// in-place raster sweeps over the (2r+1)^2 window.  Executed by ONE thread on its own grid `c`
+// (local or shared memory); the update order is the reference's, so results are identical.
+__device__ inline void geodesic_costs(const uchar4 *img, int w, int h, int cx, int cy, int radius, double *c) {
+    const int ws = 2 * radius + 1;
+    for (int i = 0; i < ws * ws; ++i) c[i] = 1000000.0;
+    c[radius * ws + radius] = 0.0;
+#pragma unroll 1
+    for (int iter = 0; iter < 3; ++iter) {
+#pragma unroll 1
+        for (int pass = 0; pass < 2; ++pass) {
+            // forward: neighbours (-1,-1),(0,-1),(1,-1),(-1,0); backward: (-1,1),(0,1),(1,1),(1,0)
+            const int sy = pass ? 1 : -1;
+#pragma unroll 1
+            for (int yi = 0; yi < ws; ++yi) {
+                const int y = pass ? radius - yi : yi - radius;
+#pragma unroll 1
+                for (int xi = 0; xi < ws; ++xi) {
+                    const int x = pass ? radius - xi : xi - radius;
+                    double r1, g1, b1;
+                    if (!load_rgb(img, w, h, cx + x, cy + y, r1, g1, b1)) continue;
+                    double wt = c[(y + radius) * ws + (x + radius)];
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const int dx = (k == 3) ? (pass ? 1 : -1) : (k - 1);
+                        const int dy = (k == 3) ? 0 : sy;
+                        const int nx = x + dx, ny = y + dy;
+                        if (nx > radius || ny > radius || nx < -radius || ny < -radius) continue;
+                        double r2, g2, b2;
+                        if (load_rgb(img, w, h, cx + nx, cy + ny, r2, g2, b2)) {
+                            r2 -= r1;
+                            g2 -= g1;
+                            b2 -= b1;
+                            const double diff = sqrt(r2 * r2 + g2 * g2 + b2 * b2);
+                            wt = fmin(wt, c[(ny + radius) * ws + (nx + radius)] + diff);
+                        }
+                    }
+                    c[(y + radius) * ws + (x + radius)] = wt;
+                }
+            }
+        }
+    }
+}
+
+// sr_compute_weights: one thread per requested window centre, output in global memory.
+__global__ void weights_kernel(const uchar4 *__restrict__ img, int w, int h, int kind, int radius, int n,
+                               const int32_t *__restrict__ cx, const int32_t *__restrict__ cy, double *out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int ws = 2 * radius + 1;
+    double *o = out + (size_t)i * ws * ws;
+    if (kind == SR_WEIGHT_ADAPTIVE) {
+        for (int row = -radius; row <= radius; ++row)
+            for (int col = -radius; col <= radius; ++col)
+                o[(row + radius) * ws + (col + radius)] = adaptive_weight(img, w, h, cx[i], cy[i], row, col, radius);
+    } else {
+        geodesic_costs(img, w, h, cx[i], cy[i], radius, o);
+        for (int k = 0; k < ws * ws; ++k) o[k] = exp(-o[k] / 50.0);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Stages (2)+(3): weights + windowed cost + WTA.
+struct MatchArgs {
+    const uchar4 *rgbaL;            // reference view colours (support weights)
+    const uint8_t *maskL;           // reference view mask
+    const double *grayL;            // reference taps  (gray_pix for C1, gray_two for C2/C3)
+    const double *grayR[SR_MAX_NBRS];  // neighbour taps (gray_pix C1, gray_two C2, gray_msk C3)
+    const int32_t *taps;            // [nbr][D][rows][w]
+    const double *depth_table;      // [D]
+    int32_t *out_index;             // [h][w]
+    double *out_depth;              // [h][w]
+    double *out_best;               // [h][w]
+    float *out_volume;              // [nbr][D][rows][w] or null
+    int w, h, row0, rows, D, num_nbrs;
+    int weight_kind, select_kind;
+    double second_best_factor, ncc_threshold;
+};
+
+template <int G>
+__device__ __forceinline__ double group_sum(double v, unsigned gmask) {
+#pragma unroll
+    for (int o = G / 2; o > 0; o >>= 1) v += __shfl_xor_sync(gmask, v, o);
+    return v;
+}
+template <int G>
+__device__ __forceinline__ int group_sum_i(int v, unsigned gmask) {
+#pragma unroll
+    for (int o = G / 2; o > 0; o >>= 1) v += __shfl_xor_sync(gmask, v, o);
+    return v;
+}
+
+// R: window radius; G: lanes cooperating on one reference pixel (taps are dealt round-robin to
+// the G lanes and live in registers); COST: SR_COST_*.
+template <int R, int G, int COST>
+__global__ void __launch_bounds__(128) match_kernel(const MatchArgs a) {
+    constexpr int WS = 2 * R + 1;
+    constexpr int WN = WS * WS;
+    constexpr int TPL = (WN + G - 1) / G;
+    constexpr bool NCC = (COST != SR_COST_SAD_TWOVIEW);
+    constexpr int PIX_PER_BLOCK = 128 / G;
+    extern __shared__ double smem[];  // geodesic grids for G > 1: [PIX_PER_BLOCK][WN]
+
+    const int lane = threadIdx.x & 31;
+    const int sub = threadIdx.x % G;
+    const unsigned gmask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << (lane & ~(G - 1)));
+    const int pid = blockIdx.x * PIX_PER_BLOCK + threadIdx.x / G;
+    if (pid >= a.rows * a.w) return;  // whole group leaves together
+    const int x = pid % a.w, y = a.row0 + pid / a.w;
+    const size_t pix = (size_t)y * a.w + x;
+    const int w = a.w, h = a.h;
+
+    if (a.maskL[pix] != 255) {  // twoviewstereo.cpp:269-271 (NaN) / multiviewstereo.cpp:559,565 (INF)
+        if (sub == 0) {
+            a.out_index[pix] = SR_INDEX_MASKED;
+            a.out_depth[pix] = (a.select_kind == SR_SELECT_MVS) ? __longlong_as_double(0x7ff0000000000000LL) : qnan();
+            a.out_best[pix] = qnan();
+        }
+        return;
+    }
+
+    // ---- support weights -> registers -------------------------------------------------------
+    double wt[TPL];
+    if (a.weight_kind == SR_WEIGHT_ADAPTIVE) {
+#pragma unroll
+        for (int i = 0; i < TPL; ++i) {
+            const int k = sub + G * i;
+            wt[i] = (k < WN) ? adaptive_weight(a.rgbaL, w, h, x, y, k / WS - R, k % WS - R, R) : 0.0;
+        }
+    } else {
+        if (G == 1) {
+            double c[WN];
+            geodesic_costs(a.rgbaL, w, h, x, y, R, c);
+#pragma unroll
+            for (int i = 0; i < TPL; ++i) wt[i] = exp(-c[i] / 50.0);
+        } else {
+            double *c = smem + (size_t)(threadIdx.x / G) * WN;
+            if (sub == 0) geodesic_costs(a.rgbaL, w, h, x, y, R, c);
+            __syncwarp(gmask);
+#pragma unroll
+            for (int i = 0; i < TPL; ++i) {
+                const int k = sub + G * i;
+                wt[i] = (k < WN) ? exp(-c[k] / 50.0) : 0.0;
+            }
+        }
+    }
+
+    // ---- reference-window invariants (hoisted out of the label sweep) -----------------------
+    // c1[i]: NCC: w*(w*gl - meanL);  SAD: gl.   Inactive taps get wt = 0, c1 = 0.
+    double c1[TPL];
+    double totW = 0.0, SL = 0.0;
+    int nact = 0;
+#pragma unroll
+    for (int i = 0; i < TPL; ++i) {
+        const int k = sub + G * i;
+        const int row = k / WS - R, col = k % WS - R;
+        const int xl = x + col, yl = y + row;
+        double gl = qnan();
+        if (k < WN && xl >= 0 && yl >= 0 && xl < w && yl < h) gl = a.grayL[(size_t)yl * w + xl];
+        const bool active = (gl == gl) && (wt[i] > 1e-10);
+        if (!active) {
+            wt[i] = 0.0;
+            gl = 0.0;
+        } else {
+            totW += wt[i];
+            SL += wt[i] * gl;
+            ++nact;
+        }
+        c1[i] = gl;
+    }
+    totW = group_sum<G>(totW, gmask);
+    SL = group_sum<G>(SL, gmask);
+    nact = group_sum_i<G>(nact, gmask);
+    const double meanL = SL / totW;
+    double s2 = 0.0, SD = 0.0;
+    if (NCC) {
+#pragma unroll
+        for (int i = 0; i < TPL; ++i) {
+            const double dl = (wt[i] > 0.0) ? wt[i] * c1[i] - meanL : 0.0;
+            s2 += dl * dl;
+            SD += dl;
+            c1[i] = wt[i] * dl;
+        }
+        s2 = group_sum<G>(s2, gmask);
+        SD = group_sum<G>(SD, gmask);
+    }
+    const bool degenerate = (COST == SR_COST_SAD_TWOVIEW) ? (nact <= 4 || totW <= 1e-10) : (totW < 1e-10);
+
+    // ---- label sweep -------------------------------------------------------------------------
+    const double INF = __longlong_as_double(0x7ff0000000000000LL);
+    double minCost = INF, secondBest = INF;  // two-view selection
+    double bestC = 0.0, bestD = -1.0;        // MVS selection
+    int bestIdx = SR_INDEX_NONE;
+    const size_t plane = (size_t)a.rows * w;
+
+#pragma unroll 1
+    for (int j = 0; j < a.num_nbrs; ++j) {
+        const double *__restrict__ gR = a.grayR[j];
+        const int32_t *__restrict__ taps = a.taps + (size_t)j * a.D * plane + pid;
+        float *vol = a.out_volume ? a.out_volume + (size_t)j * a.D * plane + pid : nullptr;
+#pragma unroll 1
+        for (int d = 0; d < a.D; ++d) {
+            const int32_t tap = taps[(size_t)d * plane];
+            double cost = qnan();
+            if (tap != TAP_NONE) {
+                const int tx = (int)(short)(tap & 0xffff), ty = (int)(short)((uint32_t)tap >> 16);
+                bool slow = !(tx >= R && ty >= R && tx < w - R && ty < h - R);
+                if (!slow) {
+                    // fast path: whole neighbour window in bounds; one streaming pass.
+                    const double *base = gR + (size_t)ty * w + tx;
+                    if (NCC) {
+                        double S1 = 0.0, S2 = 0.0, S3 = 0.0;
+#pragma unroll
+                        for (int i = 0; i < TPL; ++i) {
+                            const int k = sub + G * i;
+                            if (k < WN) {
+                                const double gr = base[(k / WS - R) * w + (k % WS - R)];
+                                const double p = wt[i] * gr;
+                                S1 += p;
+                                S2 = fma(p, p, S2);
+                                S3 = fma(c1[i], gr, S3);
+                            }
+                        }
+                        S1 = group_sum<G>(S1, gmask);
+                        S2 = group_sum<G>(S2, gmask);
+                        S3 = group_sum<G>(S3, gmask);
+                        if (S1 != S1 || S3 != S3) {
+                            slow = true;  // an invalid (NaN) neighbour tap: exact tap filtering needed
+                        } else if (degenerate) {
+                            cost = (COST == SR_COST_NCC_MVS) ? 0.0 : 1000.0;
+                        } else {
+                            const double meanR = S1 / totW;
+                            const double s1 = S3 - meanR * SD;
+                            const double s3 = S2 - 2.0 * meanR * S1 + nact * meanR * meanR;
+                            if (COST == SR_COST_NCC_MVS) {
+                                cost = (s2 * s3 < 1e-10) ? 0.0 : s1 / sqrt(s2 * s3);
+                            } else {
+                                const double v = 255.0 * (1.0 - fabs(s1) / sqrt(s2 * s3));
+                                cost = (v < 120.0) ? v : 120.0;
+                            }
+                        }
+                    } else {
+                        double S = 0.0;
+#pragma unroll
+                        for (int i = 0; i < TPL; ++i) {
+                            const int k = sub + G * i;
+                            if (k < WN) {
+                                const double gr = base[(k / WS - R) * w + (k % WS - R)];
+                                S = fma(wt[i], fmin(120.0, fabs(c1[i] - gr)), S);
+                            }
+                        }
+                        S = group_sum<G>(S, gmask);
+                        if (S != S) slow = true;
+                        else cost = degenerate ? 1000.0 : S / totW;
+                    }
+                }
+                if (slow) {
+                    // exact tap filtering as in the reference: a tap counts only if both pixels are
+                    // valid and the weight exceeds 1e-10.
+                    double mL = 0.0, mR = 0.0, tw = 0.0;
+                    int cnt = 0;
+#pragma unroll
+                    for (int i = 0; i < TPL; ++i) {
+                        const int k = sub + G * i;
+                        const int row = k / WS - R, col = k % WS - R;
+                        const int xr = tx + col, yr = ty + row, xl = x + col, yl = y + row;
+                        if (k < WN && wt[i] > 0.0 && xr >= 0 && yr >= 0 && xr < w && yr < h) {
+                            const double gr = gR[(size_t)yr * w + xr];
+                            const double gl = a.grayL[(size_t)yl * w + xl];
+                            if (gr == gr) {
+                                if (NCC) {
+                                    mL += wt[i] * gl;
+                                    mR += wt[i] * gr;
+                                } else {
+                                    mL += wt[i] * fmin(120.0, fabs(gl - gr));
+                                }
+                                tw += wt[i];
+                                ++cnt;
+                            }
+                        }
+                    }
+                    mL = group_sum<G>(mL, gmask);
+                    mR = group_sum<G>(mR, gmask);
+                    tw = group_sum<G>(tw, gmask);
+                    cnt = group_sum_i<G>(cnt, gmask);
+                    if (!NCC) {
+                        cost = (cnt <= 4 || tw <= 1e-10) ? 1000.0 : mL / tw;
+                    } else if (tw < 1e-10) {
+                        cost = (COST == SR_COST_NCC_MVS) ? 0.0 : 1000.0;
+                    } else {
+                        mL /= tw;
+                        mR /= tw;
+                        double q1 = 0.0, q2 = 0.0, q3 = 0.0;
+#pragma unroll
+                        for (int i = 0; i < TPL; ++i) {
+                            const int k = sub + G * i;
+                            const int row = k / WS - R, col = k % WS - R;
+                            const int xr = tx + col, yr = ty + row, xl = x + col, yl = y + row;
+                            if (k < WN && wt[i] > 0.0 && xr >= 0 && yr >= 0 && xr < w && yr < h) {
+                                const double gr = gR[(size_t)yr * w + xr];
+                                const double gl = a.grayL[(size_t)yl * w + xl];
+                                if (gr == gr) {
+                                    const double pl = wt[i] * gl - mL, pr = wt[i] * gr - mR;
+                                    q1 += pl * pr;
+                                    q2 += pl * pl;
+                                    q3 += pr * pr;
+                                }
+                            }
+                        }
+                        q1 = group_sum<G>(q1, gmask);
+                        q2 = group_sum<G>(q2, gmask);
+                        q3 = group_sum<G>(q3, gmask);
+                        if (COST == SR_COST_NCC_MVS) {
+                            cost = (q2 * q3 < 1e-10) ? 0.0 : q1 / sqrt(q2 * q3);
+                        } else {
+                            const double v = 255.0 * (1.0 - fabs(q1) / sqrt(q2 * q3));
+                            cost = (v < 120.0) ? v : 120.0;
+                        }
+                    }
+                }
+                // ---- stage (3): winner-take-all, fused ----
+                if (a.select_kind == SR_SELECT_MVS) {  // multiviewstereo.cpp:589-602,654-660
+                    if (cost > a.ncc_threshold) {
+                        const double depth = a.depth_table[d];
+                        if (bestIdx == SR_INDEX_NONE || cost > bestC || (cost == bestC && depth > bestD)) {
+                            bestC = cost;
+                            bestD = depth;
+                            bestIdx = d;
+                        }
+                    }
+                } else {  // twoviewstereo.cpp:320-325
+                    if (cost + 1e-10 < minCost) {
+                        secondBest = minCost;
+                        minCost = cost;
+                        bestIdx = d;
+                    }
+                }
+            }
+            if (vol && sub == 0) vol[(size_t)d * plane] = (float)cost;
+        }
+    }
+
+    if (sub == 0) {
+        if (a.select_kind == SR_SELECT_MVS) {
+            a.out_index[pix] = bestIdx;
+            a.out_depth[pix] = bestD;
+            a.out_best[pix] = bestC;
+        } else {
+            double depth = (bestIdx >= 0) ? a.depth_table[bestIdx] : qnan();
+            if (a.second_best_factor > 0.0 && minCost > a.second_best_factor * secondBest) {  // :304-305
+                depth = INF;
+                bestIdx = SR_INDEX_REJECTED;
+            }
+            a.out_index[pix] = bestIdx;
+            a.out_depth[pix] = depth;
+            a.out_best[pix] = minCost;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// crossCheck.  One launch per checked view; the launch order on the stream reproduces the
+// reference's in-place, view-by-view semantics.
+struct CrossArgs {
+    const sr_camera *cams;       // device array of all views' cameras
+    double *const *depth_ptrs;   // device array of all views' depth maps
+    int32_t *indexA;
+    int viewA, num_views;
+    int w, h;
+    double scale, thresh;
+    int two_view;                // 1: failing -> +INF (must pass against the other view);
+                                 // 0: any other view may confirm, failing -> NaN
+};
+
+__device__ __forceinline__ bool point_from_depth(d3 src, d3 dir, d3 normal, d3 C, double depth, d3 &p) {
+    const d3 nrm = normalized(normal);
+    const d3 x0 = C + depth * normal;
+    return ray_plane(src, dir, nrm, dot(nrm, x0), p);
+}
+
+__global__ void __launch_bounds__(128) cross_check_kernel(const CrossArgs a) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= a.w * a.h) return;
+    double *depthA = a.depth_ptrs[a.viewA];
+    const double depth = depthA[i];
+    if (!isfinite(depth)) return;
+    const int x = i % a.w, y = i / a.w;
+    const sr_camera &A = a.cams[a.viewA];
+    d3 src, dir, p1;
+    cam_unproject(A, (x + 0.5) / a.scale, (y + 0.5) / a.scale, src, dir);
+    if (!point_from_depth(src, dir, ld3(A.prin_dir), ld3(A.C), depth, p1)) return;
+    const double INF = __longlong_as_double(0x7ff0000000000000LL);
+    bool found = false, fail = false;
+    for (int b = 0; b < a.num_views && !found; ++b) {
+        if (b == a.viewA) continue;
+        const sr_camera &B = a.cams[b];
+        double x2, y2;
+        fail = true;
+        if (cam_project(B, p1, x2, y2)) {
+            x2 *= a.scale;
+            y2 *= a.scale;
+            if (x2 >= 0 && y2 >= 0 && x2 < a.w && y2 < a.h) {
+                const double od = a.depth_ptrs[b][(size_t)((int)y2) * a.w + (int)x2];
+                if (isfinite(od)) {
+                    d3 s2, d2, p2;
+                    cam_unproject(B, (x2 + 0.5) / a.scale, (y2 + 0.5) / a.scale, s2, d2);
+                    if (point_from_depth(s2, d2, ld3(B.prin_dir), ld3(B.C), od, p2)) {
+                        const d3 df = p1 - p2;
+                        const double nrm = sqrt(dot(df, df));
+                        if (a.two_view) {
+                            fail = (!isfinite(nrm) || nrm > a.thresh);
+                        } else if (isfinite(nrm) && nrm < a.thresh) {
+                            found = true;
+                        }
+                    }
+                }
+            }
+        }
+    }
+    if (a.two_view) {
+        if (fail) {
+            depthA[i] = INF;
+            a.indexA[i] = SR_INDEX_REJECTED;
+        }
+    } else if (!found) {
+        depthA[i] = qnan();
+        a.indexA[i] = SR_INDEX_NONE;
+    }
+}
+
+// colorFromDepth of MultiViewStereo (multiviewstereo.cpp:257-278) + the WHITE fill for masked
+// pixels (:381-395) -> RGBA8.
+__global__ void depth_image_mvs_kernel(const double *__restrict__ depth, const uint8_t *__restrict__ mask, int n,
+                                       double min_depth, double max_depth, uchar4 *__restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    unsigned char g = 255;
+    const double d = depth[i];
+    if (mask[i] == 255 && isfinite(d) && !(d + 1e-5 < min_depth)) {
+        const double t = fmin(1.0, fmax(0.0, (d - min_depth) / (max_depth - min_depth)));
+        g = (unsigned char)(int)(255 * t);
+    }
+    out[i] = make_uchar4(g, g, g, 255);
+}
+
+}  // namespace sr

@@ -1,0 +1,57 @@
+// sr_match_dispatch.cuh — (radius, cost) -> match_kernel<R,G,COST> instantiation.
+// G (lanes cooperating on one pixel) is chosen so that the per-lane tap share (two FP64
+// registers per tap) stays within the register file: ceil((2R+1)^2 / G) <= 35.
+#pragma once
+#include "sr_kernels.cuh"
+
+namespace sr {
+
+template <int R> struct LanesFor { static constexpr int G = (R <= 2) ? 1 : (R == 3) ? 2 : (R <= 5) ? 4 : (R <= 7) ? 8 : (R <= 10) ? 16 : 32; };
+
+inline bool match_supported(int r) { return (r >= 1 && r <= 8) || r == 10 || r == 12 || r == 16; }
+
+template <int R, int COST>
+cudaError_t launch_match_rc(const MatchArgs &a, cudaStream_t st) {
+    constexpr int G = LanesFor<R>::G;
+    constexpr int WN = (2 * R + 1) * (2 * R + 1);
+    constexpr int PPB = 128 / G;
+    const size_t npix = (size_t)a.rows * a.w;
+    const unsigned grid = (unsigned)((npix + PPB - 1) / PPB);
+    const size_t smem = (G > 1) ? (size_t)PPB * WN * sizeof(double) : 0;
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(match_kernel<R, G, COST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+    }
+    match_kernel<R, G, COST><<<grid, 128, smem, st>>>(a);
+    return cudaGetLastError();
+}
+
+template <int R>
+cudaError_t launch_match_r(int cost, const MatchArgs &a, cudaStream_t st) {
+    switch (cost) {
+        case SR_COST_NCC_TWOVIEW: return launch_match_rc<R, SR_COST_NCC_TWOVIEW>(a, st);
+        case SR_COST_NCC_MVS: return launch_match_rc<R, SR_COST_NCC_MVS>(a, st);
+        default: return launch_match_rc<R, SR_COST_SAD_TWOVIEW>(a, st);
+    }
+}
+
+inline cudaError_t launch_match(int radius, int cost, const MatchArgs &a, cudaStream_t st) {
+    switch (radius) {
+        case 1: return launch_match_r<1>(cost, a, st);
+        case 2: return launch_match_r<2>(cost, a, st);
+        case 3: return launch_match_r<3>(cost, a, st);
+        case 4: return launch_match_r<4>(cost, a, st);
+        case 5: return launch_match_r<5>(cost, a, st);
+#ifndef SR_FEW_RADII
+        case 6: return launch_match_r<6>(cost, a, st);
+        case 7: return launch_match_r<7>(cost, a, st);
+        case 8: return launch_match_r<8>(cost, a, st);
+        case 10: return launch_match_r<10>(cost, a, st);
+        case 12: return launch_match_r<12>(cost, a, st);
+#endif
+        case 16: return launch_match_r<16>(cost, a, st);
+        default: return cudaErrorInvalidValue;
+    }
+}
+
+}  // namespace sr
