@@ -181,7 +181,8 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     ctx = capi.Context(local_rank)
-    stream = torch.cuda.current_stream()
+    stream = torch.cuda.Stream()  # an explicit stream: the library launches on it, the events time it
+    torch.cuda.set_stream(stream)
     ctx.set_stream(stream.cuda_stream)
 
     # synthetic, photo-consistent inputs rendered through the GPU's own unproject

@@ -372,6 +372,7 @@ int sr_run_view(sr_ctx *ctx, int ref, const int32_t *nbrs, int nn) {
             ctx->vol_cap = need;
         }
         ctx->vol_elems = need / 4;
+        CK(cudaMemsetAsync(ctx->d_volume, 0xff, need, st));  // NaN: labels / pixels never evaluated
     }
 
     for (int b0 = r0; b0 < r1; b0 += band) {
