@@ -23,7 +23,7 @@ std::string g_create_error;
 struct ViewDev {
     uchar4 *rgba = nullptr;
     uint8_t *mask = nullptr;
-    double *gray_pix = nullptr, *gray_two = nullptr, *gray_msk = nullptr;
+    double *gray_pix = nullptr, *gray_two = nullptr, *gray_msk = nullptr, *edges = nullptr;
     int32_t *index = nullptr;
     double *depth = nullptr, *best = nullptr;
 };
@@ -94,6 +94,8 @@ struct sr_ctx {
     double *d_rays = nullptr;
     int32_t *d_taps = nullptr;
     size_t taps_cap = 0;
+    double *d_weights = nullptr;  // [WN][band pixels]
+    size_t weights_cap = 0;
     float *d_volume = nullptr;
     size_t vol_cap = 0, vol_elems = 0;
     void *d_scratch = nullptr;
@@ -141,6 +143,7 @@ void free_views(sr_ctx *c) {
         dfree(v.gray_pix);
         dfree(v.gray_two);
         dfree(v.gray_msk);
+        dfree(v.edges);
         dfree(v.index);
         dfree(v.depth);
         dfree(v.best);
@@ -210,6 +213,7 @@ void sr_ctx_destroy(sr_ctx *c) {
     free_views(c);
     dfree(c->d_depth_table);
     dfree(c->d_taps);
+    dfree(c->d_weights);
     dfree(c->d_volume);
     if (c->d_scratch) cudaFree(c->d_scratch);
     cudaStreamDestroy(c->own_stream);
@@ -269,6 +273,7 @@ int sr_set_views(sr_ctx *ctx, int V, const sr_camera *cams, const uint8_t *const
             CK(cudaMalloc(&v.gray_pix, n * 8));
             CK(cudaMalloc(&v.gray_two, n * 8));
             CK(cudaMalloc(&v.gray_msk, n * 8));
+            CK(cudaMalloc(&v.edges, n * 8 * 4));
             CK(cudaMalloc(&v.index, n * 4));
             CK(cudaMalloc(&v.depth, n * 8));
             CK(cudaMalloc(&v.best, n * 8));
@@ -293,7 +298,7 @@ int sr_set_views(sr_ctx *ctx, int V, const sr_camera *cams, const uint8_t *const
         if (mask8 && mask8[i]) CK(cudaMemcpyAsync(v.mask, mask8[i], n, cudaMemcpyHostToDevice, ctx->stream));
         else CK(cudaMemsetAsync(v.mask, 255, n, ctx->stream));
         prep_view_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(v.rgba, v.mask, w, h, v.gray_pix,
-                                                                             v.gray_two, v.gray_msk);
+                                                                             v.gray_two, v.gray_msk, v.edges);
         CKL();
         // results start as "not computed": NaN depth (twoviewstereo.cpp:118-119), index NONE
         CK(cudaMemsetAsync(v.depth, 0xff, n * 8, ctx->stream));
@@ -350,11 +355,22 @@ int sr_run_view(sr_ctx *ctx, int ref, const int32_t *nbrs, int nn) {
     rays_kernel<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(ctx->cams[ref], w, h, P.image_scale, ctx->d_rays);
     CKL();
 
-    // Row bands bound the tap volume (nn*D*rows*w*4 bytes); a kept cost volume needs one band.
+    // Row bands bound the scratch (tap volume nn*D*rows*w*4 bytes + support weights
+    // WN*rows*w*8 bytes); a kept cost volume needs one band.
+    const size_t wn = (size_t)(2 * P.radius + 1) * (2 * P.radius + 1);
     const size_t per_row = (size_t)nn * D * w * 4;
-    int band = (int)std::min<size_t>((size_t)(r1 - r0), std::max<size_t>(1, ctx->tap_budget / per_row));
+    const size_t per_row_w = wn * w * 8;
+    int band = (int)std::min<size_t>((size_t)(r1 - r0), std::max<size_t>(1, ctx->tap_budget / (per_row + per_row_w)));
     if (P.keep_cost_volume) band = r1 - r0;
     const size_t need = per_row * band;
+    const size_t need_w = per_row_w * band;
+    if (need_w > ctx->weights_cap) {
+        CK(cudaStreamSynchronize(st));
+        dfree(ctx->d_weights);
+        ctx->weights_cap = 0;
+        CK(cudaMalloc(&ctx->d_weights, need_w));
+        ctx->weights_cap = need_w;
+    }
     if (need > ctx->taps_cap) {
         CK(cudaStreamSynchronize(st));
         dfree(ctx->d_taps);
@@ -408,9 +424,27 @@ int sr_run_view(sr_ctx *ctx, int ref, const int32_t *nbrs, int nn) {
             CKL();
         }
         if (ctx->profiling) CK(cudaEventRecord(ev[1], st));
+        {
+            WeightArgs wa;
+            memset(&wa, 0, sizeof(wa));
+            wa.rgba = A.rgba;
+            wa.mask = A.mask;
+            wa.edges = A.edges;
+            wa.W = ctx->d_weights;
+            wa.w = w;
+            wa.h = h;
+            wa.row0 = b0;
+            wa.rows = rows;
+            wa.radius = P.radius;
+            if (P.weight_kind == SR_WEIGHT_ADAPTIVE)
+                weights_adaptive_kernel<<<gx, 128, (P.radius + 1) * sizeof(double), st>>>(wa);
+            else
+                weights_geodesic_kernel<<<gx, 128, 0, st>>>(wa);
+            CKL();
+        }
         MatchArgs ma;
         memset(&ma, 0, sizeof(ma));
-        ma.rgbaL = A.rgba;
+        ma.W = ctx->d_weights;
         ma.maskL = A.mask;
         ma.grayL = (P.cost_kind == SR_COST_NCC_MVS) ? A.gray_pix : A.gray_two;
         for (int j = 0; j < nn; ++j) {
@@ -430,7 +464,6 @@ int sr_run_view(sr_ctx *ctx, int ref, const int32_t *nbrs, int nn) {
         ma.rows = rows;
         ma.D = D;
         ma.num_nbrs = nn;
-        ma.weight_kind = P.weight_kind;
         ma.select_kind = P.select_kind;
         ma.second_best_factor = P.second_best_factor;
         ma.ncc_threshold = P.ncc_threshold;
@@ -638,13 +671,32 @@ int sr_compute_weights(sr_ctx *ctx, int view, int kind, int radius, int n, const
     if (rc) return rc;
     int32_t *dcx = (int32_t *)ctx->d_scratch;
     int32_t *dcy = dcx + n;
-    double *dout = (double *)(dcy + n);
+    double *dW = (double *)(dcy + n);
     CK(cudaMemcpyAsync(dcx, cx, (size_t)n * 4, cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemcpyAsync(dcy, cy, (size_t)n * 4, cudaMemcpyHostToDevice, ctx->stream));
-    weights_kernel<<<(n + 63) / 64, 64, 0, ctx->stream>>>(ctx->views[view].rgba, ctx->w, ctx->h, kind, radius, n, dcx,
-                                                          dcy, dout);
+    WeightArgs wa;
+    memset(&wa, 0, sizeof(wa));
+    wa.rgba = ctx->views[view].rgba;
+    wa.mask = ctx->views[view].mask;
+    wa.edges = ctx->views[view].edges;
+    wa.W = dW;
+    wa.w = ctx->w;
+    wa.h = ctx->h;
+    wa.radius = radius;
+    wa.list_x = dcx;
+    wa.list_y = dcy;
+    wa.list_n = n;
+    if (kind == SR_WEIGHT_ADAPTIVE)
+        weights_adaptive_kernel<<<(n + 127) / 128, 128, (radius + 1) * sizeof(double), ctx->stream>>>(wa);
+    else
+        weights_geodesic_kernel<<<(n + 127) / 128, 128, 0, ctx->stream>>>(wa);
     CKL();
-    return d2h(ctx, out, dout, (size_t)n * wn * 8);
+    std::vector<double> tmp((size_t)n * wn);
+    rc = d2h(ctx, tmp.data(), dW, (size_t)n * wn * 8);
+    if (rc) return rc;
+    for (int i = 0; i < n; ++i)  // device layout [tap][centre] -> the [centre][row][col] the API documents
+        for (size_t k = 0; k < wn; ++k) out[(size_t)i * wn + k] = tmp[k * n + i];
+    return SR_OK;
 }
 
 // ---- multi-GPU ---------------------------------------------------------------------------

@@ -3,8 +3,8 @@
 // What each function computes follows the reference (citations are into the reference tree);
 // how it is computed is organised for the GPU: everything that is invariant per pixel or per
 // (pixel, neighbour view) is hoisted, and the refractive projection replaces the reference's
-// quartic eigen-solve (project/camera.cpp:68-138, GSL) by a safeguarded Newton iteration on the
-// un-squared Snell equation, which has exactly one root on [0, r].
+// quartic eigen-solve (project/camera.cpp:68-138, GSL) by Newton on the un-squared Snell
+// equation, which has exactly one root on [0, r].
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -83,29 +83,74 @@ __device__ inline void cam_unproject(const sr_camera &c, double px, double py, d
     src = mul3(c.Rinv, s - ld3(c.t));
 }
 
-// Unique root in [0,r] of g(x) = x/sqrt(x^2+d^2) - n (r-x)/sqrt((r-x)^2+h^2).
-// `guess` is a starting ratio x/r in (0,1) (warm start from the previous depth label) or < 0 for
-// the paraxial start.  Safeguarded Newton in FP64; converges to ~1 ulp of the root.
-__device__ __forceinline__ double snell_root(double r, double d, double h, double n, double guess) {
+// Unique root in [0,r] of g(x) = x/sqrt(x^2+d^2) - n (r-x)/sqrt((r-x)^2+h^2)   (Snell, un-squared).
+// Robust FP64 solver: Newton with a bracketing safeguard.  `guess` is a starting ratio x/r or < 0
+// for the paraxial start.  Convergence is tested on the Newton step BEFORE the safeguard (a step
+// that rounds to zero must terminate, not bisect), and because convergence is quadratic a step
+// below 2e-9*r already leaves an error below 1e-17*r once it is applied.
+__device__ __noinline__ double snell_root_robust(double r, double d, double h, double n, double guess) {
     const double dd = d * d, hh = h * h;
     double lo = 0.0, hi = r;
     double x = (guess > 0.0) ? guess * r : n * fabs(d) * r / (fabs(h) + n * fabs(d) + 1e-300);
-    if (!(x > lo && x < hi)) x = 0.5 * r;
+    if (!(x >= lo && x <= hi)) x = 0.5 * r;
 #pragma unroll 1
-    for (int it = 0; it < 100; ++it) {
+    for (int it = 0; it < 80; ++it) {
         const double rx = r - x;
         const double ia = rsqrt(x * x + dd), ib = rsqrt(rx * rx + hh);
         const double g = x * ia - n * rx * ib;
         if (g == 0.0) break;
         if (g < 0.0) lo = x; else hi = x;
         const double gp = dd * ia * ia * ia + n * hh * ib * ib * ib;
-        double xn = x - g / gp;
-        if (!(xn > lo && xn < hi)) xn = 0.5 * (lo + hi);
-        const double dx = fabs(xn - x);
+        const double step = g / gp;
+        double xn = x - step;
+        if (fabs(step) <= 2e-9 * r) {
+            x = xn;
+            break;
+        }
+        if (!(xn >= lo && xn <= hi)) xn = 0.5 * (lo + hi);
         x = xn;
-        if (dx <= 4e-16 * r || hi - lo <= 4e-16 * r) break;
+        if (hi - lo <= 4e-16 * r) break;
     }
     return x;
+}
+
+// Fast path of the same solve, the one the build kernel runs per (pixel, label, view):
+// FP32 Newton from a warm start (the ratio x/r moves smoothly along the depth axis; w0,w1 hold
+// the ratios of the two previous labels and are linearly extrapolated), a fixed number of
+// iterations so the warp does not diverge, then ONE Newton step in FP64: with an FP32-converged
+// start (|e0| ~ 1e-6) the quadratic error after the polish is ~|g''/2g'| e0^2 < 1e-14, i.e.
+// ~1e-12 px.  If the polish step is not tiny the robust FP64 loop takes over.
+__device__ __forceinline__ double snell_root_fast(double r, double d, double h, double n, float &w0, float &w1) {
+    const float rf = (float)r, hf = (float)h, df = (float)d, nf = (float)n;
+    const float ddf = df * df, hhf = hf * hf;
+    const bool warm = w1 > 0.0f;
+    float x;
+    if (warm) x = (w0 > 0.0f ? fmaf(2.0f, w1, -w0) : w1) * rf;
+    else x = nf * fabsf(df) * rf / (fabsf(hf) + nf * fabsf(df));
+    x = fminf(fmaxf(x, 0.0f), rf);
+    const int iters = warm ? 2 : 5;
+#pragma unroll 1
+    for (int it = 0; it < iters; ++it) {
+        const float rx = rf - x;
+        const float ia = rsqrtf(fmaf(x, x, ddf)), ib = rsqrtf(fmaf(rx, rx, hhf));
+        const float g = x * ia - nf * rx * ib;
+        const float gp = ddf * ia * ia * ia + nf * hhf * ib * ib * ib;
+        x = fminf(fmaxf(x - __fdividef(g, gp), 0.0f), rf);
+    }
+    double X = (double)x;
+    {
+        const double dd = d * d, hh = h * h;
+        const double rx = r - X;
+        const double ia = rsqrt(fma(X, X, dd)), ib = rsqrt(fma(rx, rx, hh));
+        const double g = X * ia - n * rx * ib;
+        const double gp = dd * ia * ia * ia + n * hh * ib * ib * ib;
+        const double step = g / gp;
+        X -= step;
+        if (!(fabs(step) <= 2e-5 * r) || !(X >= 0.0 && X <= r)) X = snell_root_robust(r, d, h, n, -1.0);
+    }
+    w0 = w1;
+    w1 = __fdividef(x, rf);
+    return X;
 }
 
 // Per (reference pixel, target view) invariants of Camera::project applied to points
@@ -121,30 +166,37 @@ __device__ __forceinline__ RayInView ray_in_view(const sr_camera &c, d3 src, d3 
 }
 
 // Camera::project (project/camera.cpp:380-419) of the camera-local point `local`.
-// `warm` carries x/r between consecutive depth labels (set < 0 before the first call).
-__device__ __forceinline__ bool cam_project_local(const sr_camera &c, d3 local, double &warm, double &u, double &v) {
+// w0,w1: warm-start ratios of the two previous depth labels (set < 0 before the first call).
+// Divisions by per-camera constants become multiplications with reciprocals computed once per
+// thread (<= 1 ulp apart from the reference's divisions).
+struct ProjConsts {
+    double inv_fx, inv_fy;
+};
+__device__ __forceinline__ ProjConsts proj_consts(const sr_camera &c) { return {1.0 / c.K[0], 1.0 / c.K[4]}; }
+
+__device__ __forceinline__ bool cam_project_local(const sr_camera &c, const ProjConsts &pc, d3 local, float &w0,
+                                                  float &w1, double &u, double &v) {
     d3 point = local;
     if (c.is_refractive) {  // projectRefraction, camera.cpp:95-138
         const d3 N = ld3(c.plane_n);
         const double a = dot(N, local);
-        const d3 proj = a * N;
-        const d3 radv = local - proj;
+        const d3 radv = local - a * N;
         const double rr = dot(radv, radv);
-        const double r = sqrt(rr);
-        const double z = fabs(a);  // |proj|
-        if (!(r > 0.0)) return false;  // dir = radv/r is NaN: no root is accepted
-        const double x = snell_root(r, c.plane_d, z - c.plane_d, c.n, warm);
+        if (!(rr > 0.0)) return false;  // dir = radv/r is NaN in the reference: no root is accepted
+        const double ir = rsqrt(rr);
+        const double r = rr * ir;
+        const double x = snell_root_fast(r, c.plane_d, fabs(a) - c.plane_d, c.n, w0, w1);
         if (!(x == x)) return false;
-        warm = x / r;
-        // root in [0,r] always passes the y-component acceptance test of camera.cpp:119-135
-        point = warm * radv + c.plane_d * N;
+        // a root in [0,r] always passes the y-component acceptance test of camera.cpp:119-135
+        point = (x * ir) * radv + c.plane_d * N;
     }
-    d3 p = mul3(c.K, point);
-    double x = p.x / p.z, y = p.y / p.z;
+    const d3 p = mul3(c.K, point);
+    const double iz = 1.0 / p.z;
+    double x = p.x * iz, y = p.y * iz;
     if (c.is_distorted) {
         const double cx = c.K[2], cy = c.K[5], fx = c.K[0], fy = c.K[4];
-        x = (x - cx) / fx;
-        y = (y - cy) / fy;
+        x = (x - cx) * pc.inv_fx;
+        y = (y - cy) * pc.inv_fy;
         const double *k = c.dist;
         const double r2 = x * x + y * y;
         const double cdist = 1 + ((k[4] * r2 + k[1]) * r2 + k[0]) * r2;
@@ -162,8 +214,8 @@ __device__ __forceinline__ bool cam_project_local(const sr_camera &c, d3 local, 
 
 // Camera::project of a global point.
 __device__ __forceinline__ bool cam_project(const sr_camera &c, d3 p, double &u, double &v) {
-    double warm = -1.0;
-    return cam_project_local(c, mul3(c.R, p) + ld3(c.t), warm, u, v);
+    float w0 = -1.0f, w1 = -1.0f;
+    return cam_project_local(c, proj_consts(c), mul3(c.R, p) + ld3(c.t), w0, w1, u, v);
 }
 
 // The implicit double->int conversion of projected coordinates (util/lineiter.hpp:34 ctor

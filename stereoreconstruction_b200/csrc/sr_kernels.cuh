@@ -1,24 +1,29 @@
 // sr_kernels.cuh — hand-written sm_100a kernels of the dense-matching hot path.
 //
-//   prep_view_kernel      RGBA8 + mask  -> FP64 gray planes (validity folded in as NaN)
+//   prep_view_kernel      RGBA8 + mask  -> FP64 gray planes (validity folded in as NaN) and the
+//                         four colour-edge planes the geodesic sweeps walk on
 //   rays_kernel           Camera::unproject on every pixel centre        (camera.cpp:423-459)
 //   build_kernel          stage (1): per (pixel, depth label, neighbour view) refractive
 //                         reprojection -> packed integer tap volume      (twoviewstereo.cpp:308-316,
 //                                                                         multiviewstereo.cpp:768-775)
-//   match_kernel<R,G,C>   stages (2)+(3): support weights (Adaptive/Geodesic), weighted window
-//                         cost, WTA fused in the epilogue; streams the tap volume once
-//                                                                        (twoviewstereo.cpp:909-977,
+//   weights_*_kernel      AdaptiveWeight / GeodesicWeight::init_weights  (adaptiveweight.cpp:47-79,
+//                                                                         geodesicweight.cpp:59-131)
+//   match_kernel<R,G,C>   stages (2)+(3): weighted window cost with the support weights, WTA fused
+//                         in the epilogue; streams the tap volume once   (twoviewstereo.cpp:909-977,
 //                                                                         multiviewstereo.cpp:113-189,589-602)
-//   cross_check_*         crossCheck                                      (twoviewstereo.cpp:596-672,
+//   cross_check_kernel    crossCheck                                      (twoviewstereo.cpp:596-672,
 //                                                                         multiviewstereo.cpp:666-729)
 //
 // Data layout in HBM (all row-major, x fastest):
-//   gray planes  double [h][w]          per view, 3 variants (see prep_view_kernel)
-//   rays         double [6][h][w]       SoA: source xyz, direction xyz
-//   tap volume   int32  [nbr][D][rows][w]   (ty<<16 | tx&0xffff), TAP_NONE where the label
-//                                       cannot be evaluated; x fastest so one warp reads/writes
-//                                       128 contiguous bytes per label
-//   cost volume  float  [nbr][D][rows][w]   optional (keep_cost_volume)
+//   gray planes  double [h][w]            per view, 3 variants (see prep_view_kernel)
+//   edge planes  double [4][h][w]         per view: |rgb(p) - rgb(p + e)|, e = E, S, SE, SW
+//   rays         double [6][h][w]         SoA: source xyz, direction xyz
+//   tap volume   int32  [nbr][D][rows][w] (ty<<16 | tx&0xffff), TAP_NONE where the label cannot
+//                                         be evaluated; x fastest: one warp reads/writes 128
+//                                         contiguous bytes per label
+//   weights      double [WN][rows*w]      support weights of the current row band, tap-major so
+//                                         that neighbouring pixels' weights are contiguous
+//   cost volume  float  [nbr][D][rows][w] optional (keep_cost_volume)
 //   outputs      int32 index [h][w], double depth [h][w], double best [h][w]
 #pragma once
 #include "sr_geometry.cuh"
@@ -36,22 +41,37 @@ __device__ __forceinline__ double gray_of(uchar4 p) {
                      __dmul_rn(0.3, (double)p.z));
 }
 __device__ __forceinline__ double qnan() { return __longlong_as_double(0x7ff8000000000000LL); }
+__device__ __forceinline__ double dinf() { return __longlong_as_double(0x7ff0000000000000LL); }
+
+__device__ __forceinline__ double color_dist(uchar4 a, uchar4 b) {
+    // sqrt(dr^2 + dg^2 + db^2) on exact small integers (adaptiveweight.cpp:66-69, geodesicweight.cpp:92-94)
+    const double dr = (double)((int)b.x - (int)a.x), dg = (double)((int)b.y - (int)a.y), db = (double)((int)b.z - (int)a.z);
+    return sqrt(__dadd_rn(__dadd_rn(__dmul_rn(dr, dr), __dmul_rn(dg, dg)), __dmul_rn(db, db)));
+}
 
 // gray_pix: valid wherever in bounds              (VectorImage::pixel, vectorimage.cpp:115-119)
 // gray_two: NaN unless mask WHITE and x+1<w,y+1<h (mask test twoviewstereo.cpp:920-924 +
 //                                                  VectorImage::sample validity, vectorimage.cpp:132)
 // gray_msk: NaN unless mask WHITE                 (cost_sad right taps, twoviewstereo.cpp:877,885)
+// edges[e][p]: colour distance between pixel p and p + (1,0), (0,1), (1,1), (-1,1); +INF when the
+//              other end is outside the image (an edge the geodesic sweeps may not use).
 __global__ void prep_view_kernel(const uchar4 *__restrict__ rgba, const uint8_t *__restrict__ mask, int w, int h,
                                  double *__restrict__ gray_pix, double *__restrict__ gray_two,
-                                 double *__restrict__ gray_msk) {
+                                 double *__restrict__ gray_msk, double *__restrict__ edges) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= w * h) return;
     const int x = i % w, y = i / w;
-    const double g = gray_of(rgba[i]);
+    const uchar4 c = rgba[i];
+    const double g = gray_of(c);
     const bool white = mask[i] == 255;
     gray_pix[i] = g;
     gray_msk[i] = white ? g : qnan();
     gray_two[i] = (white && x + 1 < w && y + 1 < h) ? g : qnan();
+    const size_t n = (size_t)w * h;
+    edges[i] = (x + 1 < w) ? color_dist(c, rgba[i + 1]) : dinf();
+    edges[n + i] = (y + 1 < h) ? color_dist(c, rgba[i + w]) : dinf();
+    edges[2 * n + i] = (x + 1 < w && y + 1 < h) ? color_dist(c, rgba[i + w + 1]) : dinf();
+    edges[3 * n + i] = (x >= 1 && y + 1 < h) ? color_dist(c, rgba[i + w - 1]) : dinf();
 }
 
 __global__ void rays_kernel(sr_camera cam, int w, int h, double scale, double *__restrict__ rays) {
@@ -114,10 +134,13 @@ __global__ void __launch_bounds__(128) build_kernel(const BuildArgs a) {
     const double inv_nd = 1.0 / nd;
     const double nC = dot(nrm, ld3(a.C)), npn = dot(nrm, prin), nn = dot(nrm, nrm), ns = dot(nrm, src);
     const RayInView rv = ray_in_view(a.nbr, src, dir);
+    const ProjConsts pc = proj_consts(a.nbr);
+    const double scale = a.scale, shift = a.mvs ? 0.0 : -0.5;
     const int d0 = blockIdx.y * a.d_chunk;
     const int d1 = min(d0 + a.d_chunk, a.D);
     const size_t plane = (size_t)a.rows * a.w;
-    double warm = -1.0;
+    float w0 = -1.0f, w1 = -1.0f;
+#pragma unroll 1
     for (int d = d0; d < d1; ++d) {
         int32_t tap = TAP_NONE;
         const double depth = a.depth_table[d];
@@ -126,15 +149,9 @@ __global__ void __launch_bounds__(128) build_kernel(const BuildArgs a) {
         if (ray_ok && !(t < 1e-10)) {
             const d3 local = rv.Ls + t * rv.Ld;
             double u, v;
-            if (cam_project_local(a.nbr, local, warm, u, v)) {
-                int tx, ty;
-                if (a.mvs) {
-                    tx = to_int_x86(u * a.scale);
-                    ty = to_int_x86(v * a.scale);
-                } else {
-                    tx = to_int_x86(u * a.scale - 0.5);
-                    ty = to_int_x86(v * a.scale - 0.5);
-                }
+            if (cam_project_local(a.nbr, pc, local, w0, w1, u, v)) {
+                int tx = to_int_x86(fma(u, scale, shift));
+                int ty = to_int_x86(fma(v, scale, shift));
                 bool keep = true;
                 if (a.mvs) {  // multiviewstereo.cpp:787: only WHITE neighbour-mask pixels are candidates
                     keep = tx >= 0 && ty >= 0 && tx < a.w && ty < a.h && a.nbr_mask[(size_t)ty * a.w + tx] == 255;
@@ -151,100 +168,131 @@ __global__ void __launch_bounds__(128) build_kernel(const BuildArgs a) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// Support weights.
-__device__ __forceinline__ bool load_rgb(const uchar4 *img, int w, int h, int x, int y, double &r, double &g, double &b) {
-    if (x < 0 || y < 0 || x >= w || y >= h) return false;
-    const uchar4 p = img[(size_t)y * w + x];
-    r = p.x;
-    g = p.y;
-    b = p.z;
-    return true;
+// Support weights -> W[k][pid], k = (row+R)*(2R+1) + (col+R), pid = pixel index inside the band.
+struct WeightArgs {
+    const uchar4 *rgba;
+    const uint8_t *mask;
+    const double *edges;   // [4][h][w]
+    double *W;             // [WN][npix]
+    int w, h, row0, rows, radius;
+    // list mode (sr_compute_weights): explicit window centres instead of a row band; no mask test
+    const int32_t *list_x, *list_y;
+    int list_n;
+};
+__device__ __forceinline__ bool weight_centre(const WeightArgs &a, int pid, size_t &npix, int &cx, int &cy) {
+    if (a.list_x) {
+        npix = (size_t)a.list_n;
+        if (pid >= a.list_n) return false;
+        cx = a.list_x[pid];
+        cy = a.list_y[pid];
+        return true;
+    }
+    npix = (size_t)a.rows * a.w;
+    if (pid >= (int)npix) return false;
+    cx = pid % a.w;
+    cy = a.row0 + pid / a.w;
+    return a.mask[(size_t)cy * a.w + cx] == 255;
 }
 
-// AdaptiveWeight::weight (stereo/adaptiveweight.cpp:62-79)
-__device__ __forceinline__ double adaptive_weight(const uchar4 *img, int w, int h, int cx, int cy, int row, int col,
-                                                  int radius) {
-    double r0, g0, b0, r1, g1, b1;
-    if (!load_rgb(img, w, h, cx + col, cy + row, r1, g1, b1)) return 0.0;
-    if (!load_rgb(img, w, h, cx, cy, r0, g0, b0)) return 0.0;  // NaN weight -> 0
-    r1 -= r0;
-    g1 -= g0;
-    b1 -= b0;
-    const double diff = sqrt(r1 * r1 + g1 * g1 + b1 * b1);
-    const double w1 = exp(-abs(row) / (1.0 * radius)) * exp(-abs(col) / (1.0 * radius));
-    const double w2 = exp(-diff / 10.0);
-    const double wt = w1 * w2;
-    return (wt == wt) ? wt : 0.0;
-}
-
-// GeodesicWeight::init_weights (stereo/geodesicweight.cpp:59-131): 3 x (forward + backward)
-// in-place raster sweeps over the (2r+1)^2 window.  Executed by ONE thread on its own grid `c`
-// (local or shared memory); the update order is the reference's, so results are identical.
-__device__ inline void geodesic_costs(const uchar4 *img, int w, int h, int cx, int cy, int radius, double *c) {
-    const int ws = 2 * radius + 1;
-    for (int i = 0; i < ws * ws; ++i) c[i] = 1000000.0;
-    c[radius * ws + radius] = 0.0;
-#pragma unroll 1
-    for (int iter = 0; iter < 3; ++iter) {
-#pragma unroll 1
-        for (int pass = 0; pass < 2; ++pass) {
-            // forward: neighbours (-1,-1),(0,-1),(1,-1),(-1,0); backward: (-1,1),(0,1),(1,1),(1,0)
-            const int sy = pass ? 1 : -1;
-#pragma unroll 1
-            for (int yi = 0; yi < ws; ++yi) {
-                const int y = pass ? radius - yi : yi - radius;
-#pragma unroll 1
-                for (int xi = 0; xi < ws; ++xi) {
-                    const int x = pass ? radius - xi : xi - radius;
-                    double r1, g1, b1;
-                    if (!load_rgb(img, w, h, cx + x, cy + y, r1, g1, b1)) continue;
-                    double wt = c[(y + radius) * ws + (x + radius)];
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        const int dx = (k == 3) ? (pass ? 1 : -1) : (k - 1);
-                        const int dy = (k == 3) ? 0 : sy;
-                        const int nx = x + dx, ny = y + dy;
-                        if (nx > radius || ny > radius || nx < -radius || ny < -radius) continue;
-                        double r2, g2, b2;
-                        if (load_rgb(img, w, h, cx + nx, cy + ny, r2, g2, b2)) {
-                            r2 -= r1;
-                            g2 -= g1;
-                            b2 -= b1;
-                            const double diff = sqrt(r2 * r2 + g2 * g2 + b2 * b2);
-                            wt = fmin(wt, c[(ny + radius) * ws + (nx + radius)] + diff);
-                        }
-                    }
-                    c[(y + radius) * ws + (x + radius)] = wt;
-                }
+// AdaptiveWeight::weight (stereo/adaptiveweight.cpp:62-79) for every tap of every band pixel.
+__global__ void __launch_bounds__(128) weights_adaptive_kernel(const WeightArgs a) {
+    extern __shared__ double dw[];  // distance_weights[i] = exp(-i / radius), adaptiveweight.cpp:36-38
+    const int R = a.radius, WS = 2 * R + 1;
+    if ((int)threadIdx.x <= R) dw[threadIdx.x] = exp(-(double)threadIdx.x / (1.0 * R));
+    __syncthreads();
+    const int pid = blockIdx.x * blockDim.x + threadIdx.x;
+    size_t npix;
+    int cx, cy;
+    if (!weight_centre(a, pid, npix, cx, cy)) return;
+    const bool centre_ok = cx >= 0 && cy >= 0 && cx < a.w && cy < a.h;
+    const uchar4 c = centre_ok ? a.rgba[(size_t)cy * a.w + cx] : make_uchar4(0, 0, 0, 0);
+    for (int row = -R; row <= R; ++row) {
+        const int y = cy + row;
+        for (int col = -R; col <= R; ++col) {
+            const int x = cx + col;
+            double wt = 0.0;
+            if (centre_ok && x >= 0 && y >= 0 && x < a.w && y < a.h) {  // invalid centre: NaN weight -> 0
+                const double diff = color_dist(c, a.rgba[(size_t)y * a.w + x]);
+                wt = (dw[abs(row)] * dw[abs(col)]) * exp(-diff / 10.0);
             }
+            a.W[(size_t)((row + R) * WS + (col + R)) * npix + pid] = wt;
         }
     }
 }
 
-// sr_compute_weights: one thread per requested window centre, output in global memory.
-__global__ void weights_kernel(const uchar4 *__restrict__ img, int w, int h, int kind, int radius, int n,
-                               const int32_t *__restrict__ cx, const int32_t *__restrict__ cy, double *out) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const int ws = 2 * radius + 1;
-    double *o = out + (size_t)i * ws * ws;
-    if (kind == SR_WEIGHT_ADAPTIVE) {
-        for (int row = -radius; row <= radius; ++row)
-            for (int col = -radius; col <= radius; ++col)
-                o[(row + radius) * ws + (col + radius)] = adaptive_weight(img, w, h, cx[i], cy[i], row, col, radius);
-    } else {
-        geodesic_costs(img, w, h, cx[i], cy[i], radius, o);
-        for (int k = 0; k < ws * ws; ++k) o[k] = exp(-o[k] / 50.0);
+// GeodesicWeight::init_weights (stereo/geodesicweight.cpp:59-131): 3 x (forward + backward)
+// in-place raster sweeps over the window.  One thread per reference pixel; the (2R+1)^2 grid is
+// the thread's own column of W (coalesced across the warp), the update order is the
+// reference's, and the colour distances come from the precomputed edge planes, so the result is
+// the reference's up to the final exp().  Cells whose pixel is outside the image are never
+// updated and every edge into them is +INF, which reproduces the reference's validity tests.
+__global__ void __launch_bounds__(128) weights_geodesic_kernel(const WeightArgs a) {
+    const int R = a.radius, WS = 2 * R + 1;
+    const int pid = blockIdx.x * blockDim.x + threadIdx.x;
+    size_t npix;
+    int cx, cy;
+    if (!weight_centre(a, pid, npix, cx, cy)) return;
+    double *c = a.W + pid;
+    for (int k = 0; k < WS * WS; ++k) c[(size_t)k * npix] = 1000000.0;
+    c[(size_t)(R * WS + R) * npix] = 0.0;
+    const size_t n = (size_t)a.w * a.h;
+    const double *eE = a.edges, *eS = a.edges + n, *eSE = a.edges + 2 * n, *eSW = a.edges + 3 * n;
+    const int w = a.w, h = a.h;
+#pragma unroll 1
+    for (int iter = 0; iter < 3; ++iter) {
+        // forward pass: neighbours (-1,-1), (0,-1), (1,-1), (-1,0)
+#pragma unroll 1
+        for (int y = -R; y <= R; ++y) {
+            const int py = cy + y;
+            if (py < 0 || py >= h) continue;
+#pragma unroll 1
+            for (int x = -R; x <= R; ++x) {
+                const int px = cx + x;
+                if (px < 0 || px >= w) continue;
+                const size_t p = (size_t)py * w + px;
+                const size_t k = (size_t)((y + R) * WS + (x + R));
+                double wt = c[k * npix];
+                if (y > -R && py >= 1) {  // row above (inside the image): edges stored at the upper pixel
+                    if (x > -R && px >= 1) wt = fmin(wt, c[(k - WS - 1) * npix] + eSE[p - w - 1]);
+                    wt = fmin(wt, c[(k - WS) * npix] + eS[p - w]);
+                    if (x < R && px + 1 < w) wt = fmin(wt, c[(k - WS + 1) * npix] + eSW[p - w + 1]);
+                }
+                if (x > -R && px >= 1) wt = fmin(wt, c[(k - 1) * npix] + eE[p - 1]);
+                c[k * npix] = wt;
+            }
+        }
+        // backward pass: neighbours (-1,1), (0,1), (1,1), (1,0)
+#pragma unroll 1
+        for (int y = R; y >= -R; --y) {
+            const int py = cy + y;
+            if (py < 0 || py >= h) continue;
+#pragma unroll 1
+            for (int x = R; x >= -R; --x) {
+                const int px = cx + x;
+                if (px < 0 || px >= w) continue;
+                const size_t p = (size_t)py * w + px;
+                const size_t k = (size_t)((y + R) * WS + (x + R));
+                double wt = c[k * npix];
+                if (y < R) {  // row below: edges stored at this pixel
+                    if (x > -R) wt = fmin(wt, c[(k + WS - 1) * npix] + eSW[p]);
+                    wt = fmin(wt, c[(k + WS) * npix] + eS[p]);
+                    if (x < R) wt = fmin(wt, c[(k + WS + 1) * npix] + eSE[p]);
+                }
+                if (x < R) wt = fmin(wt, c[(k + 1) * npix] + eE[p]);
+                c[k * npix] = wt;
+            }
+        }
     }
+    for (int k = 0; k < WS * WS; ++k) c[(size_t)k * npix] = exp(-c[(size_t)k * npix] / 50.0);
 }
 
 // ---------------------------------------------------------------------------------------------
-// Stages (2)+(3): weights + windowed cost + WTA.
+// Stages (2)+(3): windowed cost + WTA.
 struct MatchArgs {
-    const uchar4 *rgbaL;            // reference view colours (support weights)
     const uint8_t *maskL;           // reference view mask
     const double *grayL;            // reference taps  (gray_pix for C1, gray_two for C2/C3)
     const double *grayR[SR_MAX_NBRS];  // neighbour taps (gray_pix C1, gray_two C2, gray_msk C3)
+    const double *W;                // [WN][rows*w] support weights of this band
     const int32_t *taps;            // [nbr][D][rows][w]
     const double *depth_table;      // [D]
     int32_t *out_index;             // [h][w]
@@ -252,7 +300,7 @@ struct MatchArgs {
     double *out_best;               // [h][w]
     float *out_volume;              // [nbr][D][rows][w] or null
     int w, h, row0, rows, D, num_nbrs;
-    int weight_kind, select_kind;
+    int select_kind;
     double second_best_factor, ncc_threshold;
 };
 
@@ -269,16 +317,76 @@ __device__ __forceinline__ int group_sum_i(int v, unsigned gmask) {
     return v;
 }
 
+// The exact tap filter of the reference (a tap counts only if both pixels are valid and the
+// weight exceeds 1e-10), used for the few windows that touch an image border or an invalid
+// (masked) pixel.  Runtime loops, weights re-read from W: small code, no register arrays.
+template <int R, int G, int COST>
+__device__ __noinline__ double slow_cost(const MatchArgs &a, const double *__restrict__ gR, int x, int y, int tx, int ty,
+                                         int pid, int sub, unsigned gmask) {
+    constexpr int WS = 2 * R + 1, WN = WS * WS;
+    constexpr bool NCC = (COST != SR_COST_SAD_TWOVIEW);
+    const int w = a.w, h = a.h;
+    const size_t npix = (size_t)a.rows * w;
+    double mL = 0.0, mR = 0.0, tw = 0.0;
+    int cnt = 0;
+#pragma unroll 1
+    for (int k = sub; k < WN; k += G) {
+        const int row = k / WS - R, col = k % WS - R;
+        const int xr = tx + col, yr = ty + row, xl = x + col, yl = y + row;
+        if (xr < 0 || yr < 0 || xr >= w || yr >= h || xl < 0 || yl < 0 || xl >= w || yl >= h) continue;
+        const double gl = a.grayL[(size_t)yl * w + xl], gr = gR[(size_t)yr * w + xr];
+        const double wt = a.W[(size_t)k * npix + pid];
+        if (gl == gl && gr == gr && wt > 1e-10) {
+            if (NCC) {
+                mL += wt * gl;
+                mR += wt * gr;
+            } else {
+                mL += wt * fmin(120.0, fabs(gl - gr));
+            }
+            tw += wt;
+            ++cnt;
+        }
+    }
+    mL = group_sum<G>(mL, gmask);
+    mR = group_sum<G>(mR, gmask);
+    tw = group_sum<G>(tw, gmask);
+    cnt = group_sum_i<G>(cnt, gmask);
+    if (!NCC) return (cnt <= 4 || tw <= 1e-10) ? 1000.0 : mL / tw;
+    if (tw < 1e-10) return (COST == SR_COST_NCC_MVS) ? 0.0 : 1000.0;
+    mL /= tw;
+    mR /= tw;
+    double q1 = 0.0, q2 = 0.0, q3 = 0.0;
+#pragma unroll 1
+    for (int k = sub; k < WN; k += G) {
+        const int row = k / WS - R, col = k % WS - R;
+        const int xr = tx + col, yr = ty + row, xl = x + col, yl = y + row;
+        if (xr < 0 || yr < 0 || xr >= w || yr >= h || xl < 0 || yl < 0 || xl >= w || yl >= h) continue;
+        const double gl = a.grayL[(size_t)yl * w + xl], gr = gR[(size_t)yr * w + xr];
+        const double wt = a.W[(size_t)k * npix + pid];
+        if (gl == gl && gr == gr && wt > 1e-10) {
+            const double pl = wt * gl - mL, pr = wt * gr - mR;
+            q1 += pl * pr;
+            q2 += pl * pl;
+            q3 += pr * pr;
+        }
+    }
+    q1 = group_sum<G>(q1, gmask);
+    q2 = group_sum<G>(q2, gmask);
+    q3 = group_sum<G>(q3, gmask);
+    if (COST == SR_COST_NCC_MVS) return (q2 * q3 < 1e-10) ? 0.0 : q1 / sqrt(q2 * q3);
+    const double v = 255.0 * (1.0 - fabs(q1) / sqrt(q2 * q3));
+    return (v < 120.0) ? v : 120.0;
+}
+
 // R: window radius; G: lanes cooperating on one reference pixel (taps are dealt round-robin to
 // the G lanes and live in registers); COST: SR_COST_*.
 template <int R, int G, int COST>
-__global__ void __launch_bounds__(128) match_kernel(const MatchArgs a) {
+__global__ void __launch_bounds__(128) match_kernel(const __grid_constant__ MatchArgs a) {
     constexpr int WS = 2 * R + 1;
     constexpr int WN = WS * WS;
     constexpr int TPL = (WN + G - 1) / G;
     constexpr bool NCC = (COST != SR_COST_SAD_TWOVIEW);
     constexpr int PIX_PER_BLOCK = 128 / G;
-    extern __shared__ double smem[];  // geodesic grids for G > 1: [PIX_PER_BLOCK][WN]
 
     const int lane = threadIdx.x & 31;
     const int sub = threadIdx.x % G;
@@ -288,45 +396,22 @@ __global__ void __launch_bounds__(128) match_kernel(const MatchArgs a) {
     const int x = pid % a.w, y = a.row0 + pid / a.w;
     const size_t pix = (size_t)y * a.w + x;
     const int w = a.w, h = a.h;
+    const size_t npix = (size_t)a.rows * w;
 
     if (a.maskL[pix] != 255) {  // twoviewstereo.cpp:269-271 (NaN) / multiviewstereo.cpp:559,565 (INF)
         if (sub == 0) {
             a.out_index[pix] = SR_INDEX_MASKED;
-            a.out_depth[pix] = (a.select_kind == SR_SELECT_MVS) ? __longlong_as_double(0x7ff0000000000000LL) : qnan();
+            a.out_depth[pix] = (a.select_kind == SR_SELECT_MVS) ? dinf() : qnan();
             a.out_best[pix] = qnan();
         }
         return;
     }
 
-    // ---- support weights -> registers -------------------------------------------------------
-    double wt[TPL];
-    if (a.weight_kind == SR_WEIGHT_ADAPTIVE) {
-#pragma unroll
-        for (int i = 0; i < TPL; ++i) {
-            const int k = sub + G * i;
-            wt[i] = (k < WN) ? adaptive_weight(a.rgbaL, w, h, x, y, k / WS - R, k % WS - R, R) : 0.0;
-        }
-    } else {
-        if (G == 1) {
-            double c[WN];
-            geodesic_costs(a.rgbaL, w, h, x, y, R, c);
-#pragma unroll
-            for (int i = 0; i < TPL; ++i) wt[i] = exp(-c[i] / 50.0);
-        } else {
-            double *c = smem + (size_t)(threadIdx.x / G) * WN;
-            if (sub == 0) geodesic_costs(a.rgbaL, w, h, x, y, R, c);
-            __syncwarp(gmask);
-#pragma unroll
-            for (int i = 0; i < TPL; ++i) {
-                const int k = sub + G * i;
-                wt[i] = (k < WN) ? exp(-c[k] / 50.0) : 0.0;
-            }
-        }
-    }
-
     // ---- reference-window invariants (hoisted out of the label sweep) -----------------------
-    // c1[i]: NCC: w*(w*gl - meanL);  SAD: gl.   Inactive taps get wt = 0, c1 = 0.
-    double c1[TPL];
+    // wt[i]: support weight of this lane's i-th tap (0 for taps the reference skips on the
+    //        reference side: invalid pixel or weight <= 1e-10);
+    // c1[i]: NCC: wt*(wt*gl - meanL);  SAD: gl.
+    double wt[TPL], c1[TPL];
     double totW = 0.0, SL = 0.0;
     int nact = 0;
 #pragma unroll
@@ -334,23 +419,25 @@ __global__ void __launch_bounds__(128) match_kernel(const MatchArgs a) {
         const int k = sub + G * i;
         const int row = k / WS - R, col = k % WS - R;
         const int xl = x + col, yl = y + row;
-        double gl = qnan();
-        if (k < WN && xl >= 0 && yl >= 0 && xl < w && yl < h) gl = a.grayL[(size_t)yl * w + xl];
-        const bool active = (gl == gl) && (wt[i] > 1e-10);
-        if (!active) {
-            wt[i] = 0.0;
-            gl = 0.0;
-        } else {
-            totW += wt[i];
-            SL += wt[i] * gl;
+        double gl = qnan(), wv = 0.0;
+        if (k < WN && xl >= 0 && yl >= 0 && xl < w && yl < h) {
+            gl = a.grayL[(size_t)yl * w + xl];
+            wv = a.W[(size_t)k * npix + pid];
+        }
+        const bool active = (gl == gl) && (wv > 1e-10);
+        wt[i] = active ? wv : 0.0;
+        c1[i] = active ? gl : 0.0;
+        if (active) {
+            totW += wv;
+            SL += wv * gl;
             ++nact;
         }
-        c1[i] = gl;
     }
     totW = group_sum<G>(totW, gmask);
     SL = group_sum<G>(SL, gmask);
     nact = group_sum_i<G>(nact, gmask);
     const double meanL = SL / totW;
+    const double inv_totW = 1.0 / totW;
     double s2 = 0.0, SD = 0.0;
     if (NCC) {
 #pragma unroll
@@ -364,42 +451,54 @@ __global__ void __launch_bounds__(128) match_kernel(const MatchArgs a) {
         SD = group_sum<G>(SD, gmask);
     }
     const bool degenerate = (COST == SR_COST_SAD_TWOVIEW) ? (nact <= 4 || totW <= 1e-10) : (totW < 1e-10);
+    const double dnact = (double)nact;
 
     // ---- label sweep -------------------------------------------------------------------------
-    const double INF = __longlong_as_double(0x7ff0000000000000LL);
-    double minCost = INF, secondBest = INF;  // two-view selection
-    double bestC = 0.0, bestD = -1.0;        // MVS selection
+    double minCost = dinf(), secondBest = dinf();  // two-view selection
+    double bestC = 0.0, bestD = -1.0;              // MVS selection
     int bestIdx = SR_INDEX_NONE;
-    const size_t plane = (size_t)a.rows * w;
+    const bool mvs = a.select_kind == SR_SELECT_MVS;
 
 #pragma unroll 1
     for (int j = 0; j < a.num_nbrs; ++j) {
         const double *__restrict__ gR = a.grayR[j];
-        const int32_t *__restrict__ taps = a.taps + (size_t)j * a.D * plane + pid;
-        float *vol = a.out_volume ? a.out_volume + (size_t)j * a.D * plane + pid : nullptr;
+        const int32_t *__restrict__ taps = a.taps + (size_t)j * a.D * npix + pid;
+        float *vol = a.out_volume ? a.out_volume + (size_t)j * a.D * npix + pid : nullptr;
+        int32_t tap_next = taps[0];
 #pragma unroll 1
         for (int d = 0; d < a.D; ++d) {
-            const int32_t tap = taps[(size_t)d * plane];
+            const int32_t tap = tap_next;
+            if (d + 1 < a.D) tap_next = taps[(size_t)(d + 1) * npix];  // prefetch: the volume streams from HBM
             double cost = qnan();
             if (tap != TAP_NONE) {
                 const int tx = (int)(short)(tap & 0xffff), ty = (int)(short)((uint32_t)tap >> 16);
                 bool slow = !(tx >= R && ty >= R && tx < w - R && ty < h - R);
                 if (!slow) {
-                    // fast path: whole neighbour window in bounds; one streaming pass.
-                    const double *base = gR + (size_t)ty * w + tx;
+                    // fast path: whole neighbour window in bounds; one streaming pass over the taps.
+                    const double *__restrict__ base = gR + ((size_t)ty * w + tx);
                     if (NCC) {
-                        double S1 = 0.0, S2 = 0.0, S3 = 0.0;
+                        // two interleaved accumulator sets halve the dependent-add chains
+                        double S1 = 0.0, S2 = 0.0, S3 = 0.0, T1 = 0.0, T2 = 0.0, T3 = 0.0;
 #pragma unroll
                         for (int i = 0; i < TPL; ++i) {
                             const int k = sub + G * i;
                             if (k < WN) {
                                 const double gr = base[(k / WS - R) * w + (k % WS - R)];
                                 const double p = wt[i] * gr;
-                                S1 += p;
-                                S2 = fma(p, p, S2);
-                                S3 = fma(c1[i], gr, S3);
+                                if (i & 1) {
+                                    T1 += p;
+                                    T2 = fma(p, p, T2);
+                                    T3 = fma(c1[i], gr, T3);
+                                } else {
+                                    S1 += p;
+                                    S2 = fma(p, p, S2);
+                                    S3 = fma(c1[i], gr, S3);
+                                }
                             }
                         }
+                        S1 += T1;
+                        S2 += T2;
+                        S3 += T3;
                         S1 = group_sum<G>(S1, gmask);
                         S2 = group_sum<G>(S2, gmask);
                         S3 = group_sum<G>(S3, gmask);
@@ -408,13 +507,14 @@ __global__ void __launch_bounds__(128) match_kernel(const MatchArgs a) {
                         } else if (degenerate) {
                             cost = (COST == SR_COST_NCC_MVS) ? 0.0 : 1000.0;
                         } else {
-                            const double meanR = S1 / totW;
+                            const double meanR = S1 * inv_totW;
                             const double s1 = S3 - meanR * SD;
-                            const double s3 = S2 - 2.0 * meanR * S1 + nact * meanR * meanR;
+                            const double s3 = S2 - 2.0 * meanR * S1 + dnact * meanR * meanR;
+                            const double q = s2 * s3;
                             if (COST == SR_COST_NCC_MVS) {
-                                cost = (s2 * s3 < 1e-10) ? 0.0 : s1 / sqrt(s2 * s3);
+                                cost = (q < 1e-10) ? 0.0 : s1 * rsqrt(q);
                             } else {
-                                const double v = 255.0 * (1.0 - fabs(s1) / sqrt(s2 * s3));
+                                const double v = 255.0 * (1.0 - fabs(s1) * rsqrt(q));
                                 cost = (v < 120.0) ? v : 120.0;
                             }
                         }
@@ -430,75 +530,12 @@ __global__ void __launch_bounds__(128) match_kernel(const MatchArgs a) {
                         }
                         S = group_sum<G>(S, gmask);
                         if (S != S) slow = true;
-                        else cost = degenerate ? 1000.0 : S / totW;
+                        else cost = degenerate ? 1000.0 : S * inv_totW;
                     }
                 }
-                if (slow) {
-                    // exact tap filtering as in the reference: a tap counts only if both pixels are
-                    // valid and the weight exceeds 1e-10.
-                    double mL = 0.0, mR = 0.0, tw = 0.0;
-                    int cnt = 0;
-#pragma unroll
-                    for (int i = 0; i < TPL; ++i) {
-                        const int k = sub + G * i;
-                        const int row = k / WS - R, col = k % WS - R;
-                        const int xr = tx + col, yr = ty + row, xl = x + col, yl = y + row;
-                        if (k < WN && wt[i] > 0.0 && xr >= 0 && yr >= 0 && xr < w && yr < h) {
-                            const double gr = gR[(size_t)yr * w + xr];
-                            const double gl = a.grayL[(size_t)yl * w + xl];
-                            if (gr == gr) {
-                                if (NCC) {
-                                    mL += wt[i] * gl;
-                                    mR += wt[i] * gr;
-                                } else {
-                                    mL += wt[i] * fmin(120.0, fabs(gl - gr));
-                                }
-                                tw += wt[i];
-                                ++cnt;
-                            }
-                        }
-                    }
-                    mL = group_sum<G>(mL, gmask);
-                    mR = group_sum<G>(mR, gmask);
-                    tw = group_sum<G>(tw, gmask);
-                    cnt = group_sum_i<G>(cnt, gmask);
-                    if (!NCC) {
-                        cost = (cnt <= 4 || tw <= 1e-10) ? 1000.0 : mL / tw;
-                    } else if (tw < 1e-10) {
-                        cost = (COST == SR_COST_NCC_MVS) ? 0.0 : 1000.0;
-                    } else {
-                        mL /= tw;
-                        mR /= tw;
-                        double q1 = 0.0, q2 = 0.0, q3 = 0.0;
-#pragma unroll
-                        for (int i = 0; i < TPL; ++i) {
-                            const int k = sub + G * i;
-                            const int row = k / WS - R, col = k % WS - R;
-                            const int xr = tx + col, yr = ty + row, xl = x + col, yl = y + row;
-                            if (k < WN && wt[i] > 0.0 && xr >= 0 && yr >= 0 && xr < w && yr < h) {
-                                const double gr = gR[(size_t)yr * w + xr];
-                                const double gl = a.grayL[(size_t)yl * w + xl];
-                                if (gr == gr) {
-                                    const double pl = wt[i] * gl - mL, pr = wt[i] * gr - mR;
-                                    q1 += pl * pr;
-                                    q2 += pl * pl;
-                                    q3 += pr * pr;
-                                }
-                            }
-                        }
-                        q1 = group_sum<G>(q1, gmask);
-                        q2 = group_sum<G>(q2, gmask);
-                        q3 = group_sum<G>(q3, gmask);
-                        if (COST == SR_COST_NCC_MVS) {
-                            cost = (q2 * q3 < 1e-10) ? 0.0 : q1 / sqrt(q2 * q3);
-                        } else {
-                            const double v = 255.0 * (1.0 - fabs(q1) / sqrt(q2 * q3));
-                            cost = (v < 120.0) ? v : 120.0;
-                        }
-                    }
-                }
+                if (slow) cost = slow_cost<R, G, COST>(a, gR, x, y, tx, ty, pid, sub, gmask);
                 // ---- stage (3): winner-take-all, fused ----
-                if (a.select_kind == SR_SELECT_MVS) {  // multiviewstereo.cpp:589-602,654-660
+                if (mvs) {  // multiviewstereo.cpp:589-602,654-660
                     if (cost > a.ncc_threshold) {
                         const double depth = a.depth_table[d];
                         if (bestIdx == SR_INDEX_NONE || cost > bestC || (cost == bestC && depth > bestD)) {
@@ -515,19 +552,19 @@ __global__ void __launch_bounds__(128) match_kernel(const MatchArgs a) {
                     }
                 }
             }
-            if (vol && sub == 0) vol[(size_t)d * plane] = (float)cost;
+            if (vol && sub == 0) vol[(size_t)d * npix] = (float)cost;
         }
     }
 
     if (sub == 0) {
-        if (a.select_kind == SR_SELECT_MVS) {
+        if (mvs) {
             a.out_index[pix] = bestIdx;
             a.out_depth[pix] = bestD;
             a.out_best[pix] = bestC;
         } else {
             double depth = (bestIdx >= 0) ? a.depth_table[bestIdx] : qnan();
             if (a.second_best_factor > 0.0 && minCost > a.second_best_factor * secondBest) {  // :304-305
-                depth = INF;
+                depth = dinf();
                 bestIdx = SR_INDEX_REJECTED;
             }
             a.out_index[pix] = bestIdx;
@@ -568,7 +605,6 @@ __global__ void __launch_bounds__(128) cross_check_kernel(const CrossArgs a) {
     d3 src, dir, p1;
     cam_unproject(A, (x + 0.5) / a.scale, (y + 0.5) / a.scale, src, dir);
     if (!point_from_depth(src, dir, ld3(A.prin_dir), ld3(A.C), depth, p1)) return;
-    const double INF = __longlong_as_double(0x7ff0000000000000LL);
     bool found = false, fail = false;
     for (int b = 0; b < a.num_views && !found; ++b) {
         if (b == a.viewA) continue;
@@ -598,7 +634,7 @@ __global__ void __launch_bounds__(128) cross_check_kernel(const CrossArgs a) {
     }
     if (a.two_view) {
         if (fail) {
-            depthA[i] = INF;
+            depthA[i] = dinf();
             a.indexA[i] = SR_INDEX_REJECTED;
         }
     } else if (!found) {

@@ -13,16 +13,10 @@ inline bool match_supported(int r) { return (r >= 1 && r <= 8) || r == 10 || r =
 template <int R, int COST>
 cudaError_t launch_match_rc(const MatchArgs &a, cudaStream_t st) {
     constexpr int G = LanesFor<R>::G;
-    constexpr int WN = (2 * R + 1) * (2 * R + 1);
     constexpr int PPB = 128 / G;
     const size_t npix = (size_t)a.rows * a.w;
     const unsigned grid = (unsigned)((npix + PPB - 1) / PPB);
-    const size_t smem = (G > 1) ? (size_t)PPB * WN * sizeof(double) : 0;
-    if (smem > 48 * 1024) {
-        cudaError_t e = cudaFuncSetAttribute(match_kernel<R, G, COST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-    }
-    match_kernel<R, G, COST><<<grid, 128, smem, st>>>(a);
+    match_kernel<R, G, COST><<<grid, 128, 0, st>>>(a);
     return cudaGetLastError();
 }
 
