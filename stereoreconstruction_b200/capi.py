@@ -15,7 +15,7 @@ _PKG = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_PKG, "libsr_b200.so")
 _LIB = None
 
-NVCC_FLAGS = ["-std=c++17", "-O3", "-DSR_FEW_RADII", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
+NVCC_FLAGS = ["-std=c++17", "-O3", "-fmad=false", "-DSR_FEW_RADII", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
               "--shared", "-Xcompiler", "-fPIC"]
 SOURCES = ["csrc/sr_capi.cu"]
 HEADERS = ["csrc/sr_geometry.cuh", "csrc/sr_kernels.cuh", "csrc/sr_match_dispatch.cuh",

@@ -28,6 +28,15 @@ __device__ __forceinline__ d3 mul3(const double *M, d3 v) {
             M[6] * v.x + M[7] * v.y + M[8] * v.z};
 }
 __device__ __forceinline__ d3 ld3(const double *p) { return {p[0], p[1], p[2]}; }
+// The library is compiled with -fmad=false so that plain expressions round exactly like the
+// CPU oracle (IEEE, no contraction).  Where fusion is wanted (the refractive fast path, whose
+// root solve is not bit-comparable anyway) it is written explicitly:
+__device__ __forceinline__ double fdot(d3 a, d3 b) { return fma(a.x, b.x, fma(a.y, b.y, a.z * b.z)); }
+__device__ __forceinline__ d3 faxpy(double s, d3 a, d3 b) { return {fma(s, a.x, b.x), fma(s, a.y, b.y), fma(s, a.z, b.z)}; }
+__device__ __forceinline__ d3 fmul3(const double *M, d3 v) {
+    return {fma(M[0], v.x, fma(M[1], v.y, M[2] * v.z)), fma(M[3], v.x, fma(M[4], v.y, M[5] * v.z)),
+            fma(M[6], v.x, fma(M[7], v.y, M[8] * v.z))};
+}
 
 // util/ray.cpp:78-88 (intersect) with the plane given as (unit normal, distance).
 __device__ __forceinline__ bool ray_plane(d3 src, d3 dir, d3 n, double dist, d3 &p) {
@@ -133,8 +142,8 @@ __device__ __forceinline__ double snell_root_fast(double r, double d, double h, 
     for (int it = 0; it < iters; ++it) {
         const float rx = rf - x;
         const float ia = rsqrtf(fmaf(x, x, ddf)), ib = rsqrtf(fmaf(rx, rx, hhf));
-        const float g = x * ia - nf * rx * ib;
-        const float gp = ddf * ia * ia * ia + nf * hhf * ib * ib * ib;
+        const float g = fmaf(x, ia, -(nf * rx) * ib);
+        const float gp = fmaf(ddf * ia, ia * ia, (nf * hhf) * ib * (ib * ib));
         x = fminf(fmaxf(x - __fdividef(g, gp), 0.0f), rf);
     }
     double X = (double)x;
@@ -142,8 +151,8 @@ __device__ __forceinline__ double snell_root_fast(double r, double d, double h, 
         const double dd = d * d, hh = h * h;
         const double rx = r - X;
         const double ia = rsqrt(fma(X, X, dd)), ib = rsqrt(fma(rx, rx, hh));
-        const double g = X * ia - n * rx * ib;
-        const double gp = dd * ia * ia * ia + n * hh * ib * ib * ib;
+        const double g = fma(X, ia, -(n * rx) * ib);
+        const double gp = fma(dd * ia, ia * ia, (n * hh) * ib * (ib * ib));
         const double step = g / gp;
         X -= step;
         if (!(fabs(step) <= 2e-5 * r) || !(X >= 0.0 && X <= r)) X = snell_root_robust(r, d, h, n, -1.0);
@@ -179,18 +188,18 @@ __device__ __forceinline__ bool cam_project_local(const sr_camera &c, const Proj
     d3 point = local;
     if (c.is_refractive) {  // projectRefraction, camera.cpp:95-138
         const d3 N = ld3(c.plane_n);
-        const double a = dot(N, local);
-        const d3 radv = local - a * N;
-        const double rr = dot(radv, radv);
+        const double a = fdot(N, local);
+        const d3 radv = faxpy(-a, N, local);
+        const double rr = fdot(radv, radv);
         if (!(rr > 0.0)) return false;  // dir = radv/r is NaN in the reference: no root is accepted
         const double ir = rsqrt(rr);
         const double r = rr * ir;
         const double x = snell_root_fast(r, c.plane_d, fabs(a) - c.plane_d, c.n, w0, w1);
         if (!(x == x)) return false;
         // a root in [0,r] always passes the y-component acceptance test of camera.cpp:119-135
-        point = (x * ir) * radv + c.plane_d * N;
+        point = faxpy(x * ir, radv, c.plane_d * N);
     }
-    const d3 p = mul3(c.K, point);
+    const d3 p = fmul3(c.K, point);
     const double iz = 1.0 / p.z;
     double x = p.x * iz, y = p.y * iz;
     if (c.is_distorted) {
@@ -198,22 +207,52 @@ __device__ __forceinline__ bool cam_project_local(const sr_camera &c, const Proj
         x = (x - cx) * pc.inv_fx;
         y = (y - cy) * pc.inv_fy;
         const double *k = c.dist;
-        const double r2 = x * x + y * y;
-        const double cdist = 1 + ((k[4] * r2 + k[1]) * r2 + k[0]) * r2;
+        const double r2 = fma(x, x, y * y);
+        const double cdist = fma(fma(fma(k[4], r2, k[1]), r2, k[0]), r2, 1.0);
         const double xo = x, yo = y;
-        x = xo * cdist + 2 * k[2] * xo * yo + k[3] * (r2 + 2 * xo * xo);
+        x = fma(xo, cdist, fma(2 * k[2] * xo, yo, k[3] * fma(2 * xo, xo, r2)));
         // camera.cpp:411-412: y's tangential term uses the already-distorted x
-        y = yo * cdist + k[2] * (r2 + 2 * yo * yo) + 2 * k[3] * x * yo;
-        x = fx * x + cx;
-        y = fy * y + cy;
+        y = fma(yo, cdist, fma(k[2], fma(2 * yo, yo, r2), 2 * k[3] * x * yo));
+        x = fma(fx, x, cx);
+        y = fma(fy, y, cy);
     }
     u = x;
     v = y;
     return true;
 }
 
+// Camera::project (project/camera.cpp:380-419) of a GLOBAL point for a NON-refractive camera,
+// operation for operation as the reference evaluates it (and as oracle.cpp restates it): with
+// -fmad=false every +,*,/ below rounds exactly as on the CPU, so the integer truncation of the
+// projected coordinate agrees even when the projection lands exactly on a pixel boundary
+// (rectified pairs: y2 = v - 0.5 is an exact integer in exact arithmetic).
+__device__ __forceinline__ void cam_project_exact(const sr_camera &c, d3 pg, double &u, double &v) {
+    const d3 point = mul3(c.R, pg) + ld3(c.t);
+    const d3 p = mul3(c.K, point);
+    double x = p.x / p.z, y = p.y / p.z;
+    if (c.is_distorted) {
+        const double cx = c.K[2], cy = c.K[5], fx = c.K[0], fy = c.K[4];
+        x = (x - cx) / fx;
+        y = (y - cy) / fy;
+        const double *k = c.dist;
+        const double r2 = x * x + y * y;
+        const double cdist = 1 + ((k[4] * r2 + k[1]) * r2 + k[0]) * r2;
+        const double xo = x, yo = y;
+        x = xo * cdist + 2 * k[2] * xo * yo + k[3] * (r2 + 2 * xo * xo);
+        y = yo * cdist + k[2] * (r2 + 2 * yo * yo) + 2 * k[3] * x * yo;
+        x = fx * x + cx;
+        y = fy * y + cy;
+    }
+    u = x;
+    v = y;
+}
+
 // Camera::project of a global point.
 __device__ __forceinline__ bool cam_project(const sr_camera &c, d3 p, double &u, double &v) {
+    if (!c.is_refractive) {
+        cam_project_exact(c, p, u, v);
+        return true;
+    }
     float w0 = -1.0f, w1 = -1.0f;
     return cam_project_local(c, proj_consts(c), mul3(c.R, p) + ld3(c.t), w0, w1, u, v);
 }

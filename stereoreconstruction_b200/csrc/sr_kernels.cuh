@@ -133,7 +133,8 @@ __global__ void __launch_bounds__(128) build_kernel(const BuildArgs a) {
     const bool ray_ok = !(fabs(nd) < 1e-10);
     const double inv_nd = 1.0 / nd;
     const double nC = dot(nrm, ld3(a.C)), npn = dot(nrm, prin), nn = dot(nrm, nrm), ns = dot(nrm, src);
-    const RayInView rv = ray_in_view(a.nbr, src, dir);
+    const bool exact = !a.nbr.is_refractive;  // uniform: op-for-op IEEE path (see cam_project_exact)
+    const RayInView rv = {fmul3(a.nbr.R, src) + ld3(a.nbr.t), fmul3(a.nbr.R, dir)};
     const ProjConsts pc = proj_consts(a.nbr);
     const double scale = a.scale, shift = a.mvs ? 0.0 : -0.5;
     const int d0 = blockIdx.y * a.d_chunk;
@@ -144,23 +145,41 @@ __global__ void __launch_bounds__(128) build_kernel(const BuildArgs a) {
     for (int d = d0; d < d1; ++d) {
         int32_t tap = TAP_NONE;
         const double depth = a.depth_table[d];
-        const double dist = fma(depth, npn, nC);
-        const double t = (dist * nn - ns) * inv_nd;
-        if (ray_ok && !(t < 1e-10)) {
-            const d3 local = rv.Ls + t * rv.Ld;
-            double u, v;
-            if (cam_project_local(a.nbr, pc, local, w0, w1, u, v)) {
-                int tx = to_int_x86(fma(u, scale, shift));
-                int ty = to_int_x86(fma(v, scale, shift));
-                bool keep = true;
-                if (a.mvs) {  // multiviewstereo.cpp:787: only WHITE neighbour-mask pixels are candidates
-                    keep = tx >= 0 && ty >= 0 && tx < a.w && ty < a.h && a.nbr_mask[(size_t)ty * a.w + tx] == 255;
+        bool ok = false;
+        double u, v;
+        if (exact) {
+            // Plane3d(normal, C + normal*depth); intersect(ray, plane, p)  — reference op order
+            const d3 x0 = ld3(a.C) + depth * prin;
+            const double dist = dot(nrm, x0);
+            if (ray_ok) {
+                const double t = dot(nrm, dist * nrm - src) / nd;
+                if (!(t < 1e-10)) {
+                    cam_project_exact(a.nbr, src + t * dir, u, v);
+                    ok = true;
                 }
-                if (keep) {
-                    tx = max(-TAP_CLAMP, min(TAP_CLAMP, tx));
-                    ty = max(-TAP_CLAMP, min(TAP_CLAMP, ty));
-                    tap = (int32_t)(((uint32_t)(ty & 0xffff) << 16) | (uint32_t)(tx & 0xffff));
-                }
+            }
+        } else {
+            const double dist = fma(depth, npn, nC);
+            const double t = fma(dist, nn, -ns) * inv_nd;
+            if (ray_ok && !(t < 1e-10)) ok = cam_project_local(a.nbr, pc, faxpy(t, rv.Ld, rv.Ls), w0, w1, u, v);
+        }
+        if (ok) {
+            int tx, ty;
+            if (exact) {
+                tx = to_int_x86(u * scale + shift);
+                ty = to_int_x86(v * scale + shift);
+            } else {
+                tx = to_int_x86(fma(u, scale, shift));
+                ty = to_int_x86(fma(v, scale, shift));
+            }
+            bool keep = true;
+            if (a.mvs) {  // multiviewstereo.cpp:787: only WHITE neighbour-mask pixels are candidates
+                keep = tx >= 0 && ty >= 0 && tx < a.w && ty < a.h && a.nbr_mask[(size_t)ty * a.w + tx] == 255;
+            }
+            if (keep) {
+                tx = max(-TAP_CLAMP, min(TAP_CLAMP, tx));
+                ty = max(-TAP_CLAMP, min(TAP_CLAMP, ty));
+                tap = (int32_t)(((uint32_t)(ty & 0xffff) << 16) | (uint32_t)(tx & 0xffff));
             }
         }
         a.taps[(size_t)d * plane + pid] = tap;
@@ -508,8 +527,8 @@ __global__ void __launch_bounds__(128) match_kernel(const __grid_constant__ Matc
                             cost = (COST == SR_COST_NCC_MVS) ? 0.0 : 1000.0;
                         } else {
                             const double meanR = S1 * inv_totW;
-                            const double s1 = S3 - meanR * SD;
-                            const double s3 = S2 - 2.0 * meanR * S1 + dnact * meanR * meanR;
+                            const double s1 = fma(-meanR, SD, S3);
+                            const double s3 = fma(dnact * meanR, meanR, fma(-2.0 * meanR, S1, S2));
                             const double q = s2 * s3;
                             if (COST == SR_COST_NCC_MVS) {
                                 cost = (q < 1e-10) ? 0.0 : s1 * rsqrt(q);
@@ -525,7 +544,8 @@ __global__ void __launch_bounds__(128) match_kernel(const __grid_constant__ Matc
                             const int k = sub + G * i;
                             if (k < WN) {
                                 const double gr = base[(k / WS - R) * w + (k % WS - R)];
-                                S = fma(wt[i], fmin(120.0, fabs(c1[i] - gr)), S);
+                                const double ad = fabs(c1[i] - gr);
+                                S = fma(wt[i], (ad > 120.0) ? 120.0 : ad, S);  // keeps a NaN tap visible (fmin would not)
                             }
                         }
                         S = group_sum<G>(S, gmask);
