@@ -1,0 +1,169 @@
+"""Known-answer and self-consistency tests of the CPU oracle (SURVEY §4 tier 1): Snell round trip,
+quartic residual / numpy.roots cross-check, weight KATs, depth sampling, label-vs-curve
+consistency.  CPU only."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from oracle import oracle_api as O
+from stereoreconstruction_b200 import scenes, types as T
+from scene_util import refractive_arc_scene, rectified_scene
+
+
+def test_project_unproject_round_trip_refractive_no_distortion():
+    w, h = 64, 48
+    cams = scenes.arc_cameras(3, w, h, arc_deg=20.0, distortion=None)
+    sc = O.Scene(cams, [np.zeros((h, w, 4), np.uint8)] * 3)
+    gx, gy = np.meshgrid(np.arange(w) + 0.5, np.arange(h) + 0.5)
+    want = np.stack([gx, gy], -1).reshape(-1, 2)
+    for v in range(3):
+        rays = sc.unproject_grid(v)
+        for t in (300.0, 520.0):
+            pts = (rays[..., :3] + t * rays[..., 3:]).reshape(-1, 3)
+            for mode in (0, 1):
+                xy, ok = sc.project_points(v, pts, root_mode=mode)
+                assert ok.all()
+                assert np.abs(xy - want).max() < 1e-8
+
+
+def test_quartic_and_monotone_roots_agree_and_stats_are_clean():
+    cams, imgs, ms, surf = refractive_arc_scene(V=3, w=48, h=32)
+    sc = O.Scene(cams, imgs)
+    rays = sc.unproject_grid(0)
+    rng = np.random.RandomState(0)
+    pts = (rays[..., :3] + rng.uniform(350, 650, rays.shape[:2] + (1,)) * rays[..., 3:]).reshape(-1, 3)
+    O.stats_reset()
+    for v in (1, 2):
+        sc.project_points(v, pts, root_mode=2)
+    st = O.stats()
+    assert st["project_calls"] == 2 * pts.shape[0]
+    assert st["quartic_fail"] == 0 and st["no_root"] == 0 and st["root_mismatch"] == 0
+    assert st["max_root_diff"] < 1e-9
+
+
+def test_snell_root_against_numpy_roots():
+    L = O.lib()
+    rng = np.random.RandomState(1)
+    for _ in range(300):
+        r, d, h, n = rng.uniform(0.1, 400), rng.uniform(1, 60), rng.uniform(50, 900), rng.uniform(1.05, 1.6)
+        x = L.orc_snell_root(r, d, h, n)
+        nn, dd, rr = n * n, d * d, r * r
+        coeffs = [nn - 1, -2 * r * (nn - 1), rr * (nn - 1) + dd * nn - h * h, -2 * dd * nn * r, dd * nn * rr]
+        roots = np.roots(coeffs)
+        real = roots[np.abs(roots.imag) < 1e-9].real
+        inside = real[(real >= -1e-9) & (real <= r + 1e-9)]
+        assert inside.size == 1, (r, d, h, n, roots)
+        assert abs(inside[0] - x) < 1e-8 * max(1.0, r)
+        # residual of the un-squared Snell equation
+        g = x / np.hypot(x, d) - n * (r - x) / np.hypot(r - x, h)
+        assert abs(g) < 1e-14
+        re, im = np.empty(4), np.empty(4)
+        c5 = np.array(coeffs[::-1], dtype=np.float64)
+        assert L.orc_poly_roots4(c5.ctypes.data_as(C.POINTER(C.c_double)), re.ctypes.data_as(C.POINTER(C.c_double)),
+                                 im.ctypes.data_as(C.POINTER(C.c_double)))
+        mine = np.sort_complex(re + 1j * im)
+        assert np.allclose(mine, np.sort_complex(roots), rtol=1e-7, atol=1e-7)
+
+
+def test_weight_kats():
+    h, w = 21, 23
+    const = np.full((h, w, 4), 90, np.uint8)
+    const[..., 3] = 255
+    cam = T.make_camera(np.eye(3), np.eye(3), np.zeros(3))
+    sc = O.Scene([cam], [const])
+    for r in (1, 2, 5):
+        g = sc.weights(0, T.SR_WEIGHT_GEODESIC, r, [10], [10])[0]
+        assert (g == 1.0).all()  # constant image: every geodesic distance is 0
+        a = sc.weights(0, T.SR_WEIGHT_ADAPTIVE, r, [10], [10])[0]
+        assert a[r, r] == 1.0
+        i = np.arange(-r, r + 1)
+        want = np.exp(-np.abs(i)[:, None] / r) * np.exp(-np.abs(i)[None, :] / r)
+        assert np.allclose(a, want, rtol=1e-15)
+        # window hanging over the image corner: out-of-image taps weigh 0
+        g0 = sc.weights(0, T.SR_WEIGHT_GEODESIC, r, [0], [0])[0]
+        assert (g0[:r, :] == 0).all() and (g0[:, :r] == 0).all() and (g0[r:, r:] == 1).all()
+        a0 = sc.weights(0, T.SR_WEIGHT_ADAPTIVE, r, [0], [0])[0]
+        assert (a0[:r, :] == 0).all() and (a0[:, :r] == 0).all()
+    # a colour step: geodesic weight across the step is exp(-|step|/50)
+    img = const.copy()
+    img[:, 12:, :3] = 140
+    sc2 = O.Scene([cam], [img])
+    g = sc2.weights(0, T.SR_WEIGHT_GEODESIC, 2, [11], [10])[0]
+    step = np.sqrt(3 * 50.0 ** 2)
+    assert np.allclose(g[:, :3], 1.0) and np.allclose(g[:, 3:], np.exp(-step / 50.0))
+
+
+def test_depth_from_label():
+    L = O.lib()
+    P = T.default_params(False, 100.0, 500.0, 256)
+    d = np.array([L.orc_depth_from_label(C.byref(O.as_params(P)), k) for k in range(256)])
+    assert d[0] == 100.0 and d[-1] == 500.0
+    inv = 1.0 / d  # max = 5*min  =>  uniform in inverse depth
+    assert np.allclose(np.diff(inv), np.diff(inv)[0], rtol=1e-9)
+    P2 = T.default_params(True, 300.0, 800.0, 100)
+    d2 = np.array([L.orc_depth_from_label(C.byref(O.as_params(P2)), k) for k in range(100)])
+    assert np.allclose(np.diff(d2), 500.0 / 99)
+
+
+def test_cost_identities():
+    cams, imgs, ms, surf = rectified_scene(w=96, h=40)
+    sc = O.Scene([cams[0], cams[0]], [imgs[0], imgs[0]])
+    for kind, r in ((T.SR_WEIGHT_ADAPTIVE, 3), (T.SR_WEIGHT_GEODESIC, 2)):
+        P = T.default_params(False, 100.0, 500.0, 8, radius=r, weight_kind=kind)
+        # identical windows: NCC cost 0 (up to rounding), SAD cost 0
+        assert abs(sc.cost(P, 0, 1, 40, 20, 40, 20)) < 1e-9
+        P.cost_kind = T.SR_COST_SAD_TWOVIEW
+        assert sc.cost(P, 0, 1, 40, 20, 40, 20) == 0.0
+        P.cost_kind = T.SR_COST_NCC_MVS
+        assert abs(sc.cost(P, 0, 1, 40, 20, 40, 20) - 1.0) < 1e-12
+        # a window entirely outside the neighbour image
+        P.cost_kind = T.SR_COST_NCC_TWOVIEW
+        assert sc.cost(P, 0, 1, 40, 20, -500, 20) == 1000.0  # BAD_RET
+        P.cost_kind = T.SR_COST_NCC_MVS
+        assert sc.cost(P, 0, 1, 40, 20, -500, 20) == 0.0
+
+
+def test_label_and_curve_modes_reconstruct_the_same_surface():
+    cams, imgs, ms, surf = refractive_arc_scene(V=3, w=80, h=48, arc_deg=16.0)
+    sc = O.Scene(cams, imgs)
+    P = T.default_params(True, 430.0, 570.0, 48)
+    rays = sc.unproject_grid(1)
+    gt = (surf.hit(rays) - np.array(cams[1].C[:])) @ np.array(cams[1].prin_dir[:])
+    dl, il, _, _, _ = sc.mvs_view(P, 1, [0, 2])
+    dc, _, _, _, _ = sc.mvs_view(P, 1, [0, 2], curve_mode=True)
+    okl, okc = il >= 0, dc > 0
+    assert okl.mean() > 0.8 and okc.mean() > 0.8
+    # depth resolution of this miniature rig: one pixel of disparity = Z^2 / (f * baseline) units
+    f = cams[1].K[0]
+    base = np.linalg.norm(np.array(cams[1].C[:]) - np.array(cams[0].C[:]))
+    px = 500.0 ** 2 / (f * base)
+    assert np.median(np.abs(dl - gt)[okl]) < 0.75 * px
+    assert np.median(np.abs(dc - gt)[okc]) < 0.75 * px
+
+
+def test_mvs_curve_peaks_are_sorted_topk():
+    cams, imgs, ms, surf = refractive_arc_scene(V=3, w=48, h=32, arc_deg=16.0)
+    sc = O.Scene(cams, imgs)
+    P = T.default_params(True, 430.0, 570.0, 32)
+    d, _, b, _, peaks = sc.mvs_view(P, 1, [0, 2], curve_mode=True, want_peaks=True)
+    assert (np.diff(peaks[..., 0], axis=-1) >= 0).all()  # ascending ncc, best last
+    assert (peaks[..., -1, 1] == d).all() and (peaks[..., -1, 0] == b).all()
+    none = d == -1
+    assert (peaks[none][:, :, 0] == 0).all()
+
+
+def test_neighbour_selection_matches_numpy_restatement():
+    cams = scenes.arc_cameras(8, 64, 48)
+    sc = O.Scene(cams, [np.zeros((48, 64, 4), np.uint8)] * 8)
+    assert [[int(v) for v in r] for r in sc.select_neighbours(3)] == scenes.nearest_neighbours(cams, 3)
+
+
+def test_row_band_equals_full_run():
+    cams, imgs, ms, surf = refractive_arc_scene(V=3, w=48, h=32)
+    sc = O.Scene(cams, imgs)
+    P = T.default_params(False, 420.0, 580.0, 12, radius=2)
+    full_d, full_i, _, _ = sc.twoview_label(P, 0, 1)
+    P.row_begin, P.row_end = 10, 20
+    d, i, _, vol = sc.twoview_label(P, 0, 1, want_volume=True)
+    assert (i[10:20] == full_i[10:20]).all() and vol.shape == (10, 48, 12)
