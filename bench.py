@@ -146,6 +146,7 @@ def main():
     ap.add_argument("--workload", default="cfg4")
     ap.add_argument("--cpu-rows", type=int, default=0, help="rows of the CPU sample (0 = auto)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--views", type=int, default=0, help="only the first N reference views (profiling aid; 0 = all)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -195,8 +196,9 @@ def main():
     imgs_p = [p.numpy() for p in pinned]
     ctx.set_views(cams, imgs_p, None)
     nbrs = neighbours_for(wl)
-    my_views = [v for v in range(V) if v % world == rank]
-    units_total = V * h * w * D
+    ref_views = list(range(V if args.views <= 0 else min(V, args.views)))
+    my_views = [v for v in ref_views if v % world == rank]
+    units_total = len(ref_views) * h * w * D
 
     def step():
         for v in my_views:

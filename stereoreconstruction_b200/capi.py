@@ -12,7 +12,7 @@ import numpy as np
 from .types import SrCamera, SrParams
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_PKG, "libsr_b200.so")
+LIB_PATH = os.environ.get("SR_LIB") or os.path.join(_PKG, "libsr_b200.so")  # SR_LIB: A/B kernel variants
 _LIB = None
 
 NVCC_FLAGS = ["-std=c++17", "-O3", "-fmad=false", "-DSR_FEW_RADII", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",

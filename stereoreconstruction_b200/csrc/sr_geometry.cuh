@@ -38,6 +38,28 @@ __device__ __forceinline__ d3 fmul3(const double *M, d3 v) {
             fma(M[6], v.x, fma(M[7], v.y, M[8] * v.z))};
 }
 
+// Branch-free FP64 reciprocal / reciprocal square root for the refractive fast path: MUFU seed
+// (rcp/rsqrt.approx.ftz.f64, ~2^-22 relative) + two Newton steps -> ~1 ulp.  Arguments there are
+// finite, positive and far from the denormal range, so the IEEE special-case handling that makes
+// the library versions ~25 instructions each is not needed.
+__device__ __forceinline__ double fast_rcp(double a) {
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(a));
+    double e = fma(-a, r, 1.0);
+    r = fma(r, e, r);
+    e = fma(-a, r, 1.0);
+    return fma(r, e, r);
+}
+__device__ __forceinline__ double fast_rsqrt(double a) {
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(a));
+    const double ha = 0.5 * a;
+    double e = fma(-ha * y, y, 0.5);
+    y = fma(y, e, y);
+    e = fma(-ha * y, y, 0.5);
+    return fma(y, e, y);
+}
+
 // util/ray.cpp:78-88 (intersect) with the plane given as (unit normal, distance).
 __device__ __forceinline__ bool ray_plane(d3 src, d3 dir, d3 n, double dist, d3 &p) {
     double nd = dot(n, dir);
@@ -137,7 +159,10 @@ __device__ __forceinline__ double snell_root_fast(double r, double d, double h, 
     if (warm) x = (w0 > 0.0f ? fmaf(2.0f, w1, -w0) : w1) * rf;
     else x = nf * fabsf(df) * rf / (fabsf(hf) + nf * fabsf(df));
     x = fminf(fmaxf(x, 0.0f), rf);
-    const int iters = warm ? 2 : 5;
+    // cold start (first label of a chunk): 5 iterations; warm start with one previous ratio: 2;
+    // with the linear extrapolation from two previous ratios the start is already within ~1e-5
+    // of the root and one FP32 iteration reaches FP32 accuracy.
+    const int iters = warm ? (w0 > 0.0f ? 1 : 2) : 5;
 #pragma unroll 1
     for (int it = 0; it < iters; ++it) {
         const float rx = rf - x;
@@ -150,10 +175,11 @@ __device__ __forceinline__ double snell_root_fast(double r, double d, double h, 
     {
         const double dd = d * d, hh = h * h;
         const double rx = r - X;
-        const double ia = rsqrt(fma(X, X, dd)), ib = rsqrt(fma(rx, rx, hh));
+        const double ia = fast_rsqrt(fma(X, X, dd)), ib = fast_rsqrt(fma(rx, rx, hh));
         const double g = fma(X, ia, -(n * rx) * ib);
-        const double gp = fma(dd * ia, ia * ia, (n * hh) * ib * (ib * ib));
-        const double step = g / gp;
+        const float gpf = fmaf(ddf * (float)ia, (float)(ia * ia), (nf * hhf) * (float)ib * (float)(ib * ib));
+        // the step is ~1e-6: an FP32-accurate 1/g' (1e-7 relative) changes x by ~1e-13, i.e. ~1e-11 px
+        const double step = g * (double)__frcp_rn(gpf);
         X -= step;
         if (!(fabs(step) <= 2e-5 * r) || !(X >= 0.0 && X <= r)) X = snell_root_robust(r, d, h, n, -1.0);
     }
@@ -192,7 +218,7 @@ __device__ __forceinline__ bool cam_project_local(const sr_camera &c, const Proj
         const d3 radv = faxpy(-a, N, local);
         const double rr = fdot(radv, radv);
         if (!(rr > 0.0)) return false;  // dir = radv/r is NaN in the reference: no root is accepted
-        const double ir = rsqrt(rr);
+        const double ir = fast_rsqrt(rr);
         const double r = rr * ir;
         const double x = snell_root_fast(r, c.plane_d, fabs(a) - c.plane_d, c.n, w0, w1);
         if (!(x == x)) return false;
@@ -200,7 +226,7 @@ __device__ __forceinline__ bool cam_project_local(const sr_camera &c, const Proj
         point = faxpy(x * ir, radv, c.plane_d * N);
     }
     const d3 p = fmul3(c.K, point);
-    const double iz = 1.0 / p.z;
+    const double iz = c.is_refractive ? fast_rcp(p.z) : 1.0 / p.z;
     double x = p.x * iz, y = p.y * iz;
     if (c.is_distorted) {
         const double cx = c.K[2], cy = c.K[5], fx = c.K[0], fy = c.K[4];

@@ -53,6 +53,32 @@ __global__ void kg(const T *plane, int w, int h, double *out, int n) {
     }
     out[blockIdx.x * blockDim.x + threadIdx.x] = acc;
 }
+// dependent-issue latency: one warp per SM, one chain
+__global__ void klat(double *out, long long *cyc, double a, double b, int n, int op) {
+    double x = threadIdx.x * 1e-3 + 1.0;
+    long long t0 = clock64();
+    if (op == 0) for (int i = 0; i < n; ++i) x = fma(x, a, b);
+    else if (op == 1) for (int i = 0; i < n; ++i) x = x + a;
+    else for (int i = 0; i < n; ++i) x = x * a;
+    long long t1 = clock64();
+    out[blockIdx.x * blockDim.x + threadIdx.x] = x;
+    if (threadIdx.x == 0 && blockIdx.x == 0) *cyc = t1 - t0;
+}
+// dependent chains with W warps per SMSP and C chains per thread: FP64 issue rate vs parallelism
+template <int C>
+__global__ void kchains(double *out, double a, double b, int n) {
+    double x[C];
+#pragma unroll
+    for (int c = 0; c < C; ++c) x[c] = threadIdx.x * 1e-3 + c;
+    for (int i = 0; i < n; ++i) {
+#pragma unroll
+        for (int c = 0; c < C; ++c) x[c] = fma(x[c], a, b);
+    }
+    double s = 0;
+#pragma unroll
+    for (int c = 0; c < C; ++c) s += x[c];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
 template <typename F>
 float timeit(F f) {
     cudaEvent_t a, b;
@@ -74,6 +100,20 @@ int main() {
     ms = timeit([&] { k<4><<<blocks, threads>>>(out, 1.0000001, 1e-9, ITER); }); printf("%-28s %8.3f ms  %8.2f Gop/s\n", names[4], ms, nops / ms / 1e6);
     ms = timeit([&] { k<5><<<blocks, threads>>>(out, 1.0000001, 1e-9, ITER); }); printf("%-28s %8.3f ms  %8.2f Gop/s\n", names[5], ms, nops / ms / 1e6);
     ms = timeit([&] { kf<<<blocks, threads>>>((float *)out, 1.0000001f, 1e-9f, ITER); }); printf("%-28s %8.3f ms  %8.2f Gop/s\n", "FFMA", ms, nops / ms / 1e6);
+    long long *cyc; cudaMallocManaged(&cyc, 8);
+    for (int op = 0; op < 3; ++op) {
+        klat<<<1, 32>>>(out, cyc, 1.0000001, 1e-9, 8192, op); cudaDeviceSynchronize();
+        printf("dependent %s latency: %.2f cycles\n", op == 0 ? "DFMA" : op == 1 ? "DADD" : "DMUL", (double)*cyc / 8192);
+    }
+    {
+        const int n = 8192;
+        float m;
+        m = timeit([&] { kchains<1><<<148 * 2, 128>>>(out, 1.0000001, 1e-9, n); }); printf("8 warps/SM x 1 chain : %7.2f Gop/s\n", 148.0 * 2 * 128 * n * 1 / m / 1e6);
+        m = timeit([&] { kchains<2><<<148 * 2, 128>>>(out, 1.0000001, 1e-9, n); }); printf("8 warps/SM x 2 chains: %7.2f Gop/s\n", 148.0 * 2 * 128 * n * 2 / m / 1e6);
+        m = timeit([&] { kchains<4><<<148 * 2, 128>>>(out, 1.0000001, 1e-9, n); }); printf("8 warps/SM x 4 chains: %7.2f Gop/s\n", 148.0 * 2 * 128 * n * 4 / m / 1e6);
+        m = timeit([&] { kchains<8><<<148 * 2, 128>>>(out, 1.0000001, 1e-9, n); }); printf("8 warps/SM x 8 chains: %7.2f Gop/s\n", 148.0 * 2 * 128 * n * 8 / m / 1e6);
+        m = timeit([&] { kchains<4><<<148 * 4, 128>>>(out, 1.0000001, 1e-9, n); }); printf("16 warps/SM x 4 chains: %7.2f Gop/s\n", 148.0 * 4 * 128 * n * 4 / m / 1e6);
+    }
     const int w = 1920, h = 1080;
     double *pd; float *pf; unsigned short *ps;
     cudaMalloc(&pd, w * h * 8); cudaMalloc(&pf, w * h * 4); cudaMalloc(&ps, w * h * 2);
