@@ -398,20 +398,28 @@ __device__ __noinline__ double slow_cost(const MatchArgs &a, const double *__res
 }
 
 #ifndef SR_MATCH_MINBLOCKS
-#define SR_MATCH_MINBLOCKS 3
+#define SR_MATCH_MINBLOCKS 2
 #endif
-#ifndef SR_MATCH_PAIR
-#define SR_MATCH_PAIR 1
-#endif
+constexpr int TAP_CHUNK = 16;  // labels per cp.async stage of the tap stream
+
+__device__ __forceinline__ void cp_async4(void *smem_dst, const void *gmem_src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gmem_src));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+    asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
 
 // R: window radius; G: lanes cooperating on one reference pixel (taps are dealt round-robin to
 // the G lanes and live in registers); COST: SR_COST_*.
 //
 // Inner-loop shape (what the FP64 pipe sees): per (label, neighbour) one streaming pass over the
 // lane's taps — gr = neighbour gray; p = w*gr; S1 += p; S2 += p*p; S3 += (w*dl)*gr — i.e. 4
-// FP64 instructions and one 8-byte L1 load per tap, then a ~15-instruction tail.  Two labels are
-// evaluated concurrently (they share the weight registers and have independent accumulator
-// chains and tails), which is what keeps the FP64 pipe fed at 12 warps/SM.
+// FP64 instructions and one 8-byte L1 load per tap, then a ~25-instruction tail.
+// The tap volume streams HBM -> shared memory through a two-stage cp.async ring (TAP_CHUNK
+// labels per stage, each thread fetching its own pixel's taps: a warp moves 128 contiguous
+// bytes per label), so the HBM latency of the volume is never on a warp's critical path.
 template <int R, int G, int COST>
 __global__ void __launch_bounds__(128, (R <= 2) ? SR_MATCH_MINBLOCKS : 2) match_kernel(const __grid_constant__ MatchArgs a) {
     constexpr int WS = 2 * R + 1;
@@ -419,6 +427,7 @@ __global__ void __launch_bounds__(128, (R <= 2) ? SR_MATCH_MINBLOCKS : 2) match_
     constexpr int TPL = (WN + G - 1) / G;
     constexpr bool NCC = (COST != SR_COST_SAD_TWOVIEW);
     constexpr int PIX_PER_BLOCK = 128 / G;
+    __shared__ int32_t tap_ring[2][TAP_CHUNK][128];
 
     const int lane = threadIdx.x & 31;
     const int sub = threadIdx.x % G;
@@ -485,57 +494,83 @@ __global__ void __launch_bounds__(128, (R <= 2) ? SR_MATCH_MINBLOCKS : 2) match_
     const bool degenerate = (COST == SR_COST_SAD_TWOVIEW) ? (nact <= 4 || totW <= 1e-10) : (totW < 1e-10);
     const double dnact = (double)nact;
 
-    // tail of the fast path: sums -> cost.  Returns NaN iff a neighbour tap was invalid (NaN),
-    // in which case the exact tap filter (slow_cost) decides.  A legitimately evaluated cost is
-    // never NaN (two-view: NaN -> 120 as std::min does; MVS: q < 1e-10 -> 0).
-    auto finish = [&](double S1, double S2, double S3) -> double {
-        if (NCC) {
-            if (S1 != S1 || S3 != S3) return qnan();
-            if (degenerate) return (COST == SR_COST_NCC_MVS) ? 0.0 : 1000.0;
-            const double meanR = S1 * inv_totW;
-            const double s1 = fma(-meanR, SD, S3);
-            const double s3 = fma(dnact * meanR, meanR, fma(-2.0 * meanR, S1, S2));
-            const double q = s2 * s3;
-            if (COST == SR_COST_NCC_MVS) return (q < 1e-10) ? 0.0 : s1 * rsqrt(q);
-            const double v = 255.0 * (1.0 - fabs(s1) * rsqrt(q));
-            return (v < 120.0) ? v : 120.0;
-        } else {
-            if (S1 != S1) return qnan();
-            return degenerate ? 1000.0 : S1 * inv_totW;
-        }
-    };
     // one label, fast path: whole neighbour window in bounds; one streaming pass over the taps.
+    // Returns NaN iff a neighbour tap was invalid (NaN) — then the exact tap filter (slow_cost)
+    // decides.  A legitimately evaluated cost is never NaN (two-view: NaN -> 120 as std::min
+    // does; MVS: q < 1e-10 -> 0).
     auto fast_one = [&](const double *__restrict__ base) -> double {
         double S1 = 0.0, S2 = 0.0, S3 = 0.0, T1 = 0.0, T2 = 0.0, T3 = 0.0;
+        if (G == 1) {
+            // thread-per-pixel: row pointers + compile-time column offsets
 #pragma unroll
-        for (int i = 0; i < TPL; ++i) {
-            const int k = sub + G * i;
-            if (k < WN) {
-                const double gr = base[(k / WS - R) * w + (k % WS - R)];
-                if (NCC) {
-                    const double p = wt[i] * gr;
-                    if (i & 1) {
-                        T1 += p;
-                        T2 = fma(p, p, T2);
-                        T3 = fma(c1[i], gr, T3);
+            for (int row = 0; row < WS; ++row) {
+                const double *__restrict__ rp = base + (row - R) * w;
+#pragma unroll
+                for (int col = 0; col < WS; ++col) {
+                    const int i = row * WS + col;
+                    const double gr = rp[col - R];
+                    if (NCC) {
+                        const double p = wt[i] * gr;
+                        if (i & 1) {
+                            T1 += p;
+                            T2 = fma(p, p, T2);
+                            T3 = fma(c1[i], gr, T3);
+                        } else {
+                            S1 += p;
+                            S2 = fma(p, p, S2);
+                            S3 = fma(c1[i], gr, S3);
+                        }
                     } else {
-                        S1 += p;
-                        S2 = fma(p, p, S2);
-                        S3 = fma(c1[i], gr, S3);
+                        const double ad = fabs(c1[i] - gr);  // (ad > 120 ? 120 : ad) keeps a NaN tap visible
+                        if (i & 1) T1 = fma(wt[i], (ad > 120.0) ? 120.0 : ad, T1);
+                        else S1 = fma(wt[i], (ad > 120.0) ? 120.0 : ad, S1);
                     }
-                } else {
-                    const double ad = fabs(c1[i] - gr);  // (ad > 120 ? 120 : ad) keeps a NaN tap visible
-                    if (i & 1) T1 = fma(wt[i], (ad > 120.0) ? 120.0 : ad, T1);
-                    else S1 = fma(wt[i], (ad > 120.0) ? 120.0 : ad, S1);
+                }
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < TPL; ++i) {
+                const int k = sub + G * i;
+                if (k < WN) {
+                    const double gr = base[(k / WS - R) * w + (k % WS - R)];
+                    if (NCC) {
+                        const double p = wt[i] * gr;
+                        if (i & 1) {
+                            T1 += p;
+                            T2 = fma(p, p, T2);
+                            T3 = fma(c1[i], gr, T3);
+                        } else {
+                            S1 += p;
+                            S2 = fma(p, p, S2);
+                            S3 = fma(c1[i], gr, S3);
+                        }
+                    } else {
+                        const double ad = fabs(c1[i] - gr);
+                        if (i & 1) T1 = fma(wt[i], (ad > 120.0) ? 120.0 : ad, T1);
+                        else S1 = fma(wt[i], (ad > 120.0) ? 120.0 : ad, S1);
+                    }
                 }
             }
         }
         S1 = group_sum<G>(S1 + T1, gmask);
-        if (NCC) {
-            S2 = group_sum<G>(S2 + T2, gmask);
-            S3 = group_sum<G>(S3 + T3, gmask);
+        if (!NCC) {
+            if (S1 != S1) return qnan();
+            return degenerate ? 1000.0 : S1 * inv_totW;
         }
-        return finish(S1, S2, S3);
+        S2 = group_sum<G>(S2 + T2, gmask);
+        S3 = group_sum<G>(S3 + T3, gmask);
+        // gray_pix (COST NCC_MVS) holds no NaN inside the image: no invalid-tap test needed there
+        if (COST != SR_COST_NCC_MVS && (S1 != S1 || S3 != S3)) return qnan();
+        if (degenerate) return (COST == SR_COST_NCC_MVS) ? 0.0 : 1000.0;
+        const double meanR = S1 * inv_totW;
+        const double s1 = fma(-meanR, SD, S3);
+        const double s3 = fma(dnact * meanR, meanR, fma(-2.0 * meanR, S1, S2));
+        const double q = s2 * s3;
+        if (COST == SR_COST_NCC_MVS) return (q < 1e-10) ? 0.0 : s1 * fast_rsqrt(q);
+        // two-view: 255*(1 - |s1|/sqrt(q)); q <= 0 or denormal takes the IEEE path (inf/NaN -> 120)
+        const double rs = (q > 1e-280 && q < 1e280) ? fast_rsqrt(q) : rsqrt(q);
+        const double v = 255.0 * (1.0 - fabs(s1) * rs);
+        return (v < 120.0) ? v : 120.0;
     };
 
     // ---- label sweep -------------------------------------------------------------------------
@@ -543,101 +578,62 @@ __global__ void __launch_bounds__(128, (R <= 2) ? SR_MATCH_MINBLOCKS : 2) match_
     double bestC = 0.0, bestD = -1.0;              // MVS selection
     int bestIdx = SR_INDEX_NONE;
     const bool mvs = a.select_kind == SR_SELECT_MVS;
-    // stage (3): winner-take-all, fused
-    auto wta = [&](int d, double cost) {
-        if (mvs) {  // multiviewstereo.cpp:589-602,654-660
-            if (cost > a.ncc_threshold) {
-                const double depth = a.depth_table[d];
-                if (bestIdx == SR_INDEX_NONE || cost > bestC || (cost == bestC && depth > bestD)) {
-                    bestC = cost;
-                    bestD = depth;
-                    bestIdx = d;
-                }
-            }
-        } else {  // twoviewstereo.cpp:320-325
-            if (cost + 1e-10 < minCost) {
-                secondBest = minCost;
-                minCost = cost;
-                bestIdx = d;
-            }
+    const int D = a.D;
+    const int nchunks = (D + TAP_CHUNK - 1) / TAP_CHUNK;
+    const int total_chunks = nchunks * a.num_nbrs;
+    const int tid = threadIdx.x;
+    // stage `c` of the tap stream = labels [ (c % nchunks)*TAP_CHUNK, +TAP_CHUNK ) of neighbour c / nchunks
+    auto issue_chunk = [&](int c) {
+        if (c < total_chunks) {
+            const int j = c / nchunks, d0 = (c % nchunks) * TAP_CHUNK;
+            const int32_t *src = a.taps + ((size_t)j * D + d0) * npix + pid;
+            const int nl = min(TAP_CHUNK, D - d0);
+            for (int l = 0; l < nl; ++l) cp_async4(&tap_ring[c & 1][l][tid], src + (size_t)l * npix);
         }
+        cp_async_commit();
     };
-    auto in_bounds = [&](int tx, int ty) { return tx >= R && ty >= R && tx < w - R && ty < h - R; };
+    issue_chunk(0);
 
 #pragma unroll 1
-    for (int j = 0; j < a.num_nbrs; ++j) {
+    for (int c = 0; c < total_chunks; ++c) {
+        issue_chunk(c + 1);
+        cp_async_wait<1>();  // stage c has landed (this thread's own copies; no cross-thread sharing)
+        const int j = c / nchunks, d0 = (c % nchunks) * TAP_CHUNK;
+        const int nl = min(TAP_CHUNK, D - d0);
         const double *__restrict__ gR = a.grayR[j];
-        const int32_t *__restrict__ taps = a.taps + (size_t)j * a.D * npix + pid;
-        float *vol = a.out_volume ? a.out_volume + (size_t)j * a.D * npix + pid : nullptr;
-        const int D = a.D;
-        // the tap volume streams from HBM: keep the next two label pairs in flight
-        int32_t q0 = taps[0], q1 = (1 < D) ? taps[npix] : TAP_NONE;
-        int32_t q2 = (2 < D) ? taps[2 * npix] : TAP_NONE, q3 = (3 < D) ? taps[3 * npix] : TAP_NONE;
+        float *vol = a.out_volume ? a.out_volume + ((size_t)j * D + d0) * npix + pid : nullptr;
 #pragma unroll 1
-        for (int d = 0; d < D; d += 2) {
-            const int32_t tapA = q0, tapB = q1;
-            q0 = q2;
-            q1 = q3;
-            q2 = (d + 4 < D) ? taps[(size_t)(d + 4) * npix] : TAP_NONE;
-            q3 = (d + 5 < D) ? taps[(size_t)(d + 5) * npix] : TAP_NONE;
-            const int txA = (int)(short)(tapA & 0xffff), tyA = (int)(short)((uint32_t)tapA >> 16);
-            const int txB = (int)(short)(tapB & 0xffff), tyB = (int)(short)((uint32_t)tapB >> 16);
-            const bool evA = tapA != TAP_NONE, evB = tapB != TAP_NONE;
-            const bool fastA = evA && in_bounds(txA, tyA), fastB = evB && in_bounds(txB, tyB);
-            double costA = qnan(), costB = qnan();
-            if (SR_MATCH_PAIR && NCC && fastA && fastB) {
-                // both labels on the fast path: interleave them (independent chains and tails)
-                const double *__restrict__ bA = gR + ((size_t)tyA * w + txA);
-                const double *__restrict__ bB = gR + ((size_t)tyB * w + txB);
-                double A1 = 0.0, A2 = 0.0, A3 = 0.0, B1 = 0.0, B2 = 0.0, B3 = 0.0;
-                double E1 = 0.0, E2 = 0.0, E3 = 0.0, F1 = 0.0, F2 = 0.0, F3 = 0.0;
-#pragma unroll
-                for (int i = 0; i < TPL; ++i) {
-                    const int k = sub + G * i;
-                    if (k < WN) {
-                        const int off = (k / WS - R) * w + (k % WS - R);
-                        const double ga = bA[off], gb = bB[off];
-                        const double pa = wt[i] * ga, pb = wt[i] * gb;
-                        if (i & 1) {
-                            E1 += pa;
-                            E2 = fma(pa, pa, E2);
-                            E3 = fma(c1[i], ga, E3);
-                            F1 += pb;
-                            F2 = fma(pb, pb, F2);
-                            F3 = fma(c1[i], gb, F3);
-                        } else {
-                            A1 += pa;
-                            A2 = fma(pa, pa, A2);
-                            A3 = fma(c1[i], ga, A3);
-                            B1 += pb;
-                            B2 = fma(pb, pb, B2);
-                            B3 = fma(c1[i], gb, B3);
+        for (int l = 0; l < nl; ++l) {
+            const int32_t tap = tap_ring[c & 1][l][tid];
+            double cost = qnan();
+            if (tap != TAP_NONE) {
+                const int tx = (int)(short)(tap & 0xffff), ty = (int)(short)((uint32_t)tap >> 16);
+                if (tx >= R && ty >= R && tx < w - R && ty < h - R) cost = fast_one(gR + ((size_t)ty * w + tx));
+                // windows touching a border / an invalid pixel: the reference's exact tap filter
+                if (cost != cost) cost = slow_cost<R, G, COST>(a, gR, x, y, tx, ty, pid, sub, gmask);
+                // ---- stage (3): winner-take-all, fused ----
+                const int d = d0 + l;
+                if (mvs) {  // multiviewstereo.cpp:589-602,654-660
+                    if (cost > a.ncc_threshold) {
+                        const double depth = a.depth_table[d];
+                        if (bestIdx == SR_INDEX_NONE || cost > bestC || (cost == bestC && depth > bestD)) {
+                            bestC = cost;
+                            bestD = depth;
+                            bestIdx = d;
                         }
                     }
+                } else {  // twoviewstereo.cpp:320-325
+                    if (cost + 1e-10 < minCost) {
+                        secondBest = minCost;
+                        minCost = cost;
+                        bestIdx = d;
+                    }
                 }
-                A1 = group_sum<G>(A1 + E1, gmask);
-                A2 = group_sum<G>(A2 + E2, gmask);
-                A3 = group_sum<G>(A3 + E3, gmask);
-                B1 = group_sum<G>(B1 + F1, gmask);
-                B2 = group_sum<G>(B2 + F2, gmask);
-                B3 = group_sum<G>(B3 + F3, gmask);
-                costA = finish(A1, A2, A3);
-                costB = finish(B1, B2, B3);
-            } else {
-                if (fastA) costA = fast_one(gR + ((size_t)tyA * w + txA));
-                if (fastB) costB = fast_one(gR + ((size_t)tyB * w + txB));
             }
-            // windows touching a border / an invalid pixel: the reference's exact tap filter
-            if (evA && costA != costA) costA = slow_cost<R, G, COST>(a, gR, x, y, txA, tyA, pid, sub, gmask);
-            if (evB && costB != costB) costB = slow_cost<R, G, COST>(a, gR, x, y, txB, tyB, pid, sub, gmask);
-            if (evA) wta(d, costA);
-            if (evB) wta(d + 1, costB);
-            if (vol && sub == 0) {
-                vol[(size_t)d * npix] = (float)costA;
-                if (d + 1 < D) vol[(size_t)(d + 1) * npix] = (float)costB;
-            }
+            if (vol && sub == 0) vol[(size_t)l * npix] = (float)cost;
         }
     }
+    cp_async_wait<0>();
 
     if (sub == 0) {
         if (mvs) {
