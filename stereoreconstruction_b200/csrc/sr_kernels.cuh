@@ -402,9 +402,21 @@ __device__ __noinline__ double slow_cost(const MatchArgs &a, const double *__res
 #endif
 constexpr int TAP_CHUNK = 16;  // labels per cp.async stage of the tap stream
 
-__device__ __forceinline__ void cp_async4(void *smem_dst, const void *gmem_src) {
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gmem_src));
+// The tap volume is read exactly once: fetch it with an L2 evict-first policy so that it does
+// not push the (re-used) neighbour gray planes out of the 126 MB L2.
+__device__ __forceinline__ uint64_t l2_evict_first_policy() {
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
 }
+__device__ __forceinline__ void cp_async4(void *smem_dst, const void *gmem_src, uint64_t pol) {
+    asm volatile("cp.async.ca.shared.global.L2::cache_hint [%0], [%1], 4, %2;" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)),
+                 "l"(gmem_src), "l"(pol));
+}
+__device__ __forceinline__ void prefetch_l1(const void *p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+#ifndef SR_MATCH_PREFETCH
+#define SR_MATCH_PREFETCH 2  // labels of look-ahead for the window prefetch (0 = off)
+#endif
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;"); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() {
@@ -582,13 +594,14 @@ __global__ void __launch_bounds__(128, (R <= 2) ? SR_MATCH_MINBLOCKS : 2) match_
     const int nchunks = (D + TAP_CHUNK - 1) / TAP_CHUNK;
     const int total_chunks = nchunks * a.num_nbrs;
     const int tid = threadIdx.x;
+    const uint64_t pol = l2_evict_first_policy();
     // stage `c` of the tap stream = labels [ (c % nchunks)*TAP_CHUNK, +TAP_CHUNK ) of neighbour c / nchunks
     auto issue_chunk = [&](int c) {
         if (c < total_chunks) {
             const int j = c / nchunks, d0 = (c % nchunks) * TAP_CHUNK;
             const int32_t *src = a.taps + ((size_t)j * D + d0) * npix + pid;
             const int nl = min(TAP_CHUNK, D - d0);
-            for (int l = 0; l < nl; ++l) cp_async4(&tap_ring[c & 1][l][tid], src + (size_t)l * npix);
+            for (int l = 0; l < nl; ++l) cp_async4(&tap_ring[c & 1][l][tid], src + (size_t)l * npix, pol);
         }
         cp_async_commit();
     };
@@ -605,6 +618,21 @@ __global__ void __launch_bounds__(128, (R <= 2) ? SR_MATCH_MINBLOCKS : 2) match_
 #pragma unroll 1
         for (int l = 0; l < nl; ++l) {
             const int32_t tap = tap_ring[c & 1][l][tid];
+            if (SR_MATCH_PREFETCH > 0 && l + SR_MATCH_PREFETCH < nl) {
+                // the window of a label a few steps ahead: pull its rows into L1 now, so that the
+                // L2/HBM latency of a window entering a new cache line is off the critical path
+                const int32_t tp = tap_ring[c & 1][l + SR_MATCH_PREFETCH][tid];
+                const int px = (int)(short)(tp & 0xffff), py = (int)(short)((uint32_t)tp >> 16);
+                if (tp != TAP_NONE && px >= R && py >= R && px < w - R && py < h - R) {
+                    const double *pb = gR + ((size_t)(py - R) * w + (px - R));
+                    if (G == 1) {
+#pragma unroll
+                        for (int row = 0; row < WS; ++row) prefetch_l1(pb + row * w);
+                    } else {
+                        for (int row = sub; row < WS; row += G) prefetch_l1(pb + row * w);
+                    }
+                }
+            }
             double cost = qnan();
             if (tap != TAP_NONE) {
                 const int tx = (int)(short)(tap & 0xffff), ty = (int)(short)((uint32_t)tap >> 16);
