@@ -398,7 +398,10 @@ __device__ __noinline__ double slow_cost(const MatchArgs &a, const double *__res
 }
 
 #ifndef SR_MATCH_MINBLOCKS
-#define SR_MATCH_MINBLOCKS 2
+#define SR_MATCH_MINBLOCKS 4
+#endif
+#ifndef SR_MATCH_SMEM_C1
+#define SR_MATCH_SMEM_C1 1
 #endif
 constexpr int TAP_CHUNK = 16;  // labels per cp.async stage of the tap stream
 
@@ -415,7 +418,7 @@ __device__ __forceinline__ void cp_async4(void *smem_dst, const void *gmem_src, 
 }
 __device__ __forceinline__ void prefetch_l1(const void *p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 #ifndef SR_MATCH_PREFETCH
-#define SR_MATCH_PREFETCH 2  // labels of look-ahead for the window prefetch (0 = off)
+#define SR_MATCH_PREFETCH 0  // labels of look-ahead for an explicit L1 window prefetch (measured: no gain, off)
 #endif
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;"); }
 template <int N>
@@ -440,6 +443,11 @@ __global__ void __launch_bounds__(128, (R <= 2) ? SR_MATCH_MINBLOCKS : 2) match_
     constexpr bool NCC = (COST != SR_COST_SAD_TWOVIEW);
     constexpr int PIX_PER_BLOCK = 128 / G;
     __shared__ int32_t tap_ring[2][TAP_CHUNK][128];
+    // thread-per-pixel variant: the second per-tap constant (w*dl / gl) lives in shared memory,
+    // [tap][thread] so a warp's LDS.64 is conflict-free; this halves the register arrays and lets
+    // 4 blocks (16 warps) share an SM, which is what hides the FP64 issue latency.
+    constexpr bool SMEM_C1 = (G == 1) && (SR_MATCH_SMEM_C1 != 0);
+    __shared__ double c1s[SMEM_C1 ? TPL : 1][128];
 
     const int lane = threadIdx.x & 31;
     const int sub = threadIdx.x % G;
@@ -503,6 +511,10 @@ __global__ void __launch_bounds__(128, (R <= 2) ? SR_MATCH_MINBLOCKS : 2) match_
         s2 = group_sum<G>(s2, gmask);
         SD = group_sum<G>(SD, gmask);
     }
+    if (SMEM_C1) {
+#pragma unroll
+        for (int i = 0; i < TPL; ++i) c1s[i][threadIdx.x] = c1[i];  // only this thread reads its column
+    }
     const bool degenerate = (COST == SR_COST_SAD_TWOVIEW) ? (nact <= 4 || totW <= 1e-10) : (totW < 1e-10);
     const double dnact = (double)nact;
 
@@ -521,19 +533,20 @@ __global__ void __launch_bounds__(128, (R <= 2) ? SR_MATCH_MINBLOCKS : 2) match_
                 for (int col = 0; col < WS; ++col) {
                     const int i = row * WS + col;
                     const double gr = rp[col - R];
+                    const double ci = SMEM_C1 ? c1s[i][threadIdx.x] : c1[i];
                     if (NCC) {
                         const double p = wt[i] * gr;
                         if (i & 1) {
                             T1 += p;
                             T2 = fma(p, p, T2);
-                            T3 = fma(c1[i], gr, T3);
+                            T3 = fma(ci, gr, T3);
                         } else {
                             S1 += p;
                             S2 = fma(p, p, S2);
-                            S3 = fma(c1[i], gr, S3);
+                            S3 = fma(ci, gr, S3);
                         }
                     } else {
-                        const double ad = fabs(c1[i] - gr);  // (ad > 120 ? 120 : ad) keeps a NaN tap visible
+                        const double ad = fabs(ci - gr);  // (ad > 120 ? 120 : ad) keeps a NaN tap visible
                         if (i & 1) T1 = fma(wt[i], (ad > 120.0) ? 120.0 : ad, T1);
                         else S1 = fma(wt[i], (ad > 120.0) ? 120.0 : ad, S1);
                     }
