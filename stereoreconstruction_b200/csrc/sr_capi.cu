@@ -465,6 +465,7 @@ int sr_run_view(sr_ctx *ctx, int ref, const int32_t *nbrs, int nn) {
         ma.D = D;
         ma.num_nbrs = nn;
         ma.select_kind = P.select_kind;
+        ma.depth_up = (P.max_depth >= P.min_depth) ? 1 : 0;
         ma.second_best_factor = P.second_best_factor;
         ma.ncc_threshold = P.ncc_threshold;
         cudaError_t e = launch_match(P.radius, P.cost_kind, ma, st);

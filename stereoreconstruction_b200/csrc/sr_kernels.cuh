@@ -320,6 +320,7 @@ struct MatchArgs {
     float *out_volume;              // [nbr][D][rows][w] or null
     int w, h, row0, rows, D, num_nbrs;
     int select_kind;
+    int depth_up;                   // depth_table is increasing in the label (max_depth > min_depth)
     double second_best_factor, ncc_threshold;
 };
 
@@ -398,7 +399,7 @@ __device__ __noinline__ double slow_cost(const MatchArgs &a, const double *__res
 }
 
 #ifndef SR_MATCH_MINBLOCKS
-#define SR_MATCH_MINBLOCKS 4
+#define SR_MATCH_MINBLOCKS 3
 #endif
 #ifndef SR_MATCH_SMEM_C1
 #define SR_MATCH_SMEM_C1 1
@@ -600,10 +601,11 @@ __global__ void __launch_bounds__(128, (R <= 2) ? SR_MATCH_MINBLOCKS : 2) match_
 
     // ---- label sweep -------------------------------------------------------------------------
     double minCost = dinf(), secondBest = dinf();  // two-view selection
-    double bestC = 0.0, bestD = -1.0;              // MVS selection
+    double bestC = 0.0;                            // MVS selection
     int bestIdx = SR_INDEX_NONE;
     const bool mvs = a.select_kind == SR_SELECT_MVS;
     const int D = a.D;
+    const bool depth_up = a.depth_up != 0;
     const int nchunks = (D + TAP_CHUNK - 1) / TAP_CHUNK;
     const int total_chunks = nchunks * a.num_nbrs;
     const int tid = threadIdx.x;
@@ -654,12 +656,14 @@ __global__ void __launch_bounds__(128, (R <= 2) ? SR_MATCH_MINBLOCKS : 2) match_
                 if (cost != cost) cost = slow_cost<R, G, COST>(a, gR, x, y, tx, ty, pid, sub, gmask);
                 // ---- stage (3): winner-take-all, fused ----
                 const int d = d0 + l;
-                if (mvs) {  // multiviewstereo.cpp:589-602,654-660
+                if (mvs) {  // multiviewstereo.cpp:589-602,654-660: max over (ncc, depth) pairs
+                    // depthFromLabel is strictly monotone in the label, so "depth > bestD" is decided
+                    // on the indices (deeper == d > bestIdx iff depth_up); the table is read once at
+                    // the end instead of once per label on the critical path.
                     if (cost > a.ncc_threshold) {
-                        const double depth = a.depth_table[d];
-                        if (bestIdx == SR_INDEX_NONE || cost > bestC || (cost == bestC && depth > bestD)) {
+                        const bool deeper = depth_up ? (d > bestIdx) : (d < bestIdx);
+                        if (bestIdx == SR_INDEX_NONE || cost > bestC || (cost == bestC && deeper)) {
                             bestC = cost;
-                            bestD = depth;
                             bestIdx = d;
                         }
                     }
@@ -679,7 +683,7 @@ __global__ void __launch_bounds__(128, (R <= 2) ? SR_MATCH_MINBLOCKS : 2) match_
     if (sub == 0) {
         if (mvs) {
             a.out_index[pix] = bestIdx;
-            a.out_depth[pix] = bestD;
+            a.out_depth[pix] = (bestIdx >= 0) ? a.depth_table[bestIdx] : -1.0;
             a.out_best[pix] = bestC;
         } else {
             double depth = (bestIdx >= 0) ? a.depth_table[bestIdx] : qnan();
