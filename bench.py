@@ -226,6 +226,8 @@ def main():
     ms = ev0.elapsed_time(ev1)
     clocks = sampler.finish()
     stages = ctx.stage_ms()
+    if os.environ.get("SR_MATCH_STATS"):
+        print("match stats:", ctx.match_stats(), file=sys.stderr)
     ctx.set_profiling(False)
     launches = ctx.launch_count() - launches0
     if world > 1:

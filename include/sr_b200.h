@@ -120,6 +120,10 @@ int64_t sr_launch_count(const sr_ctx *ctx);
  * {build ms, match ms, build bands, match launches} accumulated since its last call. */
 int sr_set_profiling(sr_ctx *ctx, int on);
 int sr_get_stage_ms(sr_ctx *ctx, double *out4);
+/* Debug counters of the screened MVS match kernel (FP32 screen + FP64 verify), accumulated since
+ * sr_ctx_create when the environment has SR_MATCH_STATS=1: out8[0] pixels, [1] labels screened in
+ * FP32, [2] labels forced to FP64, [3] FP64 verifications, [4] pixels evaluated in FP64 only. */
+int sr_get_match_stats(sr_ctx *ctx, uint64_t *out8);
 
 /* ---- inputs -----------------------------------------------------------------*/
 /* Replaces the image/mask ingestion of TwoViewStereo::TwoViewStereo

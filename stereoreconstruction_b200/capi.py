@@ -18,12 +18,12 @@ _LIB = None
 NVCC_FLAGS = ["-std=c++17", "-O3", "-fmad=false", "-DSR_FEW_RADII", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
               "--shared", "-Xcompiler", "-fPIC"]
 SOURCES = ["csrc/sr_capi.cu"]
-HEADERS = ["csrc/sr_geometry.cuh", "csrc/sr_kernels.cuh", "csrc/sr_match_dispatch.cuh",
+HEADERS = ["csrc/sr_geometry.cuh", "csrc/sr_kernels.cuh", "csrc/sr_match_dispatch.cuh", "csrc/sr_match_screen.cuh",
            "../include/sr_b200.h"]
 
 EXPORTS = [
     "sr_ctx_create", "sr_ctx_destroy", "sr_last_error", "sr_request_cancel", "sr_clear_cancel",
-    "sr_set_stream", "sr_params_default", "sr_launch_count", "sr_set_profiling", "sr_get_stage_ms", "sr_set_views", "sr_set_params",
+    "sr_set_stream", "sr_params_default", "sr_launch_count", "sr_set_profiling", "sr_get_stage_ms", "sr_get_match_stats", "sr_set_views", "sr_set_params",
     "sr_run_view", "sr_run_view_curve", "sr_select_neighbours", "sr_cross_check", "sr_synchronize",
     "sr_get_depth_index", "sr_get_depth", "sr_get_best_cost", "sr_get_cost_volume", "sr_set_depth",
     "sr_get_depth_image", "sr_unproject_grid", "sr_project_points", "sr_compute_weights",
@@ -108,6 +108,12 @@ class Context:
     def _ck(self, rc):
         if rc != 0:
             raise SrError(f"sr error {rc}: {self._L.sr_last_error(self._h).decode()}")
+
+    def match_stats(self):
+        out = np.zeros(8, np.uint64)
+        self._ck(self._L.sr_get_match_stats(self._h, _p(out)))
+        return dict(pixels=int(out[0]), screened=int(out[1]), forced=int(out[2]), verified=int(out[3]),
+                    fp64_only_pixels=int(out[4]))
 
     # -- setup -------------------------------------------------------------------------
     def set_stream(self, cuda_stream_ptr):

@@ -24,6 +24,7 @@ struct ViewDev {
     uchar4 *rgba = nullptr;
     uint8_t *mask = nullptr;
     double *gray_pix = nullptr, *gray_two = nullptr, *gray_msk = nullptr, *edges = nullptr;
+    float *gray_pix_f = nullptr;
     int32_t *index = nullptr;
     double *depth = nullptr, *best = nullptr;
 };
@@ -102,6 +103,8 @@ struct sr_ctx {
     size_t scratch_cap = 0;
     int64_t launches = 0;
     size_t tap_budget = (size_t)8 << 30;
+    unsigned long long *d_stats = nullptr;  // SR_MATCH_STATS=1: counters of the screened match kernel
+    bool use_screen = true;  // SR_MATCH_SCREEN=0: MVS selection through the all-FP64 match_kernel (A/B aid)
     ncclComm_t comm = nullptr;
     int rank = 0, nranks = 1;
     // per-stage CUDA-event timing (sr_set_profiling): [begin, after build, after match] per band
@@ -141,6 +144,7 @@ void free_views(sr_ctx *c) {
         dfree(v.rgba);
         dfree(v.mask);
         dfree(v.gray_pix);
+        dfree(v.gray_pix_f);
         dfree(v.gray_two);
         dfree(v.gray_msk);
         dfree(v.edges);
@@ -201,6 +205,11 @@ int sr_ctx_create(int device, sr_ctx **out) {
     }
     c->stream = c->own_stream;
     if (const char *mb = getenv("SR_TAP_BUDGET_MB")) c->tap_budget = (size_t)atoll(mb) << 20;
+    if (const char *sc = getenv("SR_MATCH_SCREEN")) c->use_screen = atoi(sc) != 0;
+    if (const char *ss = getenv("SR_MATCH_STATS")) {
+        if (atoi(ss) != 0 && cudaMalloc(&c->d_stats, 8 * sizeof(unsigned long long)) == cudaSuccess)
+            cudaMemset(c->d_stats, 0, 8 * sizeof(unsigned long long));
+    }
     *out = c;
     return SR_OK;
 }
@@ -215,6 +224,7 @@ void sr_ctx_destroy(sr_ctx *c) {
     dfree(c->d_taps);
     dfree(c->d_weights);
     dfree(c->d_volume);
+    dfree(c->d_stats);
     if (c->d_scratch) cudaFree(c->d_scratch);
     cudaStreamDestroy(c->own_stream);
     delete c;
@@ -271,6 +281,7 @@ int sr_set_views(sr_ctx *ctx, int V, const sr_camera *cams, const uint8_t *const
             CK(cudaMalloc(&v.rgba, n * 4));
             CK(cudaMalloc(&v.mask, n));
             CK(cudaMalloc(&v.gray_pix, n * 8));
+            CK(cudaMalloc(&v.gray_pix_f, n * 4));
             CK(cudaMalloc(&v.gray_two, n * 8));
             CK(cudaMalloc(&v.gray_msk, n * 8));
             CK(cudaMalloc(&v.edges, n * 8 * 4));
@@ -298,7 +309,7 @@ int sr_set_views(sr_ctx *ctx, int V, const sr_camera *cams, const uint8_t *const
         if (mask8 && mask8[i]) CK(cudaMemcpyAsync(v.mask, mask8[i], n, cudaMemcpyHostToDevice, ctx->stream));
         else CK(cudaMemsetAsync(v.mask, 255, n, ctx->stream));
         prep_view_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(v.rgba, v.mask, w, h, v.gray_pix,
-                                                                             v.gray_two, v.gray_msk, v.edges);
+                                                                             v.gray_two, v.gray_msk, v.edges, v.gray_pix_f);
         CKL();
         // results start as "not computed": NaN depth (twoviewstereo.cpp:118-119), index NONE
         CK(cudaMemsetAsync(v.depth, 0xff, n * 8, ctx->stream));
@@ -451,6 +462,7 @@ int sr_run_view(sr_ctx *ctx, int ref, const int32_t *nbrs, int nn) {
             const ViewDev &B = ctx->views[nbrs[j]];
             ma.grayR[j] = (P.cost_kind == SR_COST_NCC_MVS) ? B.gray_pix
                           : (P.cost_kind == SR_COST_NCC_TWOVIEW) ? B.gray_two : B.gray_msk;
+            ma.grayRf[j] = B.gray_pix_f;
         }
         ma.taps = ctx->d_taps;
         ma.depth_table = ctx->d_depth_table;
@@ -466,6 +478,8 @@ int sr_run_view(sr_ctx *ctx, int ref, const int32_t *nbrs, int nn) {
         ma.num_nbrs = nn;
         ma.select_kind = P.select_kind;
         ma.depth_up = (P.max_depth >= P.min_depth) ? 1 : 0;
+        ma.use_screen = ctx->use_screen ? 1 : 0;
+        ma.stats = ctx->d_stats;
         ma.second_best_factor = P.second_best_factor;
         ma.ncc_threshold = P.ncc_threshold;
         cudaError_t e = launch_match(P.radius, P.cost_kind, ma, st);
@@ -503,6 +517,18 @@ int sr_get_stage_ms(sr_ctx *ctx, double *out4) {
     }
     for (cudaEvent_t e : ctx->prof_events) cudaEventDestroy(e);
     ctx->prof_events.clear();
+    return SR_OK;
+}
+
+// Debug counters of match_mvs_screen_kernel accumulated since context creation (SR_MATCH_STATS=1):
+// out[0] pixels, [1] labels screened in FP32, [2] labels forced to FP64, [3] FP64 verifications,
+// [4] pixels whose reference window is evaluated in FP64 only.
+int sr_get_match_stats(sr_ctx *ctx, uint64_t *out8) {
+    if (!ctx || !out8) return SR_ERR_INVALID;
+    if (!ctx->d_stats) return fail(ctx, SR_ERR_STATE, "match statistics are off (set SR_MATCH_STATS=1 before sr_ctx_create)");
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaStreamSynchronize(ctx->stream));
+    CK(cudaMemcpy(out8, ctx->d_stats, 8 * sizeof(uint64_t), cudaMemcpyDeviceToHost));
     return SR_OK;
 }
 

@@ -57,7 +57,8 @@ __device__ __forceinline__ double color_dist(uchar4 a, uchar4 b) {
 //              other end is outside the image (an edge the geodesic sweeps may not use).
 __global__ void prep_view_kernel(const uchar4 *__restrict__ rgba, const uint8_t *__restrict__ mask, int w, int h,
                                  double *__restrict__ gray_pix, double *__restrict__ gray_two,
-                                 double *__restrict__ gray_msk, double *__restrict__ edges) {
+                                 double *__restrict__ gray_msk, double *__restrict__ edges,
+                                 float *__restrict__ gray_pix_f) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= w * h) return;
     const int x = i % w, y = i / w;
@@ -65,6 +66,7 @@ __global__ void prep_view_kernel(const uchar4 *__restrict__ rgba, const uint8_t 
     const double g = gray_of(c);
     const bool white = mask[i] == 255;
     gray_pix[i] = g;
+    gray_pix_f[i] = (float)g;  // FP32 copy read by the screening pass of match_mvs_screen_kernel
     gray_msk[i] = white ? g : qnan();
     gray_two[i] = (white && x + 1 < w && y + 1 < h) ? g : qnan();
     const size_t n = (size_t)w * h;
@@ -311,6 +313,7 @@ struct MatchArgs {
     const uint8_t *maskL;           // reference view mask
     const double *grayL;            // reference taps  (gray_pix for C1, gray_two for C2/C3)
     const double *grayR[SR_MAX_NBRS];  // neighbour taps (gray_pix C1, gray_two C2, gray_msk C3)
+    const float *grayRf[SR_MAX_NBRS];  // FP32 copies of gray_pix (screening pass, MVS selection only)
     const double *W;                // [WN][rows*w] support weights of this band
     const int32_t *taps;            // [nbr][D][rows][w]
     const double *depth_table;      // [D]
@@ -321,6 +324,8 @@ struct MatchArgs {
     int w, h, row0, rows, D, num_nbrs;
     int select_kind;
     int depth_up;                   // depth_table is increasing in the label (max_depth > min_depth)
+    unsigned long long *stats;      // optional [8]: pixels, screened, forced, verified, all_slow (debug)
+    int use_screen;                 // MVS selection: FP32 screen + FP64 verify (sr_match_screen.cuh)
     double second_best_factor, ncc_threshold;
 };
 

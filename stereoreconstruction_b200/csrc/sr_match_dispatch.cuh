@@ -3,6 +3,7 @@
 // registers per tap) stays within the register file: ceil((2R+1)^2 / G) <= 35.
 #pragma once
 #include "sr_kernels.cuh"
+#include "sr_match_screen.cuh"
 
 namespace sr {
 
@@ -20,8 +21,21 @@ cudaError_t launch_match_rc(const MatchArgs &a, cudaStream_t st) {
     return cudaGetLastError();
 }
 
+// MultiViewStereo selection with its own NCC and no kept cost volume: FP32 screen + FP64 verify.
+template <int R>
+cudaError_t launch_match_screen(const MatchArgs &a, cudaStream_t st) {
+    constexpr int G = LanesFor<R>::G;
+    constexpr int PPB = 128 / G;
+    const size_t npix = (size_t)a.rows * a.w;
+    const unsigned grid = (unsigned)((npix + PPB - 1) / PPB);
+    match_mvs_screen_kernel<R, G><<<grid, 128, 0, st>>>(a);
+    return cudaGetLastError();
+}
+
 template <int R>
 cudaError_t launch_match_r(int cost, const MatchArgs &a, cudaStream_t st) {
+    if (cost == SR_COST_NCC_MVS && a.select_kind == SR_SELECT_MVS && !a.out_volume && a.use_screen)
+        return launch_match_screen<R>(a, st);
     switch (cost) {
         case SR_COST_NCC_TWOVIEW: return launch_match_rc<R, SR_COST_NCC_TWOVIEW>(a, st);
         case SR_COST_NCC_MVS: return launch_match_rc<R, SR_COST_NCC_MVS>(a, st);

@@ -1,0 +1,366 @@
+// sr_match_screen.cuh — stages (2)+(3) for the MultiViewStereo selection rule, organised as an
+// FP32 screening pass with an FP64 verification of the few labels that can win.
+//
+// What the reference computes per reference pixel (stereo/multiviewstereo.cpp:583-602,654-660):
+// the weighted NCC (cost_ncc, :113-189) of every candidate, keeps those with ncc > 0.95 and
+// returns the candidate that is largest under (ncc, depth) ordering.  Only the *winner* and its
+// exact cost leave the kernel, so all but a handful of the D x N_nbr evaluations only need to be
+// accurate enough to prove that they cannot be the winner:
+//
+//   screen (FP32)  ncc32 of every (label, neighbour) by the reference's own two-pass form
+//                  t_i = w_i*g_i - meanR;  s3 = sum t_i^2;  s1 = sum dl_i*t_i;  ncc = s1/sqrt(s2*s3)
+//                  on FP32 copies of the gray planes — 25 LDG.32 + 100 FFMA per 5x5 window, the
+//                  weights, dl_i and the window taps all in registers.  |ncc32 - ncc64| is far
+//                  below SCREEN_EPS as long as the window is well conditioned (s2, s3 >= WN, i.e.
+//                  the weighted deviations have an RMS of at least one gray level); windows that
+//                  are not, or that touch the image border or hold an inactive tap, are FORCEd
+//                  into the verified set.
+//   candidates     a label can only win if ncc32 > threshold - EPS and ncc32 >= (running maximum
+//                  of ncc32) - 2*EPS: the true winner W satisfies ncc64(W) >= ncc64(X) for all X,
+//                  hence ncc32(W) >= ncc32(X) - 2*err.  Candidates go to a small per-pixel queue
+//                  in shared memory.
+//   verify (FP64)  when a queue fills (and at the end) the whole warp evaluates its queued
+//                  candidates with slow_cost — the reference's exact two-pass tap filter in FP64,
+//                  operation for operation — and applies the reference's selection rule to them
+//                  in the original order.  The result is the reference's winner, its depth and its
+//                  FP64 cost; the screening precision never reaches the output.
+//
+// Consecutive labels whose projections truncate to the same integer tap have the same cost by
+// construction; the screening pass re-uses the previous value and the queue keeps one entry per
+// distinct tap (carrying the label the tie-break would pick).
+#pragma once
+#include <type_traits>
+#include "sr_kernels.cuh"
+
+namespace sr {
+
+constexpr float SCREEN_EPS = 2e-4f;
+constexpr float SCREEN_FORCE = 3.0e38f;  // "must be verified in FP64" marker (|ncc| <= 1 otherwise)
+constexpr int SCREEN_QCAP = 8;
+
+template <int G>
+__device__ __forceinline__ float group_sum_f(float v, unsigned gmask) {
+#pragma unroll
+    for (int o = G / 2; o > 0; o >>= 1) v += __shfl_xor_sync(gmask, v, o);
+    return v;
+}
+
+// cost_ncc of stereo/multiviewstereo.cpp:113-189 in FP64 for the common case "both windows
+// inside their images, every tap active" — the reference's two passes, tap order and operation
+// order (no FMA contraction: the library is built with -fmad=false), with the label-independent
+// left-window quantities (meanL, sum of weights, s2) computed once per pixel in the same order.
+// G == 1 is bit-identical to the reference; G > 1 sums the lanes' partial sums in a butterfly.
+template <int R, int G>
+__device__ __noinline__ double verify_cost_mvs(const MatchArgs &a, const double *__restrict__ gR, int x, int y, int tx,
+                                               int ty, int pid, int sub, unsigned gmask, double meanL, double totW,
+                                               double s2) {
+    constexpr int WS = 2 * R + 1, WN = WS * WS;
+    const int w = a.w;
+    const size_t npix = (size_t)a.rows * w;
+    const double *__restrict__ Wp = a.W + pid;
+    const double *__restrict__ bl = a.grayL + ((size_t)y * w + x);
+    const double *__restrict__ br = gR + ((size_t)ty * w + tx);
+    double mR = 0.0;
+#pragma unroll 5
+    for (int k = sub; k < WN; k += G) {
+        const int o = (k / WS - R) * w + (k % WS - R);
+        mR += Wp[(size_t)k * npix] * br[o];
+    }
+    mR = group_sum<G>(mR, gmask) / totW;
+    double q1 = 0.0, q3 = 0.0;
+#pragma unroll 5
+    for (int k = sub; k < WN; k += G) {
+        const int o = (k / WS - R) * w + (k % WS - R);
+        const double wt = Wp[(size_t)k * npix];
+        const double pl = wt * bl[o] - meanL, pr = wt * br[o] - mR;
+        q1 += pl * pr;
+        q3 += pr * pr;
+    }
+    q1 = group_sum<G>(q1, gmask);
+    q3 = group_sum<G>(q3, gmask);
+    return (s2 * q3 < 1e-10) ? 0.0 : q1 / sqrt(s2 * q3);
+}
+
+#ifndef SR_SCREEN_MINBLOCKS
+#define SR_SCREEN_MINBLOCKS 4
+#endif
+
+template <int R, int G>
+__global__ void __launch_bounds__(128, (R <= 2) ? SR_SCREEN_MINBLOCKS : 2)
+    match_mvs_screen_kernel(const __grid_constant__ MatchArgs a) {
+    constexpr int COST = SR_COST_NCC_MVS;
+    constexpr int WS = 2 * R + 1;
+    constexpr int WN = WS * WS;
+    constexpr int TPL = (WN + G - 1) / G;
+    constexpr int PIX_PER_BLOCK = 128 / G;
+    __shared__ int32_t tap_ring[2][TAP_CHUNK][128];
+    __shared__ int32_t q_lab[SCREEN_QCAP][128];  // (neighbour << 16) | label
+    __shared__ int32_t q_tap[SCREEN_QCAP][128];
+    __shared__ float q_c32[SCREEN_QCAP][128];
+
+    const int tid = threadIdx.x;
+    const int lane = tid & 31;
+    const int sub = tid % G;
+    const unsigned gmask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << (lane & ~(G - 1)));
+    const int w = a.w, h = a.h;
+    const int npix_i = a.rows * w;
+    const size_t npix = (size_t)npix_i;
+    const int pid_raw = blockIdx.x * PIX_PER_BLOCK + tid / G;
+    const bool in_band = pid_raw < npix_i;
+    const int pid = in_band ? pid_raw : npix_i - 1;  // out-of-band lanes shadow the last pixel (no writes)
+    const int x = pid % w, y = a.row0 + pid / w;
+    const size_t pix = (size_t)y * w + x;
+    // Lanes stay in the loops (warp-wide votes below); `alive` gates all work and all writes.
+    const bool alive = in_band && a.maskL[pix] == 255;
+    if (in_band && !alive && sub == 0) {  // multiviewstereo.cpp:559,565: masked-out pixels stay INF
+        a.out_index[pix] = SR_INDEX_MASKED;
+        a.out_depth[pix] = dinf();
+        a.out_best[pix] = qnan();
+    }
+
+    // ---- reference-window invariants, FP64 (once per pixel) ----------------------------------
+    float wtf[TPL], dlf[TPL];
+    bool all_slow = false, has_inactive = false;
+    unsigned long long actmask = 0ull;  // bit i: this lane's i-th tap is active (TPL <= 35)
+    float s2f = 0.0f, inv_totWf = 0.0f;
+    double meanL_x = 0.0, totW_x = 0.0, s2_x = 0.0;  // exact (reference order) left-window quantities
+    {
+        double wt[TPL], gl[TPL];
+        double totW = 0.0, SL = 0.0;
+        int ninact = 0;
+#pragma unroll
+        for (int i = 0; i < TPL; ++i) {
+            const int k = sub + G * i;
+            const int row = k / WS - R, col = k % WS - R;
+            const int xl = x + col, yl = y + row;
+            double g = qnan(), wv = 0.0;
+            if (alive && k < WN && xl >= 0 && yl >= 0 && xl < w && yl < h) {
+                g = a.grayL[(size_t)yl * w + xl];
+                wv = a.W[(size_t)k * npix + pid];
+            }
+            const bool active = (g == g) && (wv > 1e-10);
+            wt[i] = active ? wv : 0.0;
+            gl[i] = active ? g : 0.0;
+            if (active) {
+                actmask |= 1ull << i;
+                totW += wv;
+                SL += wv * g;
+            } else if (k < WN) {
+                ++ninact;
+            }
+        }
+        totW = group_sum<G>(totW, gmask);
+        SL = group_sum<G>(SL, gmask);
+        ninact = group_sum_i<G>(ninact, gmask);
+        const double meanL = SL / totW;
+        double s2 = 0.0;
+#pragma unroll
+        for (int i = 0; i < TPL; ++i) {
+            const double dl = (wt[i] > 0.0) ? wt[i] * gl[i] - meanL : 0.0;
+            s2 += dl * dl;
+            wtf[i] = (float)wt[i];
+            dlf[i] = (float)dl;
+        }
+        s2 = group_sum<G>(s2, gmask);
+        // An ill-conditioned reference side is evaluated only by the exact FP64 filter.  Inactive
+        // taps (outside the image, weight <= 1e-10) carry w = dl = 0 through the screen and their
+        // t_i is masked out of s3 (screen_one<true>, taken only by the warps that hold such a pixel).
+        all_slow = !(totW >= 1e-10) || !(s2 >= (double)WN) || !(s2 < 1e30);
+        has_inactive = ninact != 0;
+        s2f = (float)s2;
+        inv_totWf = (float)(1.0 / totW);
+        meanL_x = meanL;
+        totW_x = totW;
+        s2_x = s2;
+    }
+
+    // ---- FP32 screening of one label: returns ncc32 or SCREEN_FORCE ---------------------------
+    auto screen_one = [&](const float *__restrict__ base, auto masked_tag) -> float {
+        constexpr bool MASKED = decltype(masked_tag)::value;
+        float g[TPL];
+        float S1a = 0.0f, S1b = 0.0f;
+        if (G == 1) {
+#pragma unroll
+            for (int row = 0; row < WS; ++row) {
+                const float *__restrict__ rp = base + (row - R) * w;
+#pragma unroll
+                for (int col = 0; col < WS; ++col) {
+                    const int i = row * WS + col;
+                    g[i] = rp[col - R];
+                    if (i & 1) S1b = fmaf(wtf[i], g[i], S1b);
+                    else S1a = fmaf(wtf[i], g[i], S1a);
+                }
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < TPL; ++i) {
+                const int k = sub + G * i;
+                g[i] = 0.0f;
+                if (k < WN) g[i] = base[(k / WS - R) * w + (k % WS - R)];
+                if (i & 1) S1b = fmaf(wtf[i], g[i], S1b);
+                else S1a = fmaf(wtf[i], g[i], S1a);
+            }
+        }
+        const float S1 = group_sum_f<G>(S1a + S1b, gmask);
+        const float mR = S1 * inv_totWf;
+        float s3a = 0.0f, s3b = 0.0f, s1a = 0.0f, s1b = 0.0f;
+#pragma unroll
+        for (int i = 0; i < TPL; ++i) {
+            float t = fmaf(wtf[i], g[i], -mR);
+            if (MASKED) {
+                // inactive or padding tap -> 0, branch- and predicate-free: bfe.s32 of one bit is 0 / ~0
+                const unsigned word = (i < 32) ? (unsigned)actmask : (unsigned)(actmask >> 32);
+                int m;
+                asm("bfe.s32 %0, %1, %2, 1;" : "=r"(m) : "r"(word), "r"(i & 31));
+                t = __int_as_float(__float_as_int(t) & m);
+            } else if (G > 1 && sub + G * i >= WN) {
+                t = 0.0f;  // padding taps of the last round
+            }
+            if (i & 1) {
+                s3b = fmaf(t, t, s3b);
+                s1b = fmaf(dlf[i], t, s1b);
+            } else {
+                s3a = fmaf(t, t, s3a);
+                s1a = fmaf(dlf[i], t, s1a);
+            }
+        }
+        const float s3 = group_sum_f<G>(s3a + s3b, gmask);
+        const float s1 = group_sum_f<G>(s1a + s1b, gmask);
+        // ill-conditioned or non-finite neighbour window: FP64 decides
+        if (!(s3 >= (float)WN) || !(s3 < 1e30f)) return SCREEN_FORCE;
+        return s1 * rsqrtf(s2f * s3);
+    };
+
+    // ---- exact state (FP64) and candidate queue -----------------------------------------------
+    double bestC = 0.0;
+    int bestIdx = SR_INDEX_NONE;
+    const bool depth_up = a.depth_up != 0;
+    int n_verified = 0, n_forced = 0, n_screened = 0;  // a.stats only
+    int qn = 0;
+    const float thr_lo = (float)a.ncc_threshold - SCREEN_EPS;
+    float best32 = thr_lo;  // running maximum of the screened ncc (never below the threshold bound)
+
+    auto flush = [&]() {
+        const int nmax = __reduce_max_sync(0xffffffffu, qn);
+#pragma unroll 1
+        for (int q = 0; q < nmax; ++q) {
+            if (q < qn) {  // uniform within a pixel's lane group
+                const int lab = q_lab[q][tid], tap = q_tap[q][tid];
+                const int j = lab >> 16, d = lab & 0xffff;
+                const int tx = (int)(short)(tap & 0xffff), ty = (int)(short)((uint32_t)tap >> 16);
+                const bool inside = tx >= R && ty >= R && tx < w - R && ty < h - R;
+                const double cost = (inside && !all_slow && !has_inactive)
+                                        ? verify_cost_mvs<R, G>(a, a.grayR[j], x, y, tx, ty, pid, sub, gmask, meanL_x, totW_x, s2_x)
+                                        : slow_cost<R, G, COST>(a, a.grayR[j], x, y, tx, ty, pid, sub, gmask);
+                ++n_verified;
+                if (cost > a.ncc_threshold) {  // multiviewstereo.cpp:589-602,654-660
+                    const bool deeper = depth_up ? (d > bestIdx) : (d < bestIdx);
+                    if (bestIdx == SR_INDEX_NONE || cost > bestC || (cost == bestC && deeper)) {
+                        bestC = cost;
+                        bestIdx = d;
+                    }
+                }
+            }
+        }
+        qn = 0;
+        // the verified maximum is a valid (and tighter) floor for the screen
+        if (bestIdx != SR_INDEX_NONE) best32 = fmaxf(best32, (float)bestC - SCREEN_EPS);
+    };
+
+    // ---- label sweep -------------------------------------------------------------------------
+    const int D = a.D;
+    const int nchunks = (D + TAP_CHUNK - 1) / TAP_CHUNK;
+    const int total_chunks = nchunks * a.num_nbrs;
+    const uint64_t pol = l2_evict_first_policy();
+    auto issue_chunk = [&](int c) {
+        if (c < total_chunks && alive) {
+            const int j = c / nchunks, d0 = (c % nchunks) * TAP_CHUNK;
+            const int32_t *src = a.taps + ((size_t)j * D + d0) * npix + pid;
+            const int nl = min(TAP_CHUNK, D - d0);
+            for (int l = 0; l < nl; ++l) cp_async4(&tap_ring[c & 1][l][tid], src + (size_t)l * npix, pol);
+        }
+        cp_async_commit();
+    };
+    issue_chunk(0);
+
+    int prevTap = TAP_NONE;
+    float prevC = 0.0f;
+#pragma unroll 1
+    for (int c = 0; c < total_chunks; ++c) {
+        issue_chunk(c + 1);
+        cp_async_wait<1>();
+        const int j = c / nchunks, d0 = (c % nchunks) * TAP_CHUNK;
+        const int nl = min(TAP_CHUNK, D - d0);
+        const float *__restrict__ gRf = a.grayRf[j];
+        if (d0 == 0) prevTap = TAP_NONE;  // a new neighbour view starts
+#pragma unroll 1
+        for (int l = 0; l < nl; ++l) {
+            const int32_t tap = alive ? tap_ring[c & 1][l][tid] : TAP_NONE;
+            if (tap != TAP_NONE) {
+                float c32;
+                if (tap == prevTap) {
+                    c32 = prevC;  // same integer tap as the previous label: same cost
+                } else {
+                    const int tx = (int)(short)(tap & 0xffff), ty = (int)(short)((uint32_t)tap >> 16);
+                    c32 = SCREEN_FORCE;
+                    if (!all_slow && tx >= R && ty >= R && tx < w - R && ty < h - R) {
+                        const float *base = gRf + ((size_t)ty * w + tx);
+                        c32 = has_inactive ? screen_one(base, std::true_type{}) : screen_one(base, std::false_type{});
+                    }
+                    prevTap = tap;
+                    prevC = c32;
+                    if (c32 == SCREEN_FORCE) ++n_forced;
+                    else ++n_screened;
+                }
+                if (c32 >= best32 - SCREEN_EPS) {  // candidate (FORCE always is)
+                    const int d = d0 + l;
+                    if (qn > 0 && q_tap[qn - 1][tid] == tap && (q_lab[qn - 1][tid] >> 16) == j) {
+                        // equal cost by construction: the tie-break picks the deeper label
+                        if (depth_up) q_lab[qn - 1][tid] = (j << 16) | d;
+                    } else {
+                        if (c32 != SCREEN_FORCE && c32 - SCREEN_EPS > best32) {
+                            // new running maximum: queued labels more than 2*EPS below it cannot win
+                            best32 = c32 - SCREEN_EPS;
+                            const float floor32 = best32 - SCREEN_EPS;
+                            int kept = 0;
+                            for (int q = 0; q < qn; ++q) {
+                                const float cq = q_c32[q][tid];
+                                if (cq >= floor32) {
+                                    if (kept != q) {
+                                        q_c32[kept][tid] = cq;
+                                        q_lab[kept][tid] = q_lab[q][tid];
+                                        q_tap[kept][tid] = q_tap[q][tid];
+                                    }
+                                    ++kept;
+                                }
+                            }
+                            qn = kept;
+                        }
+                        q_lab[qn][tid] = (j << 16) | d;
+                        q_tap[qn][tid] = tap;
+                        q_c32[qn][tid] = c32;
+                        ++qn;
+                    }
+                }
+            }
+            if (__any_sync(0xffffffffu, qn == SCREEN_QCAP)) flush();
+        }
+    }
+    cp_async_wait<0>();
+    flush();
+
+    if (a.stats && alive && sub == 0) {
+        atomicAdd(a.stats + 0, 1ull);
+        atomicAdd(a.stats + 1, (unsigned long long)n_screened);
+        atomicAdd(a.stats + 2, (unsigned long long)n_forced);
+        atomicAdd(a.stats + 3, (unsigned long long)n_verified);
+        if (all_slow) atomicAdd(a.stats + 4, 1ull);
+    }
+    if (alive && sub == 0) {
+        a.out_index[pix] = bestIdx;
+        a.out_depth[pix] = (bestIdx >= 0) ? a.depth_table[bestIdx] : -1.0;
+        a.out_best[pix] = bestC;
+    }
+}
+
+}  // namespace sr

@@ -207,3 +207,49 @@ def test_cross_check_mvs(arc, ctx):
     for g, o in zip(after, want):
         assert ((g == o) | (np.isnan(g) & np.isnan(o))).mean() > 1 - 1e-4
     assert sum(np.isfinite(a).sum() for a in after) > 0
+
+
+@pytest.mark.parametrize("weight", [T.SR_WEIGHT_ADAPTIVE, T.SR_WEIGHT_GEODESIC])
+@pytest.mark.parametrize("radius", [2, 3, 5])
+def test_mvs_screen_path_matches_oracle(arc, ctx, weight, radius):
+    """The production MVS path (no kept volume): FP32 screen + FP64 verify (sr_match_screen.cuh).
+    The verify step is the reference's exact tap filter, so index, depth AND winning cost must
+    equal the oracle's (cost to FP64 rounding of the geodesic/adaptive exp(), 1e-12)."""
+    cams, imgs, ms, sc = arc
+    ctx.set_views(cams, imgs, ms)
+    nb = ctx.select_neighbours(3)
+    P = T.default_params(True, 420.0, 580.0, 48, radius=radius, weight_kind=weight)
+    ctx.set_params(P)
+    for ref in (1, 3):
+        ctx.run_view(ref, nb[ref])
+        gi, gd, gb = ctx.depth_index(ref), ctx.depth(ref), ctx.best_cost(ref)
+        od, oi, ob, _, _ = sc.mvs_view(P, ref, nb[ref])
+        mism = gi != oi
+        assert mism.mean() <= 1e-4, f"index mismatch rate {mism.mean()}"
+        same = ~mism
+        assert ((gd == od) | (np.isnan(gd) & np.isnan(od)))[same].all()
+        lab = same & (gi >= 0)
+        assert lab.mean() > 0.1
+        assert np.abs(gb[lab] - ob[lab]).max() <= 1e-12
+
+
+def test_mvs_screen_equals_all_fp64_kernel(monkeypatch):
+    """A/B on a larger unmasked scene: the screened path and the all-FP64 match_kernel pick the
+    same label at every pixel (the screen only prunes labels that cannot win)."""
+    cams, imgs, ms, surf = refractive_arc_scene(V=4, w=320, h=200, arc_deg=25.0, cell=6.0)
+    P = T.default_params(True, 420.0, 580.0, 96)
+    out = []
+    for flag in ("0", "1"):
+        monkeypatch.setenv("SR_MATCH_SCREEN", flag)
+        c = capi.Context(0)
+        c.set_views(cams, imgs, None)
+        c.set_params(P)
+        nb = c.select_neighbours(3)
+        c.run_view(1, nb[1])
+        out.append((c.depth_index(1).copy(), c.best_cost(1).copy()))
+        c.close()
+    (i0, b0), (i1, b1) = out
+    assert (i0 >= 0).mean() > 0.3
+    assert (i0 == i1).all(), f"{(i0 != i1).sum()} pixels differ"
+    lab = i0 >= 0
+    assert np.abs(b0[lab] - b1[lab]).max() <= 1e-9
