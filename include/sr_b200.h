@@ -122,7 +122,9 @@ int sr_set_profiling(sr_ctx *ctx, int on);
 int sr_get_stage_ms(sr_ctx *ctx, double *out4);
 /* Debug counters of the screened MVS match kernel (FP32 screen + FP64 verify), accumulated since
  * sr_ctx_create when the environment has SR_MATCH_STATS=1: out8[0] pixels, [1] labels screened in
- * FP32, [2] labels forced to FP64, [3] FP64 verifications, [4] pixels evaluated in FP64 only. */
+ * FP32, [2] labels forced to FP64, [3] FP64 verifications, [4] pixels evaluated in FP64 only,
+ * [5] bit pattern (low 32 bits, IEEE float) of the largest |ncc32 - ncc64| seen on a verified label,
+ * [6] verified labels whose FP32 value lay outside its error bar (must be 0). */
 int sr_get_match_stats(sr_ctx *ctx, uint64_t *out8);
 
 /* ---- inputs -----------------------------------------------------------------*/

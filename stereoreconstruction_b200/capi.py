@@ -113,7 +113,9 @@ class Context:
         out = np.zeros(8, np.uint64)
         self._ck(self._L.sr_get_match_stats(self._h, _p(out)))
         return dict(pixels=int(out[0]), screened=int(out[1]), forced=int(out[2]), verified=int(out[3]),
-                    fp64_only_pixels=int(out[4]))
+                    fp64_only_pixels=int(out[4]),
+                    max_screen_err=float(np.array([out[5]], np.uint64).view(np.uint32)[0:1].view(np.float32)[0]),
+                    outside_error_bar=int(out[6]))
 
     # -- setup -------------------------------------------------------------------------
     def set_stream(self, cuda_stream_ptr):

@@ -10,15 +10,14 @@
 //   screen (FP32)  ncc32 of every (label, neighbour) by the reference's own two-pass form
 //                  t_i = w_i*g_i - meanR;  s3 = sum t_i^2;  s1 = sum dl_i*t_i;  ncc = s1/sqrt(s2*s3)
 //                  on FP32 copies of the gray planes — 25 LDG.32 + 100 FFMA per 5x5 window, the
-//                  weights, dl_i and the window taps all in registers.  |ncc32 - ncc64| is far
-//                  below SCREEN_EPS as long as the window is well conditioned (s2, s3 >= WN, i.e.
-//                  the weighted deviations have an RMS of at least one gray level); windows that
-//                  are not, or that touch the image border or hold an inactive tap, are FORCEd
+//                  weights, dl_i and the window taps all in registers.  Every screened value
+//                  carries an error bar eps (SCREEN_EPS_*, by conditioning of the two windows);
+//                  ill-conditioned windows and windows touching the neighbour's border are FORCEd
 //                  into the verified set.
-//   candidates     a label can only win if ncc32 > threshold - EPS and ncc32 >= (running maximum
-//                  of ncc32) - 2*EPS: the true winner W satisfies ncc64(W) >= ncc64(X) for all X,
-//                  hence ncc32(W) >= ncc32(X) - 2*err.  Candidates go to a small per-pixel queue
-//                  in shared memory.
+//   candidates     lower32 = max(threshold, max over labels of ncc32 - eps) is a proven lower
+//                  bound of the winning ncc64, so a label can only win if ncc32 + eps >= lower32.
+//                  Candidates live in a small per-pixel queue in shared memory; entries whose
+//                  upper bound falls below a risen lower32 are evicted.
 //   verify (FP64)  when a queue fills (and at the end) the whole warp evaluates its queued
 //                  candidates with slow_cost — the reference's exact two-pass tap filter in FP64,
 //                  operation for operation — and applies the reference's selection rule to them
@@ -34,7 +33,15 @@
 
 namespace sr {
 
-constexpr float SCREEN_EPS = 2e-4f;
+// Error bars of the screened ncc (|ncc32 - ncc64| <= eps), by conditioning of the two windows.
+// With u = 2^-24: the two FFMA chains of s1 and s3 are <= 13 long (<= 13u relative each), and an
+// input perturbation dt of the deviation vector t moves ncc by at most sqrt(1-ncc^2)*|dt|/|t|
+// (<= 0.31 for ncc >= 0.95); |dt| <= sqrt(WN)*(2u*255 + 13u*|meanR|) ~ 6e-4 for a 5x5 window.
+//   |t|^2 = s3 >= 100*WN (RMS deviation of 10 gray levels, the normal case): <= ~5e-6 -> TIGHT
+//   s3 >= WN: <= ~4e-5 -> LOOSE;   below that the label is FORCEd into the verified set.
+// SR_MATCH_STATS=1 records the largest |ncc32 - ncc64| actually seen on verified labels.
+constexpr float SCREEN_EPS_TIGHT = 1e-5f;
+constexpr float SCREEN_EPS_LOOSE = 2e-4f;
 constexpr float SCREEN_FORCE = 3.0e38f;  // "must be verified in FP64" marker (|ncc| <= 1 otherwise)
 constexpr int SCREEN_QCAP = 8;
 
@@ -122,7 +129,7 @@ __global__ void __launch_bounds__(128, (R <= 2) ? SR_SCREEN_MINBLOCKS : 2)
     float wtf[TPL], dlf[TPL];
     bool all_slow = false, has_inactive = false;
     unsigned long long actmask = 0ull;  // bit i: this lane's i-th tap is active (TPL <= 35)
-    float s2f = 0.0f, inv_totWf = 0.0f;
+    float s2f = 0.0f, inv_totWf = 0.0f, eps_pix = SCREEN_EPS_LOOSE;
     double meanL_x = 0.0, totW_x = 0.0, s2_x = 0.0;  // exact (reference order) left-window quantities
     {
         double wt[TPL], gl[TPL];
@@ -168,6 +175,7 @@ __global__ void __launch_bounds__(128, (R <= 2) ? SR_SCREEN_MINBLOCKS : 2)
         all_slow = !(totW >= 1e-10) || !(s2 >= (double)WN) || !(s2 < 1e30);
         has_inactive = ninact != 0;
         s2f = (float)s2;
+        eps_pix = (s2 >= 100.0 * WN) ? SCREEN_EPS_TIGHT : SCREEN_EPS_LOOSE;
         inv_totWf = (float)(1.0 / totW);
         meanL_x = meanL;
         totW_x = totW;
@@ -175,7 +183,7 @@ __global__ void __launch_bounds__(128, (R <= 2) ? SR_SCREEN_MINBLOCKS : 2)
     }
 
     // ---- FP32 screening of one label: returns ncc32 or SCREEN_FORCE ---------------------------
-    auto screen_one = [&](const float *__restrict__ base, auto masked_tag) -> float {
+    auto screen_one = [&](const float *__restrict__ base, float &eps, auto masked_tag) -> float {
         constexpr bool MASKED = decltype(masked_tag)::value;
         float g[TPL];
         float S1a = 0.0f, S1b = 0.0f;
@@ -228,6 +236,7 @@ __global__ void __launch_bounds__(128, (R <= 2) ? SR_SCREEN_MINBLOCKS : 2)
         const float s1 = group_sum_f<G>(s1a + s1b, gmask);
         // ill-conditioned or non-finite neighbour window: FP64 decides
         if (!(s3 >= (float)WN) || !(s3 < 1e30f)) return SCREEN_FORCE;
+        eps = (s3 >= 100.0f * WN) ? eps_pix : SCREEN_EPS_LOOSE;
         return s1 * rsqrtf(s2f * s3);
     };
 
@@ -237,8 +246,11 @@ __global__ void __launch_bounds__(128, (R <= 2) ? SR_SCREEN_MINBLOCKS : 2)
     const bool depth_up = a.depth_up != 0;
     int n_verified = 0, n_forced = 0, n_screened = 0;  // a.stats only
     int qn = 0;
-    const float thr_lo = (float)a.ncc_threshold - SCREEN_EPS;
-    float best32 = thr_lo;  // running maximum of the screened ncc (never below the threshold bound)
+    // lower32: a proven lower bound of the winning ncc64 (max over screened labels of ncc32 - eps,
+    // never below the threshold): a label whose upper bound ncc32 + eps is below it cannot win.
+    float lower32 = (float)a.ncc_threshold - 1e-6f;
+    float max_err = 0.0f;  // a.stats only
+    int n_viol = 0;        // a.stats only: verified labels outside their error bar (must stay 0)
 
     auto flush = [&]() {
         const int nmax = __reduce_max_sync(0xffffffffu, qn);
@@ -246,13 +258,20 @@ __global__ void __launch_bounds__(128, (R <= 2) ? SR_SCREEN_MINBLOCKS : 2)
         for (int q = 0; q < nmax; ++q) {
             if (q < qn) {  // uniform within a pixel's lane group
                 const int lab = q_lab[q][tid], tap = q_tap[q][tid];
-                const int j = lab >> 16, d = lab & 0xffff;
+                const int j = (lab >> 16) & 0xff, d = lab & 0xffff;
                 const int tx = (int)(short)(tap & 0xffff), ty = (int)(short)((uint32_t)tap >> 16);
                 const bool inside = tx >= R && ty >= R && tx < w - R && ty < h - R;
                 const double cost = (inside && !all_slow && !has_inactive)
                                         ? verify_cost_mvs<R, G>(a, a.grayR[j], x, y, tx, ty, pid, sub, gmask, meanL_x, totW_x, s2_x)
                                         : slow_cost<R, G, COST>(a, a.grayR[j], x, y, tx, ty, pid, sub, gmask);
                 ++n_verified;
+                if (a.stats && q_c32[q][tid] < 2.0f) {  // |ncc32 - ncc64| relative to its error bar
+                    const float e = (lab >> 30) ? SCREEN_EPS_TIGHT : SCREEN_EPS_LOOSE;
+                    const float c32 = q_c32[q][tid] - e;
+                    const float err = fabsf((float)(cost - (double)c32));
+                    max_err = fmaxf(max_err, err);
+                    if (err > e) ++n_viol;
+                }
                 if (cost > a.ncc_threshold) {  // multiviewstereo.cpp:589-602,654-660
                     const bool deeper = depth_up ? (d > bestIdx) : (d < bestIdx);
                     if (bestIdx == SR_INDEX_NONE || cost > bestC || (cost == bestC && deeper)) {
@@ -264,7 +283,7 @@ __global__ void __launch_bounds__(128, (R <= 2) ? SR_SCREEN_MINBLOCKS : 2)
         }
         qn = 0;
         // the verified maximum is a valid (and tighter) floor for the screen
-        if (bestIdx != SR_INDEX_NONE) best32 = fmaxf(best32, (float)bestC - SCREEN_EPS);
+        if (bestIdx != SR_INDEX_NONE) lower32 = fmaxf(lower32, (float)bestC - 1e-6f);
     };
 
     // ---- label sweep -------------------------------------------------------------------------
@@ -284,7 +303,7 @@ __global__ void __launch_bounds__(128, (R <= 2) ? SR_SCREEN_MINBLOCKS : 2)
     issue_chunk(0);
 
     int prevTap = TAP_NONE;
-    float prevC = 0.0f;
+    float prevC = 0.0f, prevEps = 0.0f;
 #pragma unroll 1
     for (int c = 0; c < total_chunks; ++c) {
         issue_chunk(c + 1);
@@ -297,37 +316,42 @@ __global__ void __launch_bounds__(128, (R <= 2) ? SR_SCREEN_MINBLOCKS : 2)
         for (int l = 0; l < nl; ++l) {
             const int32_t tap = alive ? tap_ring[c & 1][l][tid] : TAP_NONE;
             if (tap != TAP_NONE) {
-                float c32;
+                float c32, eps;
                 if (tap == prevTap) {
                     c32 = prevC;  // same integer tap as the previous label: same cost
+                    eps = prevEps;
                 } else {
                     const int tx = (int)(short)(tap & 0xffff), ty = (int)(short)((uint32_t)tap >> 16);
                     c32 = SCREEN_FORCE;
+                    eps = 0.0f;
                     if (!all_slow && tx >= R && ty >= R && tx < w - R && ty < h - R) {
                         const float *base = gRf + ((size_t)ty * w + tx);
-                        c32 = has_inactive ? screen_one(base, std::true_type{}) : screen_one(base, std::false_type{});
+                        c32 = has_inactive ? screen_one(base, eps, std::true_type{}) : screen_one(base, eps, std::false_type{});
                     }
                     prevTap = tap;
                     prevC = c32;
+                    prevEps = eps;
                     if (c32 == SCREEN_FORCE) ++n_forced;
                     else ++n_screened;
                 }
-                if (c32 >= best32 - SCREEN_EPS) {  // candidate (FORCE always is)
+                const float ub = c32 + eps;  // FORCE stays FORCE
+                if (ub >= lower32) {         // candidate
                     const int d = d0 + l;
-                    if (qn > 0 && q_tap[qn - 1][tid] == tap && (q_lab[qn - 1][tid] >> 16) == j) {
+                    const int lab = ((eps == SCREEN_EPS_TIGHT) ? (1 << 30) : 0) | (j << 16) | d;
+                    if (qn > 0 && q_tap[qn - 1][tid] == tap && ((q_lab[qn - 1][tid] >> 16) & 0xff) == j) {
                         // equal cost by construction: the tie-break picks the deeper label
-                        if (depth_up) q_lab[qn - 1][tid] = (j << 16) | d;
+                        if (depth_up) q_lab[qn - 1][tid] = lab;
                     } else {
-                        if (c32 != SCREEN_FORCE && c32 - SCREEN_EPS > best32) {
-                            // new running maximum: queued labels more than 2*EPS below it cannot win
-                            best32 = c32 - SCREEN_EPS;
-                            const float floor32 = best32 - SCREEN_EPS;
+                        const float lb = c32 - eps;
+                        if (c32 != SCREEN_FORCE && lb > lower32) {
+                            // the bound rises: queued labels whose upper bound is below it cannot win
+                            lower32 = lb;
                             int kept = 0;
                             for (int q = 0; q < qn; ++q) {
-                                const float cq = q_c32[q][tid];
-                                if (cq >= floor32) {
+                                const float uq = q_c32[q][tid];
+                                if (uq >= lower32) {
                                     if (kept != q) {
-                                        q_c32[kept][tid] = cq;
+                                        q_c32[kept][tid] = uq;
                                         q_lab[kept][tid] = q_lab[q][tid];
                                         q_tap[kept][tid] = q_tap[q][tid];
                                     }
@@ -336,9 +360,9 @@ __global__ void __launch_bounds__(128, (R <= 2) ? SR_SCREEN_MINBLOCKS : 2)
                             }
                             qn = kept;
                         }
-                        q_lab[qn][tid] = (j << 16) | d;
+                        q_lab[qn][tid] = lab;
                         q_tap[qn][tid] = tap;
-                        q_c32[qn][tid] = c32;
+                        q_c32[qn][tid] = ub;
                         ++qn;
                     }
                 }
@@ -355,6 +379,8 @@ __global__ void __launch_bounds__(128, (R <= 2) ? SR_SCREEN_MINBLOCKS : 2)
         atomicAdd(a.stats + 2, (unsigned long long)n_forced);
         atomicAdd(a.stats + 3, (unsigned long long)n_verified);
         if (all_slow) atomicAdd(a.stats + 4, 1ull);
+        atomicAdd(a.stats + 6, (unsigned long long)n_viol);
+        atomicMax(a.stats + 5, (unsigned long long)__float_as_uint(max_err));  // positive floats order as integers
     }
     if (alive && sub == 0) {
         a.out_index[pix] = bestIdx;
