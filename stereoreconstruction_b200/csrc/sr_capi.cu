@@ -13,6 +13,7 @@
 
 #include "sr_kernels.cuh"
 #include "sr_match_dispatch.cuh"
+#include "sr_build_refr.cuh"
 
 using namespace sr;
 
@@ -104,6 +105,8 @@ struct sr_ctx {
     int64_t launches = 0;
     size_t tap_budget = (size_t)8 << 30;
     unsigned long long *d_stats = nullptr;  // SR_MATCH_STATS=1: counters of the screened match kernel
+    bool use_refr_build = true;  // SR_BUILD_REFR=0: refractive views through the generic build_kernel (A/B aid)
+    int refr_chunk = 64;         // labels per thread of build_refr_kernel (SR_BUILD_CHUNK)
     bool use_screen = true;  // SR_MATCH_SCREEN=0: MVS selection through the all-FP64 match_kernel (A/B aid)
     ncclComm_t comm = nullptr;
     int rank = 0, nranks = 1;
@@ -206,6 +209,8 @@ int sr_ctx_create(int device, sr_ctx **out) {
     c->stream = c->own_stream;
     if (const char *mb = getenv("SR_TAP_BUDGET_MB")) c->tap_budget = (size_t)atoll(mb) << 20;
     if (const char *sc = getenv("SR_MATCH_SCREEN")) c->use_screen = atoi(sc) != 0;
+    if (const char *sb = getenv("SR_BUILD_REFR")) c->use_refr_build = atoi(sb) != 0;
+    if (const char *sk = getenv("SR_BUILD_CHUNK")) c->refr_chunk = std::max(4, atoi(sk));
     if (const char *ss = getenv("SR_MATCH_STATS")) {
         if (atoi(ss) != 0 && cudaMalloc(&c->d_stats, 8 * sizeof(unsigned long long)) == cudaSuccess)
             cudaMemset(c->d_stats, 0, 8 * sizeof(unsigned long long));
@@ -414,8 +419,48 @@ int sr_run_view(sr_ctx *ctx, int ref, const int32_t *nbrs, int nn) {
         const unsigned gx = (unsigned)((plane + 127) / 128);
         const int d_chunk = 32;
         for (int j = 0; j < nn; ++j) {
+            const sr_camera &nb = ctx->cams[nbrs[j]];
+            const bool mvs = (P.select_kind == SR_SELECT_MVS);
+            if (nb.is_refractive && ctx->use_refr_build) {
+                // refractive target view: hoisted-affine reprojection + Newton on the quartic in x/r
+                BuildRefrArgs ra;
+                ra.nbr = nb;
+                const double shift = mvs ? 0.0 : -0.5, sc = P.image_scale;
+                memcpy(ra.Kn, nb.K, sizeof(ra.Kn));
+                if (nb.is_distorted) {
+                    const double fx = nb.K[0], fy = nb.K[4], cx = nb.K[2], cy = nb.K[5];
+                    for (int c = 0; c < 3; ++c) {
+                        ra.Kn[c] = (nb.K[c] - cx * nb.K[6 + c]) / fx;
+                        ra.Kn[3 + c] = (nb.K[3 + c] - cy * nb.K[6 + c]) / fy;
+                    }
+                    ra.fxs = fx * sc;
+                    ra.cxs = cx * sc + shift;
+                    ra.fys = fy * sc;
+                    ra.cys = cy * sc + shift;
+                } else {
+                    ra.fxs = ra.fys = sc;
+                    ra.cxs = ra.cys = shift;
+                }
+                memcpy(ra.prin, ctx->cams[ref].prin_dir, sizeof(ra.prin));
+                memcpy(ra.C, ctx->cams[ref].C, sizeof(ra.C));
+                ra.rays = ctx->d_rays;
+                ra.depth_table = ctx->d_depth_table;
+                ra.ref_mask = A.mask;
+                ra.nbr_mask = ctx->views[nbrs[j]].mask;
+                ra.taps = ctx->d_taps + (size_t)j * D * plane;
+                ra.w = w;
+                ra.h = h;
+                ra.row0 = b0;
+                ra.rows = rows;
+                ra.D = D;
+                ra.d_chunk = ctx->refr_chunk;
+                ra.mvs = mvs;
+                build_refr_kernel<<<dim3(gx, (D + ra.d_chunk - 1) / ra.d_chunk), 128, 0, st>>>(ra);
+                CKL();
+                continue;
+            }
             BuildArgs ba;
-            ba.nbr = ctx->cams[nbrs[j]];
+            ba.nbr = nb;
             memcpy(ba.prin, ctx->cams[ref].prin_dir, sizeof(ba.prin));
             memcpy(ba.C, ctx->cams[ref].C, sizeof(ba.C));
             ba.rays = ctx->d_rays;
@@ -430,7 +475,7 @@ int sr_run_view(sr_ctx *ctx, int ref, const int32_t *nbrs, int nn) {
             ba.D = D;
             ba.d_chunk = d_chunk;
             ba.scale = P.image_scale;
-            ba.mvs = (P.select_kind == SR_SELECT_MVS);
+            ba.mvs = mvs;
             build_kernel<<<dim3(gx, (D + d_chunk - 1) / d_chunk), 128, 0, st>>>(ba);
             CKL();
         }
