@@ -25,10 +25,11 @@ cudaError_t launch_match_rc(const MatchArgs &a, cudaStream_t st) {
 template <int R>
 cudaError_t launch_match_screen(const MatchArgs &a, cudaStream_t st) {
     constexpr int G = LanesFor<R>::G;
-    constexpr int PPB = 128 / G;
+    constexpr int PPB = SCREEN_BLOCK / G;
     const size_t npix = (size_t)a.rows * a.w;
     const unsigned grid = (unsigned)((npix + PPB - 1) / PPB);
-    match_mvs_screen_kernel<R, G><<<grid, 128, 0, st>>>(a);
+    if (a.stats) match_mvs_screen_kernel<R, G, true><<<grid, SCREEN_BLOCK, 0, st>>>(a);
+    else match_mvs_screen_kernel<R, G, false><<<grid, SCREEN_BLOCK, 0, st>>>(a);
     return cudaGetLastError();
 }
 

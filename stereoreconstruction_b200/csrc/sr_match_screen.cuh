@@ -45,6 +45,18 @@ constexpr float SCREEN_EPS_LOOSE = 2e-4f;
 constexpr float SCREEN_FORCE = 3.0e38f;  // "must be verified in FP64" marker (|ncc| <= 1 otherwise)
 constexpr int SCREEN_QCAP = 8;
 
+// Packed FP32 FMA of sm_100 (SASS FFMA2): two independent fused multiply-adds per issue slot.
+__device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c) {
+    unsigned long long ua, ub, uc, ud;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(ua) : "f"(a.x), "f"(a.y));
+    asm("mov.b64 %0, {%1, %2};" : "=l"(ub) : "f"(b.x), "f"(b.y));
+    asm("mov.b64 %0, {%1, %2};" : "=l"(uc) : "f"(c.x), "f"(c.y));
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(ud) : "l"(ua), "l"(ub), "l"(uc));
+    float2 d;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(d.x), "=f"(d.y) : "l"(ud));
+    return d;
+}
+
 template <int G>
 __device__ __forceinline__ float group_sum_f(float v, unsigned gmask) {
 #pragma unroll
@@ -89,21 +101,36 @@ __device__ __noinline__ double verify_cost_mvs(const MatchArgs &a, const double 
 }
 
 #ifndef SR_SCREEN_MINBLOCKS
-#define SR_SCREEN_MINBLOCKS 4
+#define SR_SCREEN_MINBLOCKS 4   // blocks of 128 threads per SM for the thread-per-pixel variants
+#endif
+#ifndef SR_SCREEN_BLOCK
+#define SR_SCREEN_BLOCK 32      // threads per block: the kernel has no block-wide step, so a block is
+                                // one warp and a slow warp (verification-heavy pixels) holds no
+                                // other warp's slot
+#endif
+constexpr int SCREEN_BLOCK = SR_SCREEN_BLOCK;
+#ifndef SR_SCREEN_PREFETCH
+#define SR_SCREEN_PREFETCH 0    // labels of look-ahead for an L1 prefetch of the window's sectors
 #endif
 
-template <int R, int G>
-__global__ void __launch_bounds__(128, (R <= 2) ? SR_SCREEN_MINBLOCKS : 2)
+template <int R, int G, bool STATS>
+__global__ void __launch_bounds__(SCREEN_BLOCK, ((R <= 2) ? SR_SCREEN_MINBLOCKS : 2) * (128 / SCREEN_BLOCK))
     match_mvs_screen_kernel(const __grid_constant__ MatchArgs a) {
     constexpr int COST = SR_COST_NCC_MVS;
     constexpr int WS = 2 * R + 1;
     constexpr int WN = WS * WS;
     constexpr int TPL = (WN + G - 1) / G;
-    constexpr int PIX_PER_BLOCK = 128 / G;
-    __shared__ int32_t tap_ring[2][TAP_CHUNK][128];
-    __shared__ int32_t q_lab[SCREEN_QCAP][128];  // (neighbour << 16) | label
-    __shared__ int32_t q_tap[SCREEN_QCAP][128];
-    __shared__ float q_c32[SCREEN_QCAP][128];
+    constexpr int PIX_PER_BLOCK = SCREEN_BLOCK / G;
+    __shared__ int32_t tap_ring[2][TAP_CHUNK][SCREEN_BLOCK];
+    __shared__ int32_t q_lab[SCREEN_QCAP][SCREEN_BLOCK];  // (eps class << 30) | (neighbour << 16) | label
+    __shared__ int32_t q_tap[SCREEN_QCAP][SCREEN_BLOCK];
+    __shared__ float q_c32[SCREEN_QCAP][SCREEN_BLOCK];    // upper bound ncc32 + eps
+    // Per-pixel state that only the verification step touches lives in shared memory, so that the
+    // label loop keeps its registers for the window (w, dl, taps): exact left-window quantities
+    // in the reference's summation order, and the verified winner so far.
+    __shared__ double px_meanL[SCREEN_BLOCK], px_totW[SCREEN_BLOCK], px_s2[SCREEN_BLOCK], px_bestC[SCREEN_BLOCK];
+    __shared__ int px_bestIdx[SCREEN_BLOCK];
+    __shared__ unsigned long long px_act[SCREEN_BLOCK];  // bit i: this lane's i-th tap is active (TPL <= 35)
 
     const int tid = threadIdx.x;
     const int lane = tid & 31;
@@ -128,13 +155,12 @@ __global__ void __launch_bounds__(128, (R <= 2) ? SR_SCREEN_MINBLOCKS : 2)
     // ---- reference-window invariants, FP64 (once per pixel) ----------------------------------
     float wtf[TPL], dlf[TPL];
     bool all_slow = false, has_inactive = false;
-    unsigned long long actmask = 0ull;  // bit i: this lane's i-th tap is active (TPL <= 35)
     float s2f = 0.0f, inv_totWf = 0.0f, eps_pix = SCREEN_EPS_LOOSE;
-    double meanL_x = 0.0, totW_x = 0.0, s2_x = 0.0;  // exact (reference order) left-window quantities
     {
         double wt[TPL], gl[TPL];
         double totW = 0.0, SL = 0.0;
         int ninact = 0;
+        unsigned long long actmask = 0ull;
 #pragma unroll
         for (int i = 0; i < TPL; ++i) {
             const int k = sub + G * i;
@@ -177,27 +203,32 @@ __global__ void __launch_bounds__(128, (R <= 2) ? SR_SCREEN_MINBLOCKS : 2)
         s2f = (float)s2;
         eps_pix = (s2 >= 100.0 * WN) ? SCREEN_EPS_TIGHT : SCREEN_EPS_LOOSE;
         inv_totWf = (float)(1.0 / totW);
-        meanL_x = meanL;
-        totW_x = totW;
-        s2_x = s2;
+        px_meanL[tid] = meanL;
+        px_totW[tid] = totW;
+        px_s2[tid] = s2;
+        px_act[tid] = actmask;
+        px_bestC[tid] = 0.0;
+        px_bestIdx[tid] = SR_INDEX_NONE;
     }
+    // keep the FP32 copies as values of their own (otherwise they are re-derived from the FP64
+    // ones with an F2F / DSETP inside the label loop)
+    asm volatile("" : "+f"(s2f), "+f"(eps_pix), "+f"(inv_totWf));
 
     // ---- FP32 screening of one label: returns ncc32 or SCREEN_FORCE ---------------------------
+    // Taps are processed in pairs (2p, 2p+1) with the packed FFMA2 (fma.rn.f32x2): the pair of
+    // accumulators is the even/odd split a scalar version would use anyway, and the issue slots of
+    // the window arithmetic halve (4 FFMA2 per two taps instead of 8 FFMA).
     auto screen_one = [&](const float *__restrict__ base, float &eps, auto masked_tag) -> float {
         constexpr bool MASKED = decltype(masked_tag)::value;
+        constexpr int NP = TPL / 2;          // full pairs
+        constexpr bool ODD = (TPL & 1) != 0; // one scalar tap left over
         float g[TPL];
-        float S1a = 0.0f, S1b = 0.0f;
         if (G == 1) {
 #pragma unroll
             for (int row = 0; row < WS; ++row) {
                 const float *__restrict__ rp = base + (row - R) * w;
 #pragma unroll
-                for (int col = 0; col < WS; ++col) {
-                    const int i = row * WS + col;
-                    g[i] = rp[col - R];
-                    if (i & 1) S1b = fmaf(wtf[i], g[i], S1b);
-                    else S1a = fmaf(wtf[i], g[i], S1a);
-                }
+                for (int col = 0; col < WS; ++col) g[row * WS + col] = rp[col - R];
             }
         } else {
 #pragma unroll
@@ -205,35 +236,51 @@ __global__ void __launch_bounds__(128, (R <= 2) ? SR_SCREEN_MINBLOCKS : 2)
                 const int k = sub + G * i;
                 g[i] = 0.0f;
                 if (k < WN) g[i] = base[(k / WS - R) * w + (k % WS - R)];
-                if (i & 1) S1b = fmaf(wtf[i], g[i], S1b);
-                else S1a = fmaf(wtf[i], g[i], S1a);
             }
         }
-        const float S1 = group_sum_f<G>(S1a + S1b, gmask);
-        const float mR = S1 * inv_totWf;
-        float s3a = 0.0f, s3b = 0.0f, s1a = 0.0f, s1b = 0.0f;
+        // three independent accumulator pairs per sum: the dependent FFMA2 chains stay short
+        float2 S1p[3] = {make_float2(0.0f, 0.0f), make_float2(0.0f, 0.0f), make_float2(0.0f, 0.0f)};
 #pragma unroll
-        for (int i = 0; i < TPL; ++i) {
-            float t = fmaf(wtf[i], g[i], -mR);
-            if (MASKED) {
-                // inactive or padding tap -> 0, branch- and predicate-free: bfe.s32 of one bit is 0 / ~0
-                const unsigned word = (i < 32) ? (unsigned)actmask : (unsigned)(actmask >> 32);
-                int m;
-                asm("bfe.s32 %0, %1, %2, 1;" : "=r"(m) : "r"(word), "r"(i & 31));
-                t = __int_as_float(__float_as_int(t) & m);
-            } else if (G > 1 && sub + G * i >= WN) {
-                t = 0.0f;  // padding taps of the last round
+        for (int p = 0; p < NP; ++p)
+            S1p[p % 3] = fma2(make_float2(wtf[2 * p], wtf[2 * p + 1]), make_float2(g[2 * p], g[2 * p + 1]), S1p[p % 3]);
+        float S1s = ((S1p[0].x + S1p[0].y) + (S1p[1].x + S1p[1].y)) + (S1p[2].x + S1p[2].y);
+        if (ODD) S1s = fmaf(wtf[TPL - 1], g[TPL - 1], S1s);
+        const float S1 = group_sum_f<G>(S1s, gmask);
+        const float mR = S1 * inv_totWf;
+        const float2 nm = make_float2(-mR, -mR);
+        float2 s3p[2] = {make_float2(0.0f, 0.0f), make_float2(0.0f, 0.0f)};
+        float2 s1p[2] = {make_float2(0.0f, 0.0f), make_float2(0.0f, 0.0f)};
+        unsigned long long actmask = 0ull;
+        if (MASKED) actmask = px_act[tid];
+        auto mask_of = [&](int i) -> int {  // 0 / ~0: tap i is active (bfe.s32 of one bit)
+            const unsigned word = (i < 32) ? (unsigned)actmask : (unsigned)(actmask >> 32);
+            int m;
+            asm("bfe.s32 %0, %1, %2, 1;" : "=r"(m) : "r"(word), "r"(i & 31));
+            return m;
+        };
+#pragma unroll
+        for (int p = 0; p < NP; ++p) {
+            float2 t = fma2(make_float2(wtf[2 * p], wtf[2 * p + 1]), make_float2(g[2 * p], g[2 * p + 1]), nm);
+            if (MASKED) {  // inactive or padding tap -> 0, branch- and predicate-free
+                t.x = __int_as_float(__float_as_int(t.x) & mask_of(2 * p));
+                t.y = __int_as_float(__float_as_int(t.y) & mask_of(2 * p + 1));
+            } else if (G > 1 && !ODD && p == NP - 1) {
+                if (sub + G * (2 * p + 1) >= WN) t.y = 0.0f;  // padding tap of the last round
             }
-            if (i & 1) {
-                s3b = fmaf(t, t, s3b);
-                s1b = fmaf(dlf[i], t, s1b);
-            } else {
-                s3a = fmaf(t, t, s3a);
-                s1a = fmaf(dlf[i], t, s1a);
-            }
+            s3p[p & 1] = fma2(t, t, s3p[p & 1]);
+            s1p[p & 1] = fma2(make_float2(dlf[2 * p], dlf[2 * p + 1]), t, s1p[p & 1]);
         }
-        const float s3 = group_sum_f<G>(s3a + s3b, gmask);
-        const float s1 = group_sum_f<G>(s1a + s1b, gmask);
+        float s3s = (s3p[0].x + s3p[0].y) + (s3p[1].x + s3p[1].y);
+        float s1s = (s1p[0].x + s1p[0].y) + (s1p[1].x + s1p[1].y);
+        if (ODD) {
+            float t = fmaf(wtf[TPL - 1], g[TPL - 1], -mR);
+            if (MASKED) t = __int_as_float(__float_as_int(t) & mask_of(TPL - 1));
+            else if (G > 1 && sub + G * (TPL - 1) >= WN) t = 0.0f;
+            s3s = fmaf(t, t, s3s);
+            s1s = fmaf(dlf[TPL - 1], t, s1s);
+        }
+        const float s3 = group_sum_f<G>(s3s, gmask);
+        const float s1 = group_sum_f<G>(s1s, gmask);
         // ill-conditioned or non-finite neighbour window: FP64 decides
         if (!(s3 >= (float)WN) || !(s3 < 1e30f)) return SCREEN_FORCE;
         eps = (s3 >= 100.0f * WN) ? eps_pix : SCREEN_EPS_LOOSE;
@@ -241,19 +288,20 @@ __global__ void __launch_bounds__(128, (R <= 2) ? SR_SCREEN_MINBLOCKS : 2)
     };
 
     // ---- exact state (FP64) and candidate queue -----------------------------------------------
-    double bestC = 0.0;
-    int bestIdx = SR_INDEX_NONE;
     const bool depth_up = a.depth_up != 0;
-    int n_verified = 0, n_forced = 0, n_screened = 0;  // a.stats only
+    int n_verified = 0, n_forced = 0, n_screened = 0;  // STATS only
     int qn = 0;
     // lower32: a proven lower bound of the winning ncc64 (max over screened labels of ncc32 - eps,
     // never below the threshold): a label whose upper bound ncc32 + eps is below it cannot win.
     float lower32 = (float)a.ncc_threshold - 1e-6f;
-    float max_err = 0.0f;  // a.stats only
-    int n_viol = 0;        // a.stats only: verified labels outside their error bar (must stay 0)
+    float max_err = 0.0f;  // STATS only
+    int n_viol = 0;        // STATS only: verified labels outside their error bar (must stay 0)
 
     auto flush = [&]() {
         const int nmax = __reduce_max_sync(0xffffffffu, qn);
+        double bestC = px_bestC[tid];
+        int bestIdx = px_bestIdx[tid];
+        const double meanL_x = px_meanL[tid], totW_x = px_totW[tid], s2_x = px_s2[tid];
 #pragma unroll 1
         for (int q = 0; q < nmax; ++q) {
             if (q < qn) {  // uniform within a pixel's lane group
@@ -264,8 +312,8 @@ __global__ void __launch_bounds__(128, (R <= 2) ? SR_SCREEN_MINBLOCKS : 2)
                 const double cost = (inside && !all_slow && !has_inactive)
                                         ? verify_cost_mvs<R, G>(a, a.grayR[j], x, y, tx, ty, pid, sub, gmask, meanL_x, totW_x, s2_x)
                                         : slow_cost<R, G, COST>(a, a.grayR[j], x, y, tx, ty, pid, sub, gmask);
-                ++n_verified;
-                if (a.stats && q_c32[q][tid] < 2.0f) {  // |ncc32 - ncc64| relative to its error bar
+                if (STATS) ++n_verified;
+                if (STATS && q_c32[q][tid] < 2.0f) {  // |ncc32 - ncc64| relative to its error bar
                     const float e = (lab >> 30) ? SCREEN_EPS_TIGHT : SCREEN_EPS_LOOSE;
                     const float c32 = q_c32[q][tid] - e;
                     const float err = fabsf((float)(cost - (double)c32));
@@ -282,6 +330,8 @@ __global__ void __launch_bounds__(128, (R <= 2) ? SR_SCREEN_MINBLOCKS : 2)
             }
         }
         qn = 0;
+        px_bestC[tid] = bestC;
+        px_bestIdx[tid] = bestIdx;
         // the verified maximum is a valid (and tighter) floor for the screen
         if (bestIdx != SR_INDEX_NONE) lower32 = fmaxf(lower32, (float)bestC - 1e-6f);
     };
@@ -315,6 +365,27 @@ __global__ void __launch_bounds__(128, (R <= 2) ? SR_SCREEN_MINBLOCKS : 2)
 #pragma unroll 1
         for (int l = 0; l < nl; ++l) {
             const int32_t tap = alive ? tap_ring[c & 1][l][tid] : TAP_NONE;
+            if (SR_SCREEN_PREFETCH > 0 && alive && l + SR_SCREEN_PREFETCH < nl) {
+                // the window slides along the epipolar curve: its leading sectors come from L2;
+                // pull them into L1 a few labels early so that no LDG of the label loop misses
+                const int32_t tp = tap_ring[c & 1][l + SR_SCREEN_PREFETCH][tid];
+                const int px = (int)(short)(tp & 0xffff), py = (int)(short)((uint32_t)tp >> 16);
+                if (tp != TAP_NONE && tp != tap && px >= R && py >= R && px < w - R && py < h - R) {
+                    const float *pb = gRf + ((size_t)(py - R) * w + px);
+                    if (G == 1) {
+#pragma unroll
+                        for (int row = 0; row < WS; ++row) {
+                            prefetch_l1(pb + row * w - R);
+                            prefetch_l1(pb + row * w + R);
+                        }
+                    } else {
+                        for (int row = sub; row < WS; row += G) {
+                            prefetch_l1(pb + row * w - R);
+                            prefetch_l1(pb + row * w + R);
+                        }
+                    }
+                }
+            }
             if (tap != TAP_NONE) {
                 float c32, eps;
                 if (tap == prevTap) {
@@ -331,8 +402,10 @@ __global__ void __launch_bounds__(128, (R <= 2) ? SR_SCREEN_MINBLOCKS : 2)
                     prevTap = tap;
                     prevC = c32;
                     prevEps = eps;
-                    if (c32 == SCREEN_FORCE) ++n_forced;
-                    else ++n_screened;
+                    if (STATS) {
+                        if (c32 == SCREEN_FORCE) ++n_forced;
+                        else ++n_screened;
+                    }
                 }
                 const float ub = c32 + eps;  // FORCE stays FORCE
                 if (ub >= lower32) {         // candidate
@@ -373,7 +446,7 @@ __global__ void __launch_bounds__(128, (R <= 2) ? SR_SCREEN_MINBLOCKS : 2)
     cp_async_wait<0>();
     flush();
 
-    if (a.stats && alive && sub == 0) {
+    if (STATS && a.stats && alive && sub == 0) {
         atomicAdd(a.stats + 0, 1ull);
         atomicAdd(a.stats + 1, (unsigned long long)n_screened);
         atomicAdd(a.stats + 2, (unsigned long long)n_forced);
@@ -383,9 +456,10 @@ __global__ void __launch_bounds__(128, (R <= 2) ? SR_SCREEN_MINBLOCKS : 2)
         atomicMax(a.stats + 5, (unsigned long long)__float_as_uint(max_err));  // positive floats order as integers
     }
     if (alive && sub == 0) {
+        const int bestIdx = px_bestIdx[tid];
         a.out_index[pix] = bestIdx;
         a.out_depth[pix] = (bestIdx >= 0) ? a.depth_table[bestIdx] : -1.0;
-        a.out_best[pix] = bestC;
+        a.out_best[pix] = px_bestC[tid];
     }
 }
 
