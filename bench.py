@@ -86,7 +86,7 @@ class ClockSampler(threading.Thread):
              "clocks_event_reasons.sw_power_cap")
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={q}",
-                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             for line in self.proc.stdout:
                 if self.stop_flag:
@@ -114,22 +114,34 @@ class ClockSampler(threading.Thread):
         return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def cpu_sample(wl, imgs, rows, steps=1, warmup=0):
-    """Times the CPU oracle (all host threads) on `rows` rows of reference view 0 of the workload."""
+def cpu_sample(wl, imgs, rows, steps=1, warmup=0, target_s=12.0):
+    """Times the CPU oracle (all host threads) on a row band of reference view 0 of the workload.
+    rows <= 0: a short probe sizes the band so that one timed pass takes about `target_s`."""
     from oracle import oracle_api as O
     sc = O.Scene(wl["cams"], imgs)
     nb = neighbours_for(wl)
     P = T.SrParams.from_buffer_copy(wl["params"])
-    r0 = (wl["h"] - rows) // 2
-    P.row_begin, P.row_end = r0, r0 + rows
-    times = []
-    for i in range(warmup + steps):
+
+    def run(nrows):
+        r0 = (wl["h"] - nrows) // 2
+        P.row_begin, P.row_end = r0, r0 + nrows
         t0 = time.perf_counter()
         if wl["name"] == "cfg3":
             sc.twoview_label(P, 0, 1)
         else:
             sc.mvs_view(P, 0, nb[0])
-        dt = time.perf_counter() - t0
+        return time.perf_counter() - t0, r0
+
+    if rows <= 0:
+        probe = max(2, min(wl["h"], O.num_threads()))  # one row per thread
+        tp, _ = run(probe)
+        rows = int(max(probe, min(wl["h"], probe * target_s / max(tp, 1e-3))))
+        rows -= rows % max(1, O.num_threads())  # whole rows per thread under the static schedule
+        rows = max(rows, probe)
+    times = []
+    r0 = 0
+    for i in range(warmup + steps):
+        dt, r0 = run(rows)
         if i >= warmup:
             times.append(dt)
     units = rows * wl["w"] * wl["D"]
@@ -154,7 +166,7 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     wl = workload(args.workload)
     w, h, V, D = wl["w"], wl["h"], wl["V"], wl["D"]
-    cpu_rows = args.cpu_rows or max(2, int(16 * (1920.0 / w) * (256.0 / D) * (0.08 if wl["name"] == "cfg3" else 1)))
+    cpu_rows = args.cpu_rows  # 0: sized by a probe to ~12 s of CPU work
 
     # ------------------------------------------------------------------ reference arm (CPU oracle)
     if args.impl == "reference":
@@ -287,12 +299,21 @@ def main():
     alg_bytes_view = h * w * D * 8 + h * w * (4 * (1 + n_nbr) + 4)
     achieved = alg_bytes_match / (match_ms * 1e-3) / 1e9
     pipe_gbs = alg_bytes_view / ((match_ms + build_ms) * 1e-3) / 1e9
+    traffic = None
+    kname = "match_mvs_screen_kernel" if wl["name"] != "cfg3" else "match_kernel"
+    try:  # dram__bytes_read.sum + dram__bytes_write.sum of one launch, from the committed ncu capture
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            traffic = json.load(f).get(wl["name"], {}).get(kname)
+    except (OSError, ValueError):
+        pass
     roofline = {
-        "bound": "hbm", "kernel": "match_kernel (weights + windowed NCC + fused WTA)", "achieved": achieved,
-        "peak": peak_gbs, "unit": "GB/s", "frac": achieved / peak_gbs, "traffic": None, "peak_source": peak_src,
-        "match_ms_per_view": match_ms, "build_ms_per_view": build_ms,
+        "bound": "hbm", "kernel": kname + " (support-weight aggregation of the photo-consistency cost + fused WTA)",
+        "achieved": achieved, "peak": peak_gbs, "unit": "GB/s", "frac": achieved / peak_gbs, "traffic": traffic,
+        "peak_source": peak_src, "match_ms_per_view": match_ms, "build_ms_per_view": build_ms,
         "pipeline_achieved_gbs": pipe_gbs, "pipeline_frac": pipe_gbs / peak_gbs,
-        "binding_bound": "FP64 issue (see DESIGN.md: ~200 FP64 instructions per pixel*label*neighbour)",
+        "binding_bound": ("instruction issue / latency, not HBM: ~170 warp-instructions per (pixel, label, neighbour) in the "
+                          "match kernel and ~210 in the refractive build (profiles/, DESIGN.md section 5); HBM sees "
+                          "only the 4-byte tap per (pixel, label, neighbour)"),
     }
 
     cpu = None

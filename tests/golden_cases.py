@@ -1,0 +1,82 @@
+"""Seeded inputs shared by tests/golden/make_golden.py (which writes the fixtures) and
+tests/test_golden.py (which replays them through the oracle and the CUDA path)."""
+import numpy as np
+
+from stereoreconstruction_b200 import scenes, types as T
+from scene_util import refractive_arc_scene, rectified_scene as _rect
+
+WEIGHT_RADII = (1, 2, 5)
+ARC_CROSS_THRESH = 12.0
+
+
+def line_cases():
+    w, h = 64, 48
+    rng = np.random.RandomState(11)
+    cases = [(0, 0, 10, 3), (10, 3, 0, 0), (5, 5, 5, 5), (0, 0, 0, 9), (7, 2, 7, -6), (-5, -5, 70, 60),
+             (-20, 10, 90, 12), (30, -40, 31, 90), (63, 47, 0, 0), (64, 48, -1, -1), (100, 100, 200, 150)]
+    for _ in range(200):
+        cases.append(tuple(int(v) for v in rng.randint(-40, 110, 4)))
+    return cases, w, h
+
+
+def ray_cases():
+    rng = np.random.RandomState(5)
+    out = []
+    for _ in range(300):
+        s1, d1, s2, d2, pn = (rng.normal(size=3) for _ in range(5))
+        out.append((s1, d1, s2, d2, pn, float(rng.normal() * 3), float(rng.uniform(0.6, 1.7))))
+    return out
+
+
+def leaf_image():
+    rng = np.random.RandomState(2)
+    h, w = 37, 53
+    img = rng.randint(0, 256, size=(h, w, 4)).astype(np.uint8)
+    img[..., 3] = 255
+    img[5:9, 7:12] = 255  # a WHITE patch
+    img[20:30, 30:45, :3] //= 8  # a dark, low-contrast patch: long geodesic paths
+    return img
+
+
+def sample_points(w, h):
+    rng = np.random.RandomState(9)
+    pts = [(float(rng.uniform(-2, w + 1)), float(rng.uniform(-2, h + 1))) for _ in range(500)]
+    pts += [(float(x), float(y)) for x in (-1, 0, 1, w - 2, w - 1, w) for y in (-1, 0, 1, h - 2, h - 1, h)]
+    return pts
+
+
+def weight_centres(w, h):
+    rng = np.random.RandomState(4)
+    cx = np.concatenate([rng.randint(0, w, 30), [0, w - 1, 0, w - 1, 1]]).astype(np.int32)
+    cy = np.concatenate([rng.randint(0, h, 30), [0, 0, h - 1, h - 1, h - 2]]).astype(np.int32)
+    return cx, cy
+
+
+def arc_scene():
+    cams, imgs, ms, _ = refractive_arc_scene(V=4, w=96, h=64, masks=True)
+    return cams, imgs, ms
+
+
+def arc_mvs_params():
+    return {
+        "arc_mvs_geo_r2": T.default_params(True, 420.0, 580.0, 40),
+        "arc_mvs_ada_r2": T.default_params(True, 420.0, 580.0, 40, weight_kind=T.SR_WEIGHT_ADAPTIVE),
+        "arc_mvs_geo_r3": T.default_params(True, 420.0, 580.0, 24, radius=3),
+    }
+
+
+def arc_twoview_params():
+    return {
+        "arc_two_ncc_geo_r5": (T.default_params(False, 420.0, 580.0, 24, radius=5), 1, 2),
+        "arc_two_sad_ada_r2": (T.default_params(False, 420.0, 580.0, 24, radius=2, weight_kind=T.SR_WEIGHT_ADAPTIVE,
+                                                cost_kind=T.SR_COST_SAD_TWOVIEW), 2, 1),
+    }
+
+
+def rectified_scene():
+    cams, imgs, _, _ = _rect(w=112, h=40)
+    return cams, imgs
+
+
+def rectified_params():
+    return T.default_params(False, 100.0, 500.0, 32, radius=16, weight_kind=T.SR_WEIGHT_ADAPTIVE)

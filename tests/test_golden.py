@@ -1,0 +1,193 @@
+"""Golden-vector tests (tests/golden/*.npz, written by tests/golden/make_golden.py).
+
+CPU (`-m "not gpu"`): the oracle reproduces the outputs of the reference's own compiled sources
+(ref_leaves.npz) and its own committed scene outputs bit for bit.
+GPU (`-m gpu`): the CUDA path, through the C ABI, reproduces the committed scene outputs."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+from oracle import oracle_api as O
+from stereoreconstruction_b200 import types as T
+import golden_cases as G
+from scene_util import cost_close
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+@pytest.fixture(scope="module")
+def leaves():
+    return np.load(os.path.join(GOLD, "ref_leaves.npz"))
+
+
+@pytest.fixture(scope="module")
+def scenes_gold():
+    return np.load(os.path.join(GOLD, "oracle_scenes.npz"))
+
+
+def _ip(a):
+    return a.ctypes.data_as(C.POINTER(C.c_int32))
+
+
+def _dp(a):
+    return a.ctypes.data_as(C.POINTER(C.c_double))
+
+
+def _same(a, b):
+    a, b = np.asarray(a), np.asarray(b)
+    if a.dtype.kind == "f":
+        return bool(((a == b) | (np.isnan(a) & np.isnan(b))).all())
+    return bool((a == b).all())
+
+
+# ------------------------------------------------------------------ oracle vs reference leaves
+def test_oracle_lines_match_reference_golden(leaves):
+    L = O.lib()
+    cases, w, h = G.line_cases()
+    counts, pts, off, k = leaves["line_counts"], leaves["line_points"], 0, 0
+    for i, (x0, y0, x1, y1) in enumerate(cases):
+        for clip in (0, 1):
+            buf = np.empty((4096, 2), np.int32)
+            n = L.orc_line(x0, y0, x1, y1, clip, w, h, _ip(buf), 4096)
+            assert n == counts[k], (x0, y0, x1, y1, clip)
+            assert (buf[:n] == pts[off:off + n]).all(), (x0, y0, x1, y1, clip)
+            off += n
+            k += 1
+        a = np.array([x0, y0, x1, y1], np.int32)
+        ok = L.orc_clip_line(_ip(a), w, h)
+        assert ok == leaves["clip_ok"][i]
+        if ok:
+            assert (a == leaves["clip_out"][i]).all()
+
+
+def test_oracle_ray_ops_match_reference_golden(leaves):
+    L = O.lib()
+    for i, (s1, d1, s2, d2, pn, pd, n) in enumerate(G.ray_cases()):
+        a = np.full(3, np.nan)
+        ok = L.orc_intersect(_dp(s1), _dp(d1), _dp(pn), C.c_double(pd), _dp(a))
+        assert ok == leaves["intersect_ok"][i]
+        if ok:
+            assert _same(a, leaves["intersect"][i])
+        b = np.empty(6)
+        ok = L.orc_refract(_dp(s1), _dp(d1), _dp(pn), C.c_double(pd), C.c_double(n), _dp(b))
+        assert ok == leaves["refract_ok"][i] and _same(b, leaves["refract"][i])
+        c = np.empty(6)
+        L.orc_closest_points(_dp(s1), _dp(d1), _dp(s2), _dp(d2), _dp(c))
+        assert _same(c, leaves["closest"][i])
+
+
+def test_oracle_sample_and_weights_match_reference_golden(leaves):
+    img = G.leaf_image()
+    h, w = img.shape[:2]
+    sc = O.Scene([T.make_camera(np.eye(3), np.eye(3), np.zeros(3))], [img])
+    L = O.lib()
+    a = np.empty(4)
+    for i, (x, y) in enumerate(G.sample_points(w, h)):
+        L.orc_sample(sc.ptr, 0, C.c_double(x), C.c_double(y), _dp(a))
+        assert _same(a, leaves["sample"][i]), (x, y)
+    cx, cy = G.weight_centres(w, h)
+    for kind in (0, 1):
+        for radius in G.WEIGHT_RADII:
+            mine = np.asarray(sc.weights(0, kind, radius, cx, cy)).reshape(cx.size, -1)
+            assert _same(mine, leaves[f"weights_k{kind}_r{radius}"]), (kind, radius)
+
+
+# ------------------------------------------------------------------ oracle vs its committed scene outputs
+def test_oracle_reproduces_scene_golden(scenes_gold):
+    cams, imgs, ms = G.arc_scene()
+    sc = O.Scene(cams, imgs, ms)
+    nb = sc.select_neighbours(3)
+    assert _same(np.array([[int(v) for v in r] for r in nb], np.int32), scenes_gold["arc_neighbours"])
+    name, P = "arc_mvs_geo_r2", G.arc_mvs_params()["arc_mvs_geo_r2"]
+    depths = []
+    for ref in range(len(cams)):
+        od, oi, ob, _, _ = sc.mvs_view(P, ref, nb[ref])
+        assert _same(oi, scenes_gold[f"{name}_v{ref}_index"])
+        assert _same(od, scenes_gold[f"{name}_v{ref}_depth"])
+        assert _same(ob, scenes_gold[f"{name}_v{ref}_best"])
+        depths.append(od)
+    for v, d in enumerate(sc.crosscheck_mvs(P, depths, G.ARC_CROSS_THRESH)):
+        assert _same(d, scenes_gold[f"{name}_v{v}_crosschecked"])
+    name = "arc_two_sad_ada_r2"
+    P, a, b = G.arc_twoview_params()[name]
+    od, oi, ob, ov = sc.twoview_label(P, a, b, root_mode=1, want_volume=True)
+    assert _same(oi, scenes_gold[f"{name}_index"]) and _same(od, scenes_gold[f"{name}_depth"])
+    assert _same(np.transpose(ov, (2, 0, 1)).astype(np.float32), scenes_gold[f"{name}_volume"])
+
+
+# ------------------------------------------------------------------ CUDA path vs the committed scene outputs
+@pytest.fixture(scope="module")
+def gpu_ctx():
+    from stereoreconstruction_b200 import capi
+    c = capi.Context(0)
+    yield c
+    c.close()
+
+
+def _check_maps(gi, gd, gb, oi, od, ob, best_tol):
+    mism = gi != oi
+    assert mism.mean() <= 1e-4, f"index mismatch rate {mism.mean()}"
+    same = ~mism
+    assert ((gd == od) | (np.isnan(gd) & np.isnan(od)))[same].all()
+    lab = same & (oi >= 0)
+    assert lab.any()
+    assert not cost_close(gb[lab], ob[lab], rel=best_tol, abs_floor=best_tol).any()
+
+
+@pytest.mark.gpu
+def test_gpu_weights_match_reference_golden(leaves, gpu_ctx):
+    """AdaptiveWeight / GeodesicWeight on the GPU against the reference's own compiled sources."""
+    img = G.leaf_image()
+    h, w = img.shape[:2]
+    gpu_ctx.set_views([T.make_camera(np.eye(3), np.eye(3), np.zeros(3))], [img], None)
+    cx, cy = G.weight_centres(w, h)
+    for kind in (0, 1):
+        for radius in G.WEIGHT_RADII:
+            g = np.asarray(gpu_ctx.weights(0, kind, radius, cx, cy)).reshape(cx.size, -1)
+            o = leaves[f"weights_k{kind}_r{radius}"]
+            assert np.allclose(g, o, rtol=1e-13, atol=1e-300), (kind, radius, np.abs(g - o).max())
+
+
+@pytest.mark.gpu
+def test_gpu_mvs_matches_scene_golden(scenes_gold, gpu_ctx):
+    cams, imgs, ms = G.arc_scene()
+    gpu_ctx.set_views(cams, imgs, ms)
+    nb = gpu_ctx.select_neighbours(3)
+    assert _same(np.array(nb, np.int32), scenes_gold["arc_neighbours"])
+    for name, P in G.arc_mvs_params().items():
+        gpu_ctx.set_views(cams, imgs, ms)
+        gpu_ctx.set_params(P)
+        for ref in range(len(cams)):
+            gpu_ctx.run_view(ref, nb[ref])
+            _check_maps(gpu_ctx.depth_index(ref), gpu_ctx.depth(ref), gpu_ctx.best_cost(ref),
+                        scenes_gold[f"{name}_v{ref}_index"], scenes_gold[f"{name}_v{ref}_depth"],
+                        scenes_gold[f"{name}_v{ref}_best"], best_tol=1e-12)
+        if name == "arc_mvs_geo_r2":
+            gpu_ctx.cross_check(False, G.ARC_CROSS_THRESH)
+            for v in range(len(cams)):
+                g, o = gpu_ctx.depth(v), scenes_gold[f"{name}_v{v}_crosschecked"]
+                assert ((g == o) | (np.isnan(g) & np.isnan(o))).mean() > 1 - 1e-4
+
+
+@pytest.mark.gpu
+def test_gpu_twoview_matches_scene_golden(scenes_gold, gpu_ctx):
+    cams, imgs, ms = G.arc_scene()
+    gpu_ctx.set_views(cams, imgs, ms)
+    for name, (P, a, b) in G.arc_twoview_params().items():
+        P.keep_cost_volume = 1
+        gpu_ctx.set_params(P)
+        gpu_ctx.run_view(a, [b])
+        _check_maps(gpu_ctx.depth_index(a), gpu_ctx.depth(a), gpu_ctx.best_cost(a), scenes_gold[f"{name}_index"],
+                    scenes_gold[f"{name}_depth"], scenes_gold[f"{name}_best"], best_tol=1e-4)
+        gv = gpu_ctx.cost_volume(1)[0]
+        assert cost_close(gv, scenes_gold[f"{name}_volume"]).mean() <= 1e-4
+    cams2, imgs2 = G.rectified_scene()
+    gpu_ctx.set_views(cams2, imgs2, None)
+    P = G.rectified_params()
+    gpu_ctx.set_params(P)
+    for (a, b) in ((0, 1), (1, 0)):
+        gpu_ctx.run_view(a, [b])
+        _check_maps(gpu_ctx.depth_index(a), gpu_ctx.depth(a), gpu_ctx.best_cost(a), scenes_gold[f"rect_{a}{b}_index"],
+                    scenes_gold[f"rect_{a}{b}_depth"], scenes_gold[f"rect_{a}{b}_best"], best_tol=1e-4)
