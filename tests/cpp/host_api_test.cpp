@@ -1,0 +1,111 @@
+// host_api_test — drives the stereo/ class API (include/stereo, include/project, include/util)
+// the way gui/widgets/stereowidget.cpp:974-1002 does, headless: loads a project XML + image set,
+// runs MultiViewStereo over all cameras and TwoViewStereo over the first two, and dumps raw
+// results for tests/test_host_api.py to compare against the C ABI called directly and the oracle.
+//
+//   host_api_test <project.xml> <imageSetId> <outdir> <minDepth> <maxDepth> <levels> <crossCheck>
+#include <cstdio>
+#include <fstream>
+#include <iostream>
+
+#include "project/project.hpp"
+#include "stereo/adaptiveweight.hpp"
+#include "stereo/geodesicweight.hpp"
+#include "stereo/multiviewstereo.hpp"
+#include "stereo/twoviewstereo.hpp"
+
+template <typename T>
+static void dump(const std::string &path, const T *data, size_t n) {
+    std::ofstream f(path.c_str(), std::ios::binary);
+    f.write(reinterpret_cast<const char *>(data), (std::streamsize)(n * sizeof(T)));
+}
+
+int main(int argc, char **argv) {
+    if (argc < 8) {
+        std::fprintf(stderr, "usage: %s project.xml imageSetId outdir minDepth maxDepth levels crossCheck\n", argv[0]);
+        return 2;
+    }
+    const std::string out = argv[3];
+    const double minDepth = std::atof(argv[4]), maxDepth = std::atof(argv[5]), crossCheck = std::atof(argv[7]);
+    const int levels = std::atoi(argv[6]);
+    try {
+        ProjectPtr project(new Project(argv[1]));
+        ImageSetPtr set = project->imageSet(argv[2]);
+        if (!set) throw std::runtime_error("image set not found");
+        std::vector<CameraPtr> views;
+        for (const auto &kv : project->cameras()) views.push_back(kv.second);  // stereowidget.cpp:985-987
+        std::printf("project: %zu cameras, image set '%s'\n", views.size(), set->name().c_str());
+
+        // ---- MultiViewStereo, as the GUI runs it
+        MultiViewStereo mvs;
+        int lastProgress = -1;
+        std::string lastStage;
+        mvs.onProgressUpdate = [&](int v) { lastProgress = v; };
+        mvs.onStageUpdate = [&](const std::string &s) { lastStage = s; };
+        mvs.initialize(project, set, views, minDepth, maxDepth, levels, crossCheck, 1.0);
+        std::printf("mvs: %zu views loaded, numSteps=%d, title=%s\n", mvs.numViews(), mvs.numSteps(), mvs.title().c_str());
+        mvs.run();
+        std::vector<sr_camera> pods;
+        for (const CameraPtr &c : views) pods.push_back(c->toPod());
+        dump(out + "/cams.bin", pods.data(), pods.size());
+        for (size_t v = 0; v < mvs.numViews(); ++v) {
+            const std::string tag = out + "/mvs_v" + std::to_string(v);
+            dump(tag + "_depth.bin", mvs.depths(v).data(), mvs.depths(v).size());
+            dump(tag + "_index.bin", mvs.indices(v).data(), mvs.indices(v).size());
+            QImage img = mvs.depthMap(views[v]);
+            dump(tag + "_image.bin", img.bits(), (size_t)img.width() * img.height() * 4);
+            std::vector<int32_t> nb(mvs.selectedNeighbours()[v].begin(), mvs.selectedNeighbours()[v].end());
+            dump(tag + "_nbrs.bin", nb.data(), nb.size());
+            std::printf("  view %zu (%s): %.1f%% of in-mask pixels have depth before, %.1f%% after cross-check\n", v,
+                        views[v]->name().c_str(), 100 * mvs.coverageBeforeCrossCheck()[v], 100 * mvs.coverageAfterCrossCheck()[v]);
+        }
+        std::printf("mvs: last stage '%s', last progress %d, unknown view -> null image: %d\n", lastStage.c_str(), lastProgress,
+                    (int)mvs.depthMap(CameraPtr(new Camera("nope", "nope"))).isNull());
+        const std::vector<PLYPoint> cloud = mvs.pointCloud();
+        outputPLYFile(out + "/cloud.ply", cloud);
+        std::printf("mvs: point cloud of %zu points written\n", cloud.size());
+
+        // ---- TwoViewStereo on the first two views (library API only in the reference)
+        if (views.size() >= 2) {
+            QImage l(set->defaultImageForCamera(views[0])->file()), r(set->defaultImageForCamera(views[1])->file());
+            TwoViewStereo two(views[0], l, QImage(), views[1], r, QImage(), minDepth, maxDepth, levels, 1.0);
+            two.params().radius = 2;               // keep the harness quick; the reference constant is 5
+            two.setCrossCheckThreshold(30.0);
+            two.run();
+            dump(out + "/two_left_depth.bin", two.leftDepths().data(), two.leftDepths().size());
+            dump(out + "/two_right_depth.bin", two.rightDepths().data(), two.rightDepths().size());
+            dump(out + "/two_left_index.bin", two.leftIndices().data(), two.leftIndices().size());
+            QImage li = two.leftDepthMap();
+            dump(out + "/two_left_image.bin", li.bits(), (size_t)li.width() * li.height() * 4);
+            // the public curve preview
+            const Ray3d ray = views[0]->unproject((l.width() / 2 + 0.5), (l.height() / 2 + 0.5));
+            const auto curve = two.epipolarCurve(ray, views[0]->C(), views[0]->principleRay().direction(), VectorImage(), views[1]);
+            std::vector<int32_t> cp;
+            for (const auto &p : curve) { cp.push_back((int32_t)p[0]); cp.push_back((int32_t)p[1]); }
+            dump(out + "/two_curve.bin", cp.data(), cp.size());
+            std::printf("two-view: done, centre-pixel epipolar curve has %zu pixels\n", curve.size());
+        }
+
+        // ---- weight functors, reference call shape: init_weights(img, x, y) then operator()(row, col)
+        {
+            VectorImage img = VectorImage::fromFile(set->defaultImageForCamera(views[0])->file());
+            GeodesicWeight gw(2);
+            AdaptiveWeight aw(2);
+            const int cx = img.width() / 3, cy = img.height() / 2;
+            gw.init_weights(img, cx, cy);
+            aw.init_weights(img, cx, cy);
+            std::vector<double> wv;
+            for (int row = -2; row <= 2; ++row)
+                for (int col = -2; col <= 2; ++col) wv.push_back(gw(row, col));
+            for (int row = -2; row <= 2; ++row)
+                for (int col = -2; col <= 2; ++col) wv.push_back(aw(row, col));
+            dump(out + "/weights.bin", wv.data(), wv.size());
+            std::printf("weights: geodesic centre %.3f, adaptive centre %.3f\n", gw(0, 0), aw(0, 0));
+        }
+    } catch (const std::exception &e) {
+        std::fprintf(stderr, "host_api_test: %s\n", e.what());
+        return 1;
+    }
+    std::printf("OK\n");
+    return 0;
+}

@@ -1,0 +1,148 @@
+"""The C++ class API (include/stereo, include/project, include/util) end to end on the GPU.
+
+tests/cpp/host_api_test.cpp is compiled by __graft_entry__.build() against the C-ABI library and
+drives Project / ImageSet / Camera / MultiViewStereo / TwoViewStereo / GeodesicWeight /
+AdaptiveWeight the way the reference GUI does (gui/widgets/stereowidget.cpp:974-1002).  This test
+writes a project XML + RGBA PNGs (alpha = mask), runs the harness, and checks its raw outputs
+against the C ABI called directly with the harness's own camera PODs, and against the oracle."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from stereoreconstruction_b200 import capi, types as T
+from scene_util import refractive_arc_scene
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HARNESS = os.path.join(ROOT, "stereoreconstruction_b200", "host_api_test")
+
+
+def write_project(tmp, cams, imgs, masks):
+    from PIL import Image
+    os.makedirs(os.path.join(tmp, "images"), exist_ok=True)
+    xml = ["<project>", " <cameras>"]
+    for i, c in enumerate(cams):
+        K = np.array(c.K).reshape(3, 3)
+        R = np.array(c.R).reshape(3, 3)
+        t = np.array(c.t)
+        P = K @ np.hstack([R, t[:, None]])
+        attrs = " ".join(f'm{r + 1}{k + 1}="{P[r, k]:.17g}"' for r in range(3) for k in range(4))
+        xml.append(f'  <camera id="cam{i}" name="view {i}">')
+        xml.append(f"   <projectionMatrix {attrs}/>")
+        d = list(c.dist)
+        xml.append(f'   <lensDistortion k1="{d[0]:.17g}" k2="{d[1]:.17g}" p1="{d[2]:.17g}" p2="{d[3]:.17g}" k3="{d[4]:.17g}"/>')
+        if c.is_refractive:
+            kn = K @ np.array(c.plane_n)
+            xml.append(f'   <refractiveInterface px="{kn[0] / kn[2]:.17g}" py="{kn[1] / kn[2]:.17g}" '
+                       f'dist="{c.plane_d:.17g}" refractiveRatio="{c.n:.17g}"/>')
+        xml.append("  </camera>")
+    xml += [" </cameras>", " <imageSets>", '  <imageSet root="images" id="set0" name="synthetic arc">']
+    for i, (im, m) in enumerate(zip(imgs, masks)):
+        rgba = im.copy()
+        rgba[..., 3] = m
+        Image.fromarray(rgba, "RGBA").save(os.path.join(tmp, "images", f"v{i}.png"))
+        xml.append(f'   <image for="cam{i}" default="yes" file="v{i}.png"/>')
+    xml += ["  </imageSet>", " </imageSets>", "</project>"]
+    path = os.path.join(tmp, "project.xml")
+    with open(path, "w") as f:
+        f.write("\n".join(xml))
+    return path
+
+
+def test_harness_is_built():
+    assert os.path.exists(HARNESS), "run __graft_entry__.build()"
+
+
+@pytest.mark.gpu
+def test_cpp_class_api_end_to_end(tmp_path):
+    cams, imgs, ms, _ = refractive_arc_scene(V=4, w=96, h=64, masks=True)
+    h, w = imgs[0].shape[:2]
+    proj = write_project(str(tmp_path), cams, imgs, ms)
+    out = str(tmp_path)
+    mind, maxd, levels, cross = 420.0, 580.0, 32, 12.0
+    r = subprocess.run([HARNESS, proj, "set0", out, str(mind), str(maxd), str(levels), str(cross)],
+                       capture_output=True, text=True, timeout=600)
+    print(r.stdout, r.stderr)
+    assert r.returncode == 0 and r.stdout.strip().endswith("OK"), r.stderr
+
+    # the camera PODs the C++ Camera class derived from the XML (setP -> RQ decomposition)
+    raw = np.fromfile(os.path.join(out, "cams.bin"), dtype=np.uint8)
+    V = len(cams)
+    assert raw.size == V * C.sizeof(T.SrCamera)
+    pods = [T.SrCamera.from_buffer_copy(raw[i * C.sizeof(T.SrCamera):(i + 1) * C.sizeof(T.SrCamera)].tobytes()) for i in range(V)]
+    for a, b in zip(pods, cams):  # the decomposition recovers the cameras the XML was written from
+        assert np.allclose(np.array(a.K), np.array(b.K), rtol=1e-9, atol=1e-7)
+        assert np.allclose(np.array(a.R), np.array(b.R), atol=1e-10)
+        assert np.allclose(np.array(a.C), np.array(b.C), atol=1e-7)
+        assert np.allclose(np.array(a.plane_n), np.array(b.plane_n), atol=1e-10)
+        assert a.is_refractive == b.is_refractive and a.is_distorted == b.is_distorted
+
+    # MultiViewStereo == the C ABI driven directly with the same PODs (bit for bit), == oracle
+    masks = [np.where(m == 255, 255, 0).astype(np.uint8) for m in ms]
+    rgba = []
+    for im, m in zip(imgs, ms):
+        x = im.copy()
+        x[..., 3] = m
+        rgba.append(x)
+    ctx = capi.Context(0)
+    ctx.set_views(pods, rgba, masks)
+    P = T.default_params(True, mind, maxd, levels)
+    ctx.set_params(P)
+    nb = ctx.select_neighbours(3)
+    for v in range(V):
+        ctx.run_view(v, nb[v])
+    ctx.cross_check(False, cross)
+    from oracle import oracle_api as O
+    sc = O.Scene(pods, rgba, masks)
+    before = []
+    for v in range(V):
+        od, _, _, _, _ = sc.mvs_view(P, v, nb[v])
+        before.append(od)
+    want = sc.crosscheck_mvs(P, before, cross)
+    for v in range(V):
+        gd = np.fromfile(os.path.join(out, f"mvs_v{v}_depth.bin"), dtype=np.float64).reshape(h, w)
+        gi = np.fromfile(os.path.join(out, f"mvs_v{v}_index.bin"), dtype=np.int32).reshape(h, w)
+        gn = np.fromfile(os.path.join(out, f"mvs_v{v}_nbrs.bin"), dtype=np.int32)
+        assert list(gn) == nb[v]
+        d = ctx.depth(v)
+        assert ((gd == d) | (np.isnan(gd) & np.isnan(d))).all()
+        assert (gi == ctx.depth_index(v)).all()
+        assert ((gd == want[v]) | (np.isnan(gd) & np.isnan(want[v]))).mean() > 1 - 1e-4
+        img = np.fromfile(os.path.join(out, f"mvs_v{v}_image.bin"), dtype=np.uint8).reshape(h, w, 4)
+        fin = np.isfinite(gd) & (masks[v] == 255) & ~(gd + 1e-5 < mind)
+        t = np.clip((gd[fin] - mind) / (maxd - mind), 0, 1)
+        assert (img[..., 0][fin] == (255 * t).astype(np.int64)).all()  # colorFromDepth, multiviewstereo.cpp:257-278
+        assert (img[..., 0][~fin] == 255).all()
+        assert np.isfinite(gd).sum() > 0
+
+    # TwoViewStereo (no masks, radius 2, cross-check 30) == the C ABI directly
+    two = [pods[0], pods[1]]
+    plain = [rgba[0], rgba[1]]  # QImage(file) keeps the alpha byte; the mask argument was null
+    ctx.set_views(two, plain, None)
+    P2 = T.default_params(False, mind, maxd, levels, radius=2)
+    ctx.set_params(P2)
+    ctx.run_view(0, [1])
+    ctx.run_view(1, [0])
+    ctx.cross_check(True, 30.0)
+    for name, v in (("left", 0), ("right", 1)):
+        gd = np.fromfile(os.path.join(out, f"two_{name}_depth.bin"), dtype=np.float64).reshape(h, w)
+        d = ctx.depth(v)
+        assert ((gd == d) | (np.isnan(gd) & np.isnan(d))).all()
+    li = np.fromfile(os.path.join(out, "two_left_image.bin"), dtype=np.uint8).reshape(h, w, 4)
+    gd = np.fromfile(os.path.join(out, "two_left_depth.bin"), dtype=np.float64).reshape(h, w)
+    assert (li[..., :3][~np.isfinite(gd)] == 0).all() and np.isfinite(gd).sum() > 0
+    # the public epipolar-curve preview against the oracle's curve (two-view flavour, no mask)
+    sc2 = O.Scene(two, plain, None)
+    curve = np.fromfile(os.path.join(out, "two_curve.bin"), dtype=np.int32).reshape(-1, 2)
+    want_curve = sc2.epipolar_curve(P2, 0, 1, w // 2, h // 2, mvs=False)
+    assert curve.shape == want_curve.shape and (curve == want_curve).all()
+
+    # weight functors == sr_compute_weights == oracle
+    wv = np.fromfile(os.path.join(out, "weights.bin"), dtype=np.float64).reshape(2, 5, 5)
+    cx, cy = np.array([w // 3], np.int32), np.array([h // 2], np.int32)
+    sc1 = O.Scene([pods[0]], [rgba[0]], None)
+    assert np.allclose(wv[0], sc1.weights(0, T.SR_WEIGHT_GEODESIC, 2, cx, cy)[0], rtol=1e-13, atol=1e-300)
+    assert np.allclose(wv[1], sc1.weights(0, T.SR_WEIGHT_ADAPTIVE, 2, cx, cy)[0], rtol=1e-13, atol=1e-300)
+    ctx.close()
