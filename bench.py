@@ -240,6 +240,7 @@ def main():
     stages = ctx.stage_ms()
     if os.environ.get("SR_MATCH_STATS"):
         print("match stats:", ctx.match_stats(), file=sys.stderr)
+        print("build stats:", ctx.build_stats(), file=sys.stderr)
     ctx.set_profiling(False)
     launches = ctx.launch_count() - launches0
     if world > 1:

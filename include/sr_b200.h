@@ -126,6 +126,12 @@ int sr_get_stage_ms(sr_ctx *ctx, double *out4);
  * [5] bit pattern (low 32 bits, IEEE float) of the largest |ncc32 - ncc64| seen on a verified label,
  * [6] verified labels whose FP32 value lay outside its error bar (must be 0). */
 int sr_get_match_stats(sr_ctx *ctx, uint64_t *out8);
+/* Self-check counters of the refractive tap-volume build (same switch, SR_MATCH_STATS=1): with
+ * the switch on, every interpolated label is ALSO projected exactly.  out4[0] labels taken from
+ * the anchor interpolation, [1] labels that fell back to the exact projection because the
+ * interpolated coordinate was within the guard of a pixel boundary, [2] interpolated labels
+ * whose integer tap differs from the exact projection's (must be 0). */
+int sr_get_build_stats(sr_ctx *ctx, uint64_t *out4);
 
 /* ---- inputs -----------------------------------------------------------------*/
 /* Replaces the image/mask ingestion of TwoViewStereo::TwoViewStereo

@@ -23,7 +23,7 @@ HEADERS = ["csrc/sr_geometry.cuh", "csrc/sr_kernels.cuh", "csrc/sr_match_dispatc
 
 EXPORTS = [
     "sr_ctx_create", "sr_ctx_destroy", "sr_last_error", "sr_request_cancel", "sr_clear_cancel",
-    "sr_set_stream", "sr_params_default", "sr_launch_count", "sr_set_profiling", "sr_get_stage_ms", "sr_get_match_stats", "sr_set_views", "sr_set_params",
+    "sr_set_stream", "sr_params_default", "sr_launch_count", "sr_set_profiling", "sr_get_stage_ms", "sr_get_match_stats", "sr_get_build_stats", "sr_set_views", "sr_set_params",
     "sr_run_view", "sr_run_view_curve", "sr_select_neighbours", "sr_cross_check", "sr_synchronize",
     "sr_get_depth_index", "sr_get_depth", "sr_get_best_cost", "sr_get_cost_volume", "sr_set_depth",
     "sr_get_depth_image", "sr_unproject_grid", "sr_project_points", "sr_compute_weights",
@@ -108,6 +108,11 @@ class Context:
     def _ck(self, rc):
         if rc != 0:
             raise SrError(f"sr error {rc}: {self._L.sr_last_error(self._h).decode()}")
+
+    def build_stats(self):
+        out = np.zeros(4, np.uint64)
+        self._ck(self._L.sr_get_build_stats(self._h, _p(out)))
+        return dict(interpolated=int(out[0]), guard_fallbacks=int(out[1]), tap_mismatches=int(out[2]))
 
     def match_stats(self):
         out = np.zeros(8, np.uint64)

@@ -35,6 +35,8 @@ struct BuildRefrArgs {
     int32_t *taps;               // [D][rows][w] for this neighbour
     int w, h, row0, rows, D, d_chunk;
     int mvs;
+    unsigned long long *check;   // optional [4] (SR_BUILD_CHECK=1): labels interpolated, guard fall-backs,
+                                 // interpolated labels whose tap differs from the exact projection (must be 0)
 };
 
 __device__ __forceinline__ double rcp_approx(double a) {  // ~2^-20 relative (MUFU.RCP64H)
@@ -42,6 +44,20 @@ __device__ __forceinline__ double rcp_approx(double a) {  // ~2^-20 relative (MU
     asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(a));
     return r;
 }
+
+// Labels between two anchors are not re-projected: the pixel coordinate (U,V)(label) is an
+// analytic, slowly varying function of the label, so it is read off the cubic through the four
+// surrounding ANCHOR labels (every BUILD_STRIDE-th label, projected exactly as above).  What
+// must be exact is only trunc(U), trunc(V): the interpolated value is accepted when it is farther
+// from the nearest integer than a guard, otherwise that label is projected exactly as well.
+//   guard = |cubic - quadratic| + 1e-6 px = |third difference| * L2(x) + 1e-6
+// i.e. the full error of the NEXT-LOWER-order interpolant, ~100x the cubic's own error for these
+// functions (each higher difference shrinks by ~BUILD_STRIDE*dDepth/Depth ~ 1e-2).  With the
+// guard ~1e-4 px a label falls back with probability ~4e-4.
+#ifndef SR_BUILD_STRIDE
+#define SR_BUILD_STRIDE 4
+#endif
+constexpr int BUILD_STRIDE = SR_BUILD_STRIDE;
 
 __global__ void __launch_bounds__(128) build_refr_kernel(const __grid_constant__ BuildRefrArgs a) {
     const int pid = blockIdx.x * blockDim.x + threadIdx.x;
@@ -71,75 +87,73 @@ __global__ void __launch_bounds__(128) build_refr_kernel(const __grid_constant__
     const double dd = pd * pd, n1 = a.nbr.n, n2 = n1 * n1;
     const bool distorted = a.nbr.is_distorted != 0;
     const double *k = a.nbr.dist;
+    const int D = a.D;
 
-    const int d0 = blockIdx.y * a.d_chunk;
-    const int d1 = min(d0 + a.d_chunk, a.D);
-    const size_t plane = (size_t)a.rows * a.w;
-    double r1 = 0.0, r2 = 0.0, r3 = 0.0;  // rho of the previous three labels
-    int nhist = 0;
-#pragma unroll 1
-    for (int d = d0; d < d1; ++d) {
-        int32_t tap = TAP_NONE;
+    // Exact projection of label d.  rho_guess in [0,1] or < 0 (paraxial start).  Outputs the
+    // coordinate that is truncated (U,V) and the root rho.
+    auto project_label = [&](int d, double rho_guess, double &U, double &V, double &rho_out) -> bool {
         const double t = fma(a.depth_table[d], tA, tB);
-        bool ok = ray_ok && !(t < 1e-10);
-        double rho = 0.0;
+        if (!ray_ok || t < 1e-10) return false;
         const d3 radv = faxpy(t, R1, R0);
         const double rr = fdot(radv, radv);
-        if (ok) {
-            const double av = fma(t, a1, a0);
-            const double h = fabs(av) - pd, hh = h * h;
-            ok = rr > 0.0;  // on the axis dir = radv/r is NaN in the reference: no root is accepted
-            if (ok) {
-                if (nhist >= 3) rho = fma(3.0, r1 - r2, r3);
-                else if (nhist == 2) rho = fma(2.0, r1, -r2);
-                else if (nhist == 1) rho = r1;
-                else rho = n1 * fabs(pd) / (fabs(h) + n1 * fabs(pd) + 1e-300);  // paraxial
-                rho = fmin(fmax(rho, 0.0), 1.0);
-                bool conv = false;
+        if (!(rr > 0.0)) return false;  // on the axis dir = radv/r is NaN in the reference: no root is accepted
+        const double av = fma(t, a1, a0);
+        const double h = fabs(av) - pd, hh = h * h;
+        double rho = (rho_guess >= 0.0) ? rho_guess : n1 * fabs(pd) / (fabs(h) + n1 * fabs(pd) + 1e-300);
+        rho = fmin(fmax(rho, 0.0), 1.0);
+        bool conv = false;
 #pragma unroll 1
-                for (int it = 0; it < 8; ++it) {
-                    const double s = 1.0 - rho;
-                    const double p2 = rho * rho, s2 = s * s;
-                    const double A = fma(p2, rr, dd), B = fma(s2, rr, hh);
-                    const double G = fma(p2, B, -((n2 * s2) * A));
-                    const double u = fma(n2, s, rho);
-                    // G'/2 = rho*B + n^2 s A - rho s rr (rho + n^2 s)
-                    const double g2 = fma(n2 * s, A, fma(rho, B, -(((rho * s) * rr) * u)));
-                    const double step = (0.5 * G) * rcp_approx(g2);
-                    rho -= step;
-                    if (fabs(step) <= 3e-8) {
-                        conv = true;
-                        break;
-                    }
-                    rho = fmin(fmax(rho, 0.0), 1.0);
-                }
-                if (!conv || !(rho >= 0.0 && rho <= 1.0)) {
-                    const double r = sqrt(rr);
-                    rho = snell_root_robust(r, pd, h, n1, -1.0) / r;
-                }
-                ok = rho == rho;
+        for (int it = 0; it < 8; ++it) {
+            const double s = 1.0 - rho;
+            const double p2 = rho * rho, s2 = s * s;
+            const double A = fma(p2, rr, dd), B = fma(s2, rr, hh);
+            const double G = fma(p2, B, -((n2 * s2) * A));
+            const double u = fma(n2, s, rho);
+            // G'/2 = rho*B + n^2 s A - rho s rr (rho + n^2 s)
+            const double g2 = fma(n2 * s, A, fma(rho, B, -(((rho * s) * rr) * u)));
+            const double step = (0.5 * G) * rcp_approx(g2);
+            rho -= step;
+            if (fabs(step) <= 3e-8) {
+                conv = true;
+                break;
             }
+            rho = fmin(fmax(rho, 0.0), 1.0);
         }
+        if (!conv || !(rho >= 0.0 && rho <= 1.0)) {
+            const double r = sqrt(rr);
+            rho = snell_root_robust(r, pd, h, n1, -1.0) / r;
+        }
+        if (!(rho == rho)) return false;
+        rho_out = rho;
+        // point on the interface = rho*radv + d*N (camera.cpp:127); K*point hoisted
+        const d3 Kr = faxpy(t, KR1, KR0);
+        const d3 p = faxpy(rho, Kr, KdN);
+        const double iz = fast_rcp(p.z);
+        double xn = p.x * iz, yn = p.y * iz;
+        if (distorted) {  // camera.cpp:395-416 on normalised coordinates
+            const double q2 = fma(xn, xn, yn * yn);
+            const double cdist = fma(fma(fma(k[4], q2, k[1]), q2, k[0]), q2, 1.0);
+            const double xo = xn, yo = yn;
+            xn = fma(xo, cdist, fma(2 * k[2] * xo, yo, k[3] * fma(2 * xo, xo, q2)));
+            // camera.cpp:411-412: y's tangential term uses the already-distorted x
+            yn = fma(yo, cdist, fma(k[2], fma(2 * yo, yo, q2), 2 * k[3] * xn * yo));
+        }
+        U = fma(a.fxs, xn, a.cxs);
+        V = fma(a.fys, yn, a.cys);
+        return true;
+    };
+
+    const size_t plane = (size_t)a.rows * a.w;
+    auto emit = [&](int d, bool ok, double U, double V) {
+        int32_t tap = TAP_NONE;
         if (ok) {
-            r3 = r2;
-            r2 = r1;
-            r1 = rho;
-            ++nhist;
-            // point on the interface = rho*radv + d*N (camera.cpp:127); K*point hoisted
-            const d3 Kr = faxpy(t, KR1, KR0);
-            const d3 p = faxpy(rho, Kr, KdN);
-            const double iz = fast_rcp(p.z);
-            double xn = p.x * iz, yn = p.y * iz;
-            if (distorted) {  // camera.cpp:395-416 on normalised coordinates
-                const double q2 = fma(xn, xn, yn * yn);
-                const double cdist = fma(fma(fma(k[4], q2, k[1]), q2, k[0]), q2, 1.0);
-                const double xo = xn, yo = yn;
-                xn = fma(xo, cdist, fma(2 * k[2] * xo, yo, k[3] * fma(2 * xo, xo, q2)));
-                // camera.cpp:411-412: y's tangential term uses the already-distorted x
-                yn = fma(yo, cdist, fma(k[2], fma(2 * yo, yo, q2), 2 * k[3] * xn * yo));
+            // x86 cvttsd2si: out of range / NaN -> INT_MIN; any |coordinate| >= TAP_CLAMP is
+            // outside every window of every image, so one range test serves both coordinates
+            int tx = INT32_MIN, ty = INT32_MIN;
+            if (fabs(U) + fabs(V) < 2.0e9) {
+                tx = __double2int_rz(U);
+                ty = __double2int_rz(V);
             }
-            int tx = to_int_x86(fma(a.fxs, xn, a.cxs));
-            int ty = to_int_x86(fma(a.fys, yn, a.cys));
             bool keep = true;
             if (a.mvs)  // multiviewstereo.cpp:787: only WHITE neighbour-mask pixels are candidates
                 keep = tx >= 0 && ty >= 0 && tx < a.w && ty < a.h && a.nbr_mask[(size_t)ty * a.w + tx] == 255;
@@ -148,10 +162,90 @@ __global__ void __launch_bounds__(128) build_refr_kernel(const __grid_constant__
                 ty = max(-TAP_CLAMP, min(TAP_CLAMP, ty));
                 tap = (int32_t)(((uint32_t)(ty & 0xffff) << 16) | (uint32_t)(tx & 0xffff));
             }
-        } else {
-            nhist = 0;
         }
         a.taps[(size_t)d * plane + pid] = tap;
+    };
+
+    constexpr int S = BUILD_STRIDE;
+    const int d0 = blockIdx.y * a.d_chunk;  // d_chunk is a multiple of S
+    const int d1 = min(d0 + a.d_chunk, D);
+    // anchor window: labels (k-1)S, kS, (k+1)S, (k+2)S for the interval [kS, (k+1)S)
+    double au[4], av_[4], ar[4];
+    bool aok[4];
+    auto anchor = [&](int slot, int d, double guess) {
+        aok[slot] = false;
+        if (d >= 0 && d < D) aok[slot] = project_label(d, guess, au[slot], av_[slot], ar[slot]);
+    };
+    const int kfirst = d0 / S;
+    anchor(0, (kfirst - 1) * S, -1.0);
+    anchor(1, kfirst * S, aok[0] ? ar[0] : -1.0);
+    anchor(2, (kfirst + 1) * S, (aok[0] && aok[1]) ? fma(2.0, ar[1], -ar[0]) : (aok[1] ? ar[1] : -1.0));
+    // Lagrange weights of the cubic through nodes -1,0,1,2 at x = s/S and of its top term L2(x)
+    double lw[S][4], l2[S];
+#pragma unroll
+    for (int s = 1; s < S; ++s) {
+        const double xq = (double)s / S;
+        lw[s][0] = -xq * (xq - 1) * (xq - 2) / 6;
+        lw[s][1] = (xq + 1) * (xq - 1) * (xq - 2) / 2;
+        lw[s][2] = -(xq + 1) * xq * (xq - 2) / 2;
+        lw[s][3] = (xq + 1) * xq * (xq - 1) / 6;
+        l2[s] = fabs(lw[s][3]);
+    }
+#pragma unroll 1
+    for (int kk = kfirst; kk * S < d1; ++kk) {
+        {
+            double g = -1.0;
+            if (aok[0] && aok[1] && aok[2]) g = fma(3.0, ar[2] - ar[1], ar[0]);
+            else if (aok[1] && aok[2]) g = fma(2.0, ar[2], -ar[1]);
+            else if (aok[2]) g = ar[2];
+            anchor(3, (kk + 2) * S, g);
+        }
+        const int db = kk * S;
+        emit(db, aok[1], au[1], av_[1]);
+        const bool full = aok[0] && aok[1] && aok[2] && aok[3];
+        double d3u = 0.0, d3v = 0.0;
+        if (full) {
+            d3u = fabs((au[3] - au[0]) - 3.0 * (au[2] - au[1]));
+            d3v = fabs((av_[3] - av_[0]) - 3.0 * (av_[2] - av_[1]));
+        }
+#pragma unroll
+        for (int s = 1; s < S; ++s) {
+            const int d = db + s;
+            if (d >= d1) break;
+            bool done = false;
+            if (full) {
+                const double U = fma(lw[s][0], au[0], fma(lw[s][1], au[1], fma(lw[s][2], au[2], lw[s][3] * au[3])));
+                const double V = fma(lw[s][0], av_[0], fma(lw[s][1], av_[1], fma(lw[s][2], av_[2], lw[s][3] * av_[3])));
+                const double gu = fma(l2[s], d3u, 1e-6), gv = fma(l2[s], d3v, 1e-6);
+                if (fabs(U - rint(U)) > gu && fabs(V - rint(V)) > gv) {
+                    emit(d, true, U, V);
+                    done = true;
+                    if (a.check) {  // self-check: the interpolated tap against the exact projection
+                        double Ue, Ve, re;
+                        const bool oke = project_label(d, fma((double)s / S, ar[2] - ar[1], ar[1]), Ue, Ve, re);
+                        atomicAdd(a.check + 0, 1ull);
+                        if (!oke || __double2int_rz(Ue) != __double2int_rz(U) || __double2int_rz(Ve) != __double2int_rz(V))
+                            atomicAdd(a.check + 2, 1ull);
+                    }
+                } else if (a.check) {
+                    atomicAdd(a.check + 1, 1ull);
+                }
+            }
+            if (!done) {  // too close to a pixel boundary, or no full stencil: project this label exactly
+                double U, V, rho;
+                double g = -1.0;
+                if (aok[1] && aok[2]) g = fma((double)s / S, ar[2] - ar[1], ar[1]);
+                const bool ok = project_label(d, g, U, V, rho);
+                emit(d, ok, U, V);
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            au[i] = au[i + 1];
+            av_[i] = av_[i + 1];
+            ar[i] = ar[i + 1];
+            aok[i] = aok[i + 1];
+        }
     }
 }
 

@@ -212,8 +212,8 @@ int sr_ctx_create(int device, sr_ctx **out) {
     if (const char *sb = getenv("SR_BUILD_REFR")) c->use_refr_build = atoi(sb) != 0;
     if (const char *sk = getenv("SR_BUILD_CHUNK")) c->refr_chunk = std::max(4, atoi(sk));
     if (const char *ss = getenv("SR_MATCH_STATS")) {
-        if (atoi(ss) != 0 && cudaMalloc(&c->d_stats, 8 * sizeof(unsigned long long)) == cudaSuccess)
-            cudaMemset(c->d_stats, 0, 8 * sizeof(unsigned long long));
+        if (atoi(ss) != 0 && cudaMalloc(&c->d_stats, 16 * sizeof(unsigned long long)) == cudaSuccess)
+            cudaMemset(c->d_stats, 0, 16 * sizeof(unsigned long long));
     }
     *out = c;
     return SR_OK;
@@ -453,8 +453,9 @@ int sr_run_view(sr_ctx *ctx, int ref, const int32_t *nbrs, int nn) {
                 ra.row0 = b0;
                 ra.rows = rows;
                 ra.D = D;
-                ra.d_chunk = ctx->refr_chunk;
+                ra.d_chunk = std::max(BUILD_STRIDE, ctx->refr_chunk - ctx->refr_chunk % BUILD_STRIDE);
                 ra.mvs = mvs;
+                ra.check = ctx->d_stats ? ctx->d_stats + 8 : nullptr;
                 build_refr_kernel<<<dim3(gx, (D + ra.d_chunk - 1) / ra.d_chunk), 128, 0, st>>>(ra);
                 CKL();
                 continue;
@@ -568,6 +569,15 @@ int sr_get_stage_ms(sr_ctx *ctx, double *out4) {
 // Debug counters of match_mvs_screen_kernel accumulated since context creation (SR_MATCH_STATS=1):
 // out[0] pixels, [1] labels screened in FP32, [2] labels forced to FP64, [3] FP64 verifications,
 // [4] pixels whose reference window is evaluated in FP64 only.
+int sr_get_build_stats(sr_ctx *ctx, uint64_t *out4) {
+    if (!ctx || !out4) return SR_ERR_INVALID;
+    if (!ctx->d_stats) return fail(ctx, SR_ERR_STATE, "build statistics are off (set SR_MATCH_STATS=1 before sr_ctx_create)");
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaStreamSynchronize(ctx->stream));
+    CK(cudaMemcpy(out4, ctx->d_stats + 8, 4 * sizeof(uint64_t), cudaMemcpyDeviceToHost));
+    return SR_OK;
+}
+
 int sr_get_match_stats(sr_ctx *ctx, uint64_t *out8) {
     if (!ctx || !out8) return SR_ERR_INVALID;
     if (!ctx->d_stats) return fail(ctx, SR_ERR_STATE, "match statistics are off (set SR_MATCH_STATS=1 before sr_ctx_create)");

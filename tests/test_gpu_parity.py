@@ -253,3 +253,22 @@ def test_mvs_screen_equals_all_fp64_kernel(monkeypatch):
     assert (i0 == i1).all(), f"{(i0 != i1).sum()} pixels differ"
     lab = i0 >= 0
     assert np.abs(b0[lab] - b1[lab]).max() <= 1e-9
+
+
+def test_build_interpolation_self_check(monkeypatch):
+    """The refractive build projects every 4th label exactly and reads the labels in between off a
+    cubic through the anchors, guarded by the distance to the nearest pixel boundary.  With the
+    self-check on, every interpolated label is also projected exactly: no tap may differ."""
+    monkeypatch.setenv("SR_MATCH_STATS", "1")
+    cams, imgs, ms, surf = refractive_arc_scene(V=4, w=320, h=200, arc_deg=25.0, cell=6.0)
+    c = capi.Context(0)
+    c.set_views(cams, imgs, None)
+    for D in (96, 37, 7):  # also label counts that are not multiples of the anchor stride
+        c.set_params(T.default_params(True, 420.0, 580.0, D))
+        nb = c.select_neighbours(3)
+        c.run_view(1, nb[1])
+    st = c.build_stats()
+    c.close()
+    assert st["interpolated"] > 1e6
+    assert st["tap_mismatches"] == 0
+    assert st["guard_fallbacks"] < 0.01 * st["interpolated"]
