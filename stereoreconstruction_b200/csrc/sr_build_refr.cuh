@@ -31,7 +31,7 @@ struct BuildRefrArgs {
     const double *rays;          // [6][h][w] of the reference view
     const double *depth_table;   // [D]
     const uint8_t *ref_mask;
-    const uint8_t *nbr_mask;
+    const uint8_t *nbr_mask;     // null: every neighbour pixel is WHITE (no mask was given)
     int32_t *taps;               // [D][rows][w] for this neighbour
     int w, h, row0, rows, D, d_chunk;
     int mvs;
@@ -144,26 +144,17 @@ __global__ void __launch_bounds__(128) build_refr_kernel(const __grid_constant__
     };
 
     const size_t plane = (size_t)a.rows * a.w;
-    auto emit = [&](int d, bool ok, double U, double V) {
-        int32_t tap = TAP_NONE;
-        if (ok) {
-            // x86 cvttsd2si: out of range / NaN -> INT_MIN; any |coordinate| >= TAP_CLAMP is
-            // outside every window of every image, so one range test serves both coordinates
-            int tx = INT32_MIN, ty = INT32_MIN;
-            if (fabs(U) + fabs(V) < 2.0e9) {
-                tx = __double2int_rz(U);
-                ty = __double2int_rz(V);
-            }
-            bool keep = true;
-            if (a.mvs)  // multiviewstereo.cpp:787: only WHITE neighbour-mask pixels are candidates
-                keep = tx >= 0 && ty >= 0 && tx < a.w && ty < a.h && a.nbr_mask[(size_t)ty * a.w + tx] == 255;
-            if (keep) {
-                tx = max(-TAP_CLAMP, min(TAP_CLAMP, tx));
-                ty = max(-TAP_CLAMP, min(TAP_CLAMP, ty));
-                tap = (int32_t)(((uint32_t)(ty & 0xffff) << 16) | (uint32_t)(tx & 0xffff));
-            }
-        }
-        a.taps[(size_t)d * plane + pid] = tap;
+    // trunc toward zero of a coordinate without the conversion pipe (F2I.F64 issues at 16
+    // lanes/clk/SM): r = rint(|c|) through the 1.5*2^52 constant, whose sum carries the integer in
+    // its low word; diff = |c| - r is exact and tells floor from rint.  Also returns |diff|, the
+    // distance to the nearest integer (the guard test).  Valid for |c| < 2^31; callers clamp.
+    auto trunc_magic = [](double c, double &dist) -> int {
+        const double MAGIC = 6755399441055744.0;
+        const double m = fabs(c) + MAGIC;
+        const double diff = fabs(c) - (m - MAGIC);
+        dist = fabs(diff);
+        const int fl = __double2loint(m) + (__double2hiint(diff) >> 31);  // rint - [diff < 0]
+        return (__double2hiint(c) < 0) ? -fl : fl;
     };
 
     constexpr int S = BUILD_STRIDE;
@@ -171,10 +162,14 @@ __global__ void __launch_bounds__(128) build_refr_kernel(const __grid_constant__
     const int d1 = min(d0 + a.d_chunk, D);
     // anchor window: labels (k-1)S, kS, (k+1)S, (k+2)S for the interval [kS, (k+1)S)
     double au[4], av_[4], ar[4];
-    bool aok[4];
+    bool aok[4], asane[4];
     auto anchor = [&](int slot, int d, double guess) {
         aok[slot] = false;
+        au[slot] = av_[slot] = ar[slot] = 0.0;
         if (d >= 0 && d < D) aok[slot] = project_label(d, guess, au[slot], av_[slot], ar[slot]);
+        // an anchor far outside any image (a projection near the camera plane) is not interpolated
+        // through: the labels around it are projected exactly, and the cubic never leaves 2^31
+        asane[slot] = aok[slot] && fabs(au[slot]) + fabs(av_[slot]) < 1.0e6;
     };
     const int kfirst = d0 / S;
     anchor(0, (kfirst - 1) * S, -1.0);
@@ -191,6 +186,7 @@ __global__ void __launch_bounds__(128) build_refr_kernel(const __grid_constant__
         lw[s][3] = (xq + 1) * xq * (xq - 1) / 6;
         l2[s] = fabs(lw[s][3]);
     }
+    const double CL = 30000.0;  // beyond any image: |c| >= TAP_CLAMP is outside every window
 #pragma unroll 1
     for (int kk = kfirst; kk * S < d1; ++kk) {
         {
@@ -201,43 +197,88 @@ __global__ void __launch_bounds__(128) build_refr_kernel(const __grid_constant__
             anchor(3, (kk + 2) * S, g);
         }
         const int db = kk * S;
-        emit(db, aok[1], au[1], av_[1]);
-        const bool full = aok[0] && aok[1] && aok[2] && aok[3];
+        const bool full = asane[0] && asane[1] && asane[2] && asane[3];
         double d3u = 0.0, d3v = 0.0;
         if (full) {
             d3u = fabs((au[3] - au[0]) - 3.0 * (au[2] - au[1]));
             d3v = fabs((av_[3] - av_[0]) - 3.0 * (av_[2] - av_[1]));
         }
+        // ---- stage 1: coordinates of the S labels of this interval (branch-free) ----
+        int tx[S], ty[S];
+        bool ok[S];
+        unsigned need_exact = 0;  // bit s: label must be projected exactly
+        {
+            double du, dv;
+            tx[0] = trunc_magic(fmin(fmax(au[1], -CL), CL), du);
+            ty[0] = trunc_magic(fmin(fmax(av_[1], -CL), CL), dv);
+            ok[0] = aok[1];
+        }
 #pragma unroll
         for (int s = 1; s < S; ++s) {
-            const int d = db + s;
-            if (d >= d1) break;
-            bool done = false;
-            if (full) {
-                const double U = fma(lw[s][0], au[0], fma(lw[s][1], au[1], fma(lw[s][2], au[2], lw[s][3] * au[3])));
-                const double V = fma(lw[s][0], av_[0], fma(lw[s][1], av_[1], fma(lw[s][2], av_[2], lw[s][3] * av_[3])));
-                const double gu = fma(l2[s], d3u, 1e-6), gv = fma(l2[s], d3v, 1e-6);
-                if (fabs(U - rint(U)) > gu && fabs(V - rint(V)) > gv) {
-                    emit(d, true, U, V);
-                    done = true;
-                    if (a.check) {  // self-check: the interpolated tap against the exact projection
-                        double Ue, Ve, re;
-                        const bool oke = project_label(d, fma((double)s / S, ar[2] - ar[1], ar[1]), Ue, Ve, re);
-                        atomicAdd(a.check + 0, 1ull);
-                        if (!oke || __double2int_rz(Ue) != __double2int_rz(U) || __double2int_rz(Ve) != __double2int_rz(V))
-                            atomicAdd(a.check + 2, 1ull);
-                    }
-                } else if (a.check) {
-                    atomicAdd(a.check + 1, 1ull);
+            const double U = fma(lw[s][0], au[0], fma(lw[s][1], au[1], fma(lw[s][2], au[2], lw[s][3] * au[3])));
+            const double V = fma(lw[s][0], av_[0], fma(lw[s][1], av_[1], fma(lw[s][2], av_[2], lw[s][3] * av_[3])));
+            double du, dv;
+            tx[s] = trunc_magic(U, du);  // |U|,|V| < 2^31 when `full`; otherwise recomputed below
+            ty[s] = trunc_magic(V, dv);
+            ok[s] = true;
+            const bool safe = full && du > fma(l2[s], d3u, 1e-6) && dv > fma(l2[s], d3v, 1e-6);
+            if (!safe && db + s < d1) need_exact |= 1u << s;
+        }
+        // ---- stage 2 (rare): labels too close to a pixel boundary, or without a full stencil ----
+        if (a.check) {
+#pragma unroll
+            for (int s = 1; s < S; ++s) {
+                if (db + s >= d1) continue;
+                if (need_exact & (1u << s)) {
+                    if (full) atomicAdd(a.check + 1, 1ull);
+                    continue;
+                }
+                double Ue, Ve, re, du;
+                const bool oke = project_label(db + s, fma((double)s / S, ar[2] - ar[1], ar[1]), Ue, Ve, re);
+                atomicAdd(a.check + 0, 1ull);
+                if (!oke || trunc_magic(fmin(fmax(Ue, -CL), CL), du) != tx[s] || trunc_magic(fmin(fmax(Ve, -CL), CL), du) != ty[s])
+                    atomicAdd(a.check + 2, 1ull);
+            }
+        }
+        if (need_exact) {
+#pragma unroll
+            for (int s = 1; s < S; ++s) {
+                if (need_exact & (1u << s)) {
+                    double U = 0.0, V = 0.0, rho, du;
+                    double g = -1.0;
+                    if (aok[1] && aok[2]) g = fma((double)s / S, ar[2] - ar[1], ar[1]);
+                    ok[s] = project_label(db + s, g, U, V, rho);
+                    tx[s] = trunc_magic(fmin(fmax(U, -CL), CL), du);
+                    ty[s] = trunc_magic(fmin(fmax(V, -CL), CL), du);
                 }
             }
-            if (!done) {  // too close to a pixel boundary, or no full stencil: project this label exactly
-                double U, V, rho;
-                double g = -1.0;
-                if (aok[1] && aok[2]) g = fma((double)s / S, ar[2] - ar[1], ar[1]);
-                const bool ok = project_label(d, g, U, V, rho);
-                emit(d, ok, U, V);
+        }
+        // ---- stage 3: neighbour-mask test (loads issued together), pack, store ----
+        bool keep[S];
+        uint8_t mk[S];
+#pragma unroll
+        for (int s = 0; s < S; ++s) {
+            keep[s] = ok[s];
+            mk[s] = 255;
+            if (a.mvs) {  // multiviewstereo.cpp:787: only WHITE neighbour-mask pixels are candidates
+                keep[s] = keep[s] && (unsigned)tx[s] < (unsigned)a.w && (unsigned)ty[s] < (unsigned)a.h;
+                if (keep[s] && a.nbr_mask) mk[s] = a.nbr_mask[(size_t)ty[s] * a.w + tx[s]];
             }
+        }
+#pragma unroll
+        for (int s = 0; s < S; ++s) {
+            const int d = db + s;
+            if (d >= d1) break;
+            int32_t tap = TAP_NONE;
+            if (keep[s] && mk[s] == 255) {
+                int cx = tx[s], cy = ty[s];
+                if (!a.mvs) {  // (with the MVS rule the tap is inside the image already)
+                    cx = max(-TAP_CLAMP, min(TAP_CLAMP, cx));
+                    cy = max(-TAP_CLAMP, min(TAP_CLAMP, cy));
+                }
+                tap = (int32_t)(((uint32_t)(cy & 0xffff) << 16) | (uint32_t)(cx & 0xffff));
+            }
+            a.taps[(size_t)d * plane + pid] = tap;
         }
 #pragma unroll
         for (int i = 0; i < 3; ++i) {
@@ -245,6 +286,7 @@ __global__ void __launch_bounds__(128) build_refr_kernel(const __grid_constant__
             av_[i] = av_[i + 1];
             ar[i] = ar[i + 1];
             aok[i] = aok[i + 1];
+            asane[i] = asane[i + 1];
         }
     }
 }

@@ -26,6 +26,7 @@ struct ViewDev {
     uint8_t *mask = nullptr;
     double *gray_pix = nullptr, *gray_two = nullptr, *gray_msk = nullptr, *edges = nullptr;
     float *gray_pix_f = nullptr;
+    bool all_white = false;  // no mask was passed for this view: every pixel is WHITE
     int32_t *index = nullptr;
     double *depth = nullptr, *best = nullptr;
 };
@@ -106,7 +107,7 @@ struct sr_ctx {
     size_t tap_budget = (size_t)8 << 30;
     unsigned long long *d_stats = nullptr;  // SR_MATCH_STATS=1: counters of the screened match kernel
     bool use_refr_build = true;  // SR_BUILD_REFR=0: refractive views through the generic build_kernel (A/B aid)
-    int refr_chunk = 64;         // labels per thread of build_refr_kernel (SR_BUILD_CHUNK)
+    int refr_chunk = 256;        // labels per thread of build_refr_kernel (SR_BUILD_CHUNK)
     bool use_screen = true;  // SR_MATCH_SCREEN=0: MVS selection through the all-FP64 match_kernel (A/B aid)
     ncclComm_t comm = nullptr;
     int rank = 0, nranks = 1;
@@ -311,7 +312,8 @@ int sr_set_views(sr_ctx *ctx, int V, const sr_camera *cams, const uint8_t *const
         ViewDev &v = ctx->views[i];
         if (!rgba8[i]) return fail(ctx, SR_ERR_INVALID, "sr_set_views: null image");
         CK(cudaMemcpyAsync(v.rgba, rgba8[i], n * 4, cudaMemcpyHostToDevice, ctx->stream));
-        if (mask8 && mask8[i]) CK(cudaMemcpyAsync(v.mask, mask8[i], n, cudaMemcpyHostToDevice, ctx->stream));
+        v.all_white = !(mask8 && mask8[i]);
+        if (!v.all_white) CK(cudaMemcpyAsync(v.mask, mask8[i], n, cudaMemcpyHostToDevice, ctx->stream));
         else CK(cudaMemsetAsync(v.mask, 255, n, ctx->stream));
         prep_view_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(v.rgba, v.mask, w, h, v.gray_pix,
                                                                              v.gray_two, v.gray_msk, v.edges, v.gray_pix_f);
@@ -446,7 +448,7 @@ int sr_run_view(sr_ctx *ctx, int ref, const int32_t *nbrs, int nn) {
                 ra.rays = ctx->d_rays;
                 ra.depth_table = ctx->d_depth_table;
                 ra.ref_mask = A.mask;
-                ra.nbr_mask = ctx->views[nbrs[j]].mask;
+                ra.nbr_mask = ctx->views[nbrs[j]].all_white ? nullptr : ctx->views[nbrs[j]].mask;
                 ra.taps = ctx->d_taps + (size_t)j * D * plane;
                 ra.w = w;
                 ra.h = h;
