@@ -155,7 +155,12 @@ int sr_set_params(sr_ctx *ctx, const sr_params *p);
 int sr_run_view(sr_ctx *ctx, int ref, const int32_t *nbrs, int num_nbrs);
 /* Curve-mode search: rasterised refractive epipolar curve, exactly the live path
  * of the reference (stereo/multiviewstereo.cpp:574-602,754-810 and
- * stereo/twoviewstereo.cpp:285-305,999-1054). */
+ * stereo/twoviewstereo.cpp:285-305,999-1054).  The candidates of a pixel are the WHITE-mask
+ * pixels of the Bresenham segments joining consecutive label projections; a candidate's depth is
+ * the z of the midpoint of the two viewing rays' closest approach.  Results: sr_get_depth (the
+ * winner's depth hypothesis; -1 / NaN / +INF sentinels as in label mode), sr_get_best_cost, and
+ * sr_get_depth_index = ordinal of the winning candidate along the concatenated curves (>= 0), or
+ * the sentinels.  keep_cost_volume is not available in this mode. */
 int sr_run_view_curve(sr_ctx *ctx, int ref, const int32_t *nbrs, int num_nbrs);
 /* Neighbour selection of MultiViewStereo::runTask (stereo/multiviewstereo.cpp:335-360).
  * out_nbrs has room for max_nbrs entries per view; out_counts[v] receives the count. */

@@ -93,6 +93,10 @@ public:
     // ---- extensions ------------------------------------------------------------------------
     sr_params &params() { return params_; }
     void setDevice(int device) { device_ = device; }
+    //! true: search along the rasterised epipolar curve, depth from the rays' closest approach —
+    //! the reference's live formulation (multiviewstereo.cpp:574-602); false (default): the
+    //! depth-label cost volume + WTA of the same rule (SURVEY §8a S4 applied to S2).
+    void setCurveMode(bool on) { curveMode_ = on; }
     size_t numViews() const { return views.size(); }
     const std::vector<double> &depths(size_t viewIndex) const { return computedDepths[viewIndex]; }
     const std::vector<int32_t> &indices(size_t viewIndex) const { return depthIndices[viewIndex]; }
@@ -150,7 +154,10 @@ protected:
             progressUpdate(step++);
             if (isCancelled()) { sr_request_cancel(s.get()); return; }
             stageUpdate("Computing cost volume for camera " + views[v]->name());
-            if (cnt[v] > 0) s.check(sr_run_view(s.get(), v, &nb[(size_t)v * maxN], cnt[v]), "sr_run_view");
+            if (cnt[v] > 0) {
+                if (curveMode_) s.check(sr_run_view_curve(s.get(), v, &nb[(size_t)v * maxN], cnt[v]), "sr_run_view_curve");
+                else s.check(sr_run_view(s.get(), v, &nb[(size_t)v * maxN], cnt[v]), "sr_run_view");
+            }
         }
         stageUpdate("Constructing depth maps");
         fetch(s, w, h);
@@ -227,5 +234,6 @@ private:
     sr_params params_;
     int device_ = 0;
     bool inMemory_ = false;
+    bool curveMode_ = false;
 };
 #endif

@@ -70,11 +70,11 @@ public:
         stageUpdate("Computing cost volume (left to right)");
         progressUpdate(0);
         if (isCancelled()) return;
-        s.check(sr_run_view(s.get(), 0, &one, 1), "sr_run_view");
+        s.check(curveMode_ ? sr_run_view_curve(s.get(), 0, &one, 1) : sr_run_view(s.get(), 0, &one, 1), "sr_run_view");
         stageUpdate("Computing cost volume (right to left)");
         progressUpdate(3);
         if (isCancelled()) return;
-        s.check(sr_run_view(s.get(), 1, &zero, 1), "sr_run_view");
+        s.check(curveMode_ ? sr_run_view_curve(s.get(), 1, &zero, 1) : sr_run_view(s.get(), 1, &zero, 1), "sr_run_view");
         fetch(s, w, h);  // the reference colourises once before cross-checking (:160-180)
         if (isCancelled()) return;
         stageUpdate("Cross-checking");
@@ -119,6 +119,9 @@ public:
     // ---- extensions ------------------------------------------------------------------------
     sr_params &params() { return params_; }
     void setDevice(int device) { device_ = device; }
+    //! true: the reference's live search along the rasterised epipolar curve (twoviewstereo.cpp:285-305);
+    //! false (default): the depth-label cost volume + WTA (the compiled-out branch, :308-329).
+    void setCurveMode(bool on) { curveMode_ = on; }
     void setCrossCheckThreshold(double t) { crossCheckThreshold_ = t; }
     const DepthMap &leftDepths() const { return computedDepthLeft; }
     const DepthMap &rightDepths() const { return computedDepthRight; }
@@ -198,5 +201,6 @@ private:
     double crossCheckThreshold_;
     sr_params params_;
     int device_ = 0;
+    bool curveMode_ = false;
 };
 #endif

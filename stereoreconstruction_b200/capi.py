@@ -18,7 +18,7 @@ _LIB = None
 NVCC_FLAGS = ["-std=c++17", "-O3", "-fmad=false", "-DSR_FEW_RADII", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
               "--shared", "-Xcompiler", "-fPIC"]
 SOURCES = ["csrc/sr_capi.cu"]
-HEADERS = ["csrc/sr_geometry.cuh", "csrc/sr_kernels.cuh", "csrc/sr_match_dispatch.cuh", "csrc/sr_match_screen.cuh", "csrc/sr_build_refr.cuh",
+HEADERS = ["csrc/sr_geometry.cuh", "csrc/sr_kernels.cuh", "csrc/sr_match_dispatch.cuh", "csrc/sr_match_screen.cuh", "csrc/sr_build_refr.cuh", "csrc/sr_curve.cuh",
            "../include/sr_b200.h"]
 
 EXPORTS = [

@@ -45,54 +45,55 @@ __device__ __forceinline__ double rcp_approx(double a) {  // ~2^-20 relative (MU
     return r;
 }
 
-// Labels between two anchors are not re-projected: the pixel coordinate (U,V)(label) is an
-// analytic, slowly varying function of the label, so it is read off the cubic through the four
-// surrounding ANCHOR labels (every BUILD_STRIDE-th label, projected exactly as above).  What
-// must be exact is only trunc(U), trunc(V): the interpolated value is accepted when it is farther
-// from the nearest integer than a guard, otherwise that label is projected exactly as well.
-//   guard = |cubic - quadratic| + 1e-6 px = |third difference| * L2(x) + 1e-6
-// i.e. the full error of the NEXT-LOWER-order interpolant, ~100x the cubic's own error for these
-// functions (each higher difference shrinks by ~BUILD_STRIDE*dDepth/Depth ~ 1e-2).  With the
-// guard ~1e-4 px a label falls back with probability ~4e-4.
-#ifndef SR_BUILD_STRIDE
-#define SR_BUILD_STRIDE 4
-#endif
-constexpr int BUILD_STRIDE = SR_BUILD_STRIDE;
+// Per (reference pixel, refractive target view) state of the label sweep: the hoisted affine
+// geometry, and the exact projection of one label.  Shared by the label-mode build below and the
+// curve-mode rasteriser (sr_curve.cuh).
+struct RefrProjector {
+    double tA, tB, a0, a1, pd, dd, n1, n2, fxs, cxs, fys, cys;
+    d3 R0, R1, KR0, KR1, KdN;
+    const double *depth_table, *k;
+    bool ray_ok, distorted;
 
-__global__ void __launch_bounds__(128) build_refr_kernel(const __grid_constant__ BuildRefrArgs a) {
-    const int pid = blockIdx.x * blockDim.x + threadIdx.x;
-    if (pid >= a.rows * a.w) return;
-    const int x = pid % a.w, y = a.row0 + pid / a.w;
-    const size_t pix = (size_t)y * a.w + x;
-    if (a.ref_mask[pix] != 255) return;  // the match kernels never read taps of masked-out pixels
-    const size_t n = (size_t)a.w * a.h;
-    const d3 src = {a.rays[pix], a.rays[n + pix], a.rays[2 * n + pix]};
-    const d3 dir = {a.rays[3 * n + pix], a.rays[4 * n + pix], a.rays[5 * n + pix]};
-    // pointFromDepth: plane through C + prin*depth with unit normal nrm; t = (dist*nn - ns)/nd
-    const d3 prin = ld3(a.prin);
-    const d3 nrm = normalized(prin);
-    const double nd = dot(nrm, dir);
-    const bool ray_ok = !(fabs(nd) < 1e-10);
-    const double inv_nd = 1.0 / nd;
-    const double nC = dot(nrm, ld3(a.C)), npn = dot(nrm, prin), nn = dot(nrm, nrm), ns = dot(nrm, src);
-    const double tA = npn * nn * inv_nd, tB = (nC * nn - ns) * inv_nd;
-    // camera-local ray and its decomposition about the interface normal
-    const d3 Ls = fmul3(a.nbr.R, src) + ld3(a.nbr.t), Ld = fmul3(a.nbr.R, dir);
-    const d3 N = ld3(a.nbr.plane_n);
-    const double a0 = fdot(N, Ls), a1 = fdot(N, Ld);
-    const d3 R0 = faxpy(-a0, N, Ls), R1 = faxpy(-a1, N, Ld);
-    const d3 KR0 = fmul3(a.Kn, R0), KR1 = fmul3(a.Kn, R1);
-    const double pd = a.nbr.plane_d;
-    const d3 KdN = fmul3(a.Kn, pd * N);
-    const double dd = pd * pd, n1 = a.nbr.n, n2 = n1 * n1;
-    const bool distorted = a.nbr.is_distorted != 0;
-    const double *k = a.nbr.dist;
-    const int D = a.D;
+    // Kn: K, or K with rows 0/1 normalised for a distorted view (see BuildRefrArgs)
+    __device__ __forceinline__ void init(const sr_camera &nbr, const double *Kn, const double *prin_, const double *C_,
+                                         d3 src, d3 dir, const double *table, double fxs_, double cxs_, double fys_,
+                                         double cys_) {
+        // pointFromDepth: plane through C + prin*depth with unit normal nrm; t = (dist*nn - ns)/nd
+        const d3 prin = ld3(prin_);
+        const d3 nrm = normalized(prin);
+        const double nd = dot(nrm, dir);
+        ray_ok = !(fabs(nd) < 1e-10);
+        const double inv_nd = 1.0 / nd;
+        const double nC = dot(nrm, ld3(C_)), npn = dot(nrm, prin), nn = dot(nrm, nrm), ns = dot(nrm, src);
+        tA = npn * nn * inv_nd;
+        tB = (nC * nn - ns) * inv_nd;
+        // camera-local ray and its decomposition about the interface normal
+        const d3 Ls = fmul3(nbr.R, src) + ld3(nbr.t), Ld = fmul3(nbr.R, dir);
+        const d3 N = ld3(nbr.plane_n);
+        a0 = fdot(N, Ls);
+        a1 = fdot(N, Ld);
+        R0 = faxpy(-a0, N, Ls);
+        R1 = faxpy(-a1, N, Ld);
+        KR0 = fmul3(Kn, R0);
+        KR1 = fmul3(Kn, R1);
+        pd = nbr.plane_d;
+        KdN = fmul3(Kn, pd * N);
+        dd = pd * pd;
+        n1 = nbr.n;
+        n2 = n1 * n1;
+        distorted = nbr.is_distorted != 0;
+        k = nbr.dist;
+        depth_table = table;
+        fxs = fxs_;
+        cxs = cxs_;
+        fys = fys_;
+        cys = cys_;
+    }
 
     // Exact projection of label d.  rho_guess in [0,1] or < 0 (paraxial start).  Outputs the
     // coordinate that is truncated (U,V) and the root rho.
-    auto project_label = [&](int d, double rho_guess, double &U, double &V, double &rho_out) -> bool {
-        const double t = fma(a.depth_table[d], tA, tB);
+    __device__ __forceinline__ bool project(int d, double rho_guess, double &U, double &V, double &rho_out) const {
+        const double t = fma(depth_table[d], tA, tB);
         if (!ray_ok || t < 1e-10) return false;
         const d3 radv = faxpy(t, R1, R0);
         const double rr = fdot(radv, radv);
@@ -138,9 +139,40 @@ __global__ void __launch_bounds__(128) build_refr_kernel(const __grid_constant__
             // camera.cpp:411-412: y's tangential term uses the already-distorted x
             yn = fma(yo, cdist, fma(k[2], fma(2 * yo, yo, q2), 2 * k[3] * xn * yo));
         }
-        U = fma(a.fxs, xn, a.cxs);
-        V = fma(a.fys, yn, a.cys);
+        U = fma(fxs, xn, cxs);
+        V = fma(fys, yn, cys);
         return true;
+    }
+};
+
+// Labels between two anchors are not re-projected: the pixel coordinate (U,V)(label) is an
+// analytic, slowly varying function of the label, so it is read off the cubic through the four
+// surrounding ANCHOR labels (every BUILD_STRIDE-th label, projected exactly as above).  What
+// must be exact is only trunc(U), trunc(V): the interpolated value is accepted when it is farther
+// from the nearest integer than a guard, otherwise that label is projected exactly as well.
+//   guard = |cubic - quadratic| + 1e-6 px = |third difference| * L2(x) + 1e-6
+// i.e. the full error of the NEXT-LOWER-order interpolant, ~100x the cubic's own error for these
+// functions (each higher difference shrinks by ~BUILD_STRIDE*dDepth/Depth ~ 1e-2).  With the
+// guard ~1e-4 px a label falls back with probability ~4e-4.
+#ifndef SR_BUILD_STRIDE
+#define SR_BUILD_STRIDE 4
+#endif
+constexpr int BUILD_STRIDE = SR_BUILD_STRIDE;
+
+__global__ void __launch_bounds__(128) build_refr_kernel(const __grid_constant__ BuildRefrArgs a) {
+    const int pid = blockIdx.x * blockDim.x + threadIdx.x;
+    if (pid >= a.rows * a.w) return;
+    const int x = pid % a.w, y = a.row0 + pid / a.w;
+    const size_t pix = (size_t)y * a.w + x;
+    if (a.ref_mask[pix] != 255) return;  // the match kernels never read taps of masked-out pixels
+    const size_t n = (size_t)a.w * a.h;
+    const d3 src = {a.rays[pix], a.rays[n + pix], a.rays[2 * n + pix]};
+    const d3 dir = {a.rays[3 * n + pix], a.rays[4 * n + pix], a.rays[5 * n + pix]};
+    RefrProjector pj;
+    pj.init(a.nbr, a.Kn, a.prin, a.C, src, dir, a.depth_table, a.fxs, a.cxs, a.fys, a.cys);
+    const int D = a.D;
+    auto project_label = [&](int d, double rho_guess, double &U, double &V, double &rho_out) -> bool {
+        return pj.project(d, rho_guess, U, V, rho_out);
     };
 
     const size_t plane = (size_t)a.rows * a.w;

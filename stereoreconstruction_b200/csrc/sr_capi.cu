@@ -14,6 +14,7 @@
 #include "sr_kernels.cuh"
 #include "sr_match_dispatch.cuh"
 #include "sr_build_refr.cuh"
+#include "sr_curve.cuh"
 
 using namespace sr;
 
@@ -27,6 +28,8 @@ struct ViewDev {
     double *gray_pix = nullptr, *gray_two = nullptr, *gray_msk = nullptr, *edges = nullptr;
     float *gray_pix_f = nullptr;
     bool all_white = false;  // no mask was passed for this view: every pixel is WHITE
+    double *rays = nullptr;  // [6][h][w] Camera::unproject of every pixel centre (curve mode), lazily
+    double rays_scale = 0.0; // image_scale the table was computed for (0: stale)
     int32_t *index = nullptr;
     double *depth = nullptr, *best = nullptr;
 };
@@ -149,6 +152,7 @@ void free_views(sr_ctx *c) {
         dfree(v.mask);
         dfree(v.gray_pix);
         dfree(v.gray_pix_f);
+        dfree(v.rays);
         dfree(v.gray_two);
         dfree(v.gray_msk);
         dfree(v.edges);
@@ -312,6 +316,7 @@ int sr_set_views(sr_ctx *ctx, int V, const sr_camera *cams, const uint8_t *const
         ViewDev &v = ctx->views[i];
         if (!rgba8[i]) return fail(ctx, SR_ERR_INVALID, "sr_set_views: null image");
         CK(cudaMemcpyAsync(v.rgba, rgba8[i], n * 4, cudaMemcpyHostToDevice, ctx->stream));
+        v.rays_scale = 0.0;  // cameras may have changed
         v.all_white = !(mask8 && mask8[i]);
         if (!v.all_white) CK(cudaMemcpyAsync(v.mask, mask8[i], n, cudaMemcpyHostToDevice, ctx->stream));
         else CK(cudaMemsetAsync(v.mask, 255, n, ctx->stream));
@@ -589,11 +594,203 @@ int sr_get_match_stats(sr_ctx *ctx, uint64_t *out8) {
     return SR_OK;
 }
 
+static int ensure_rays(sr_ctx *ctx, int v) {
+    ViewDev &d = ctx->views[v];
+    const size_t n = (size_t)ctx->w * ctx->h;
+    const double scale = ctx->params.image_scale;
+    if (!d.rays) CK(cudaMalloc(&d.rays, n * 6 * 8));
+    if (d.rays_scale != scale) {
+        rays_kernel<<<(unsigned)((n + 127) / 128), 128, 0, ctx->stream>>>(ctx->cams[v], ctx->w, ctx->h, scale, d.rays);
+        CKL();
+        d.rays_scale = scale;
+    }
+    return SR_OK;
+}
+
+// Curve-mode search (the reference's live path): rasterised epipolar curves as the candidate
+// set, depth of a candidate = closest approach of the two viewing rays.
 int sr_run_view_curve(sr_ctx *ctx, int ref, const int32_t *nbrs, int nn) {
-    (void)ref;
-    (void)nbrs;
-    (void)nn;
-    return fail(ctx, SR_ERR_STATE, "sr_run_view_curve: curve-mode search is not built yet (SURVEY §8f rank 2)");
+    int rc = check_view(ctx, ref);
+    if (rc) return rc;
+    if (!ctx->have_params) return fail(ctx, SR_ERR_STATE, "sr_set_params has not been called");
+    if (!nbrs || nn <= 0 || nn > SR_MAX_NBRS) return fail(ctx, SR_ERR_INVALID, "1..8 neighbour views required");
+    for (int j = 0; j < nn; ++j)
+        if (nbrs[j] < 0 || nbrs[j] >= ctx->V || nbrs[j] == ref) return fail(ctx, SR_ERR_INVALID, "bad neighbour index");
+    const sr_params &P = ctx->params;
+    const bool mvs = (P.select_kind == SR_SELECT_MVS);
+    if (!mvs && nn != 1) return fail(ctx, SR_ERR_INVALID, "two-view selection takes exactly one neighbour");
+    if (P.keep_cost_volume) return fail(ctx, SR_ERR_INVALID, "curve mode keeps no cost volume (candidates are not labels)");
+    if (mvs && P.cost_kind != SR_COST_NCC_MVS) return fail(ctx, SR_ERR_INVALID, "multi-view curve search uses SR_COST_NCC_MVS");
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    const int w = ctx->w, h = ctx->h, D = P.num_levels;
+    const int r0 = std::max(P.row_begin, 0);
+    const int r1 = (P.row_end > 0 && P.row_end < h) ? P.row_end : h;
+    if (r0 >= r1) return fail(ctx, SR_ERR_INVALID, "empty row range");
+    ViewDev &A = ctx->views[ref];
+    rc = ensure_rays(ctx, ref);
+    if (rc) return rc;
+    for (int j = 0; j < nn; ++j) {
+        rc = ensure_rays(ctx, nbrs[j]);
+        if (rc) return rc;
+    }
+    const size_t wn = (size_t)(2 * P.radius + 1) * (2 * P.radius + 1);
+    const size_t per_row_w = wn * w * 8;
+
+    auto curve_args = [&](int j, int b0, int rows) {
+        const sr_camera &nb = ctx->cams[nbrs[j]];
+        CurveArgs ca;
+        memset(&ca, 0, sizeof(ca));
+        ca.nbr = nb;
+        const double sc = P.image_scale;
+        memcpy(ca.Kn, nb.K, sizeof(ca.Kn));
+        if (nb.is_distorted) {
+            const double fx = nb.K[0], fy = nb.K[4], cx = nb.K[2], cy = nb.K[5];
+            for (int c = 0; c < 3; ++c) {
+                ca.Kn[c] = (nb.K[c] - cx * nb.K[6 + c]) / fx;
+                ca.Kn[3 + c] = (nb.K[3 + c] - cy * nb.K[6 + c]) / fy;
+            }
+            ca.fxs = fx * sc;
+            ca.cxs = cx * sc;
+            ca.fys = fy * sc;
+            ca.cys = cy * sc;
+        } else {
+            ca.fxs = ca.fys = sc;
+            ca.cxs = ca.cys = 0.0;
+        }
+        memcpy(ca.prin, ctx->cams[ref].prin_dir, sizeof(ca.prin));
+        memcpy(ca.C, ctx->cams[ref].C, sizeof(ca.C));
+        ca.scale = sc;
+        ca.rays = A.rays;
+        ca.depth_table = ctx->d_depth_table;
+        ca.ref_mask = A.mask;
+        ca.nbr_mask = ctx->views[nbrs[j]].mask;
+        ca.w = w;
+        ca.h = h;
+        ca.row0 = b0;
+        ca.rows = rows;
+        ca.D = D;
+        ca.mvs = mvs;
+        return ca;
+    };
+    auto launch_curve = [&](const CurveArgs &ca, unsigned gx) {
+        if (ca.nbr.is_refractive) curve_build_kernel<true><<<gx, 128, 0, st>>>(ca);
+        else curve_build_kernel<false><<<gx, 128, 0, st>>>(ca);
+    };
+
+    int band = r1 - r0;
+    {   // first guess of the band height from a typical curve length of 2 D candidates
+        const size_t per_row = (size_t)nn * (size_t)std::max(64, 2 * D) * w * 4;
+        band = (int)std::min<size_t>((size_t)band, std::max<size_t>(1, ctx->tap_budget / (per_row + per_row_w)));
+    }
+    for (int b0 = r0; b0 < r1;) {
+        if (ctx->cancel.load()) return fail(ctx, SR_ERR_CANCELLED, "cancelled");
+        int rows = std::min(band, r1 - b0);
+        int L = 1;
+        for (;;) {  // count pass: the longest curve of this band over all neighbours
+            const size_t plane = (size_t)rows * w;
+            rc = ensure_scratch(ctx, plane * 4 + 16);
+            if (rc) return rc;
+            int32_t *d_counts = (int32_t *)ctx->d_scratch;
+            int32_t *d_max = d_counts + plane;
+            CK(cudaMemsetAsync(d_max, 0, 4, st));
+            const unsigned gx = (unsigned)((plane + 127) / 128);
+            for (int j = 0; j < nn; ++j) {
+                CurveArgs ca = curve_args(j, b0, rows);
+                ca.counts = d_counts;
+                ca.max_count = d_max;
+                launch_curve(ca, gx);
+                CKL();
+            }
+            int32_t hmax = 0;
+            CK(cudaMemcpyAsync(&hmax, d_max, 4, cudaMemcpyDeviceToHost, st));
+            CK(cudaStreamSynchronize(st));
+            L = std::max(1, (int)hmax);
+            const size_t need_all = (size_t)nn * L * plane * 4 + per_row_w * rows;
+            if (need_all <= ctx->tap_budget || rows == 1) break;
+            rows = (int)std::max<size_t>(1, ctx->tap_budget / ((size_t)nn * L * w * 4 + per_row_w));
+        }
+        const size_t plane = (size_t)rows * w;
+        const size_t need = (size_t)nn * L * plane * 4, need_w = per_row_w * rows;
+        if (need_w > ctx->weights_cap) {
+            CK(cudaStreamSynchronize(st));
+            dfree(ctx->d_weights);
+            ctx->weights_cap = 0;
+            CK(cudaMalloc(&ctx->d_weights, need_w));
+            ctx->weights_cap = need_w;
+        }
+        if (need > ctx->taps_cap) {
+            CK(cudaStreamSynchronize(st));
+            dfree(ctx->d_taps);
+            ctx->taps_cap = 0;
+            CK(cudaMalloc(&ctx->d_taps, need));
+            ctx->taps_cap = need;
+        }
+        const unsigned gx = (unsigned)((plane + 127) / 128);
+        for (int j = 0; j < nn; ++j) {  // fill pass
+            CurveArgs ca = curve_args(j, b0, rows);
+            ca.taps = ctx->d_taps + (size_t)j * L * plane;
+            ca.capacity = L;
+            launch_curve(ca, gx);
+            CKL();
+        }
+        {
+            WeightArgs wa;
+            memset(&wa, 0, sizeof(wa));
+            wa.rgba = A.rgba;
+            wa.mask = A.mask;
+            wa.edges = A.edges;
+            wa.W = ctx->d_weights;
+            wa.w = w;
+            wa.h = h;
+            wa.row0 = b0;
+            wa.rows = rows;
+            wa.radius = P.radius;
+            if (P.weight_kind == SR_WEIGHT_ADAPTIVE)
+                weights_adaptive_kernel<<<gx, 128, (P.radius + 1) * sizeof(double), st>>>(wa);
+            else
+                weights_geodesic_kernel<<<gx, 128, 0, st>>>(wa);
+            CKL();
+        }
+        MatchArgs ma;
+        memset(&ma, 0, sizeof(ma));
+        ma.W = ctx->d_weights;
+        ma.maskL = A.mask;
+        ma.grayL = (P.cost_kind == SR_COST_NCC_MVS) ? A.gray_pix : A.gray_two;
+        for (int j = 0; j < nn; ++j) {
+            const ViewDev &B = ctx->views[nbrs[j]];
+            ma.grayR[j] = (P.cost_kind == SR_COST_NCC_MVS) ? B.gray_pix
+                          : (P.cost_kind == SR_COST_NCC_TWOVIEW) ? B.gray_two : B.gray_msk;
+            ma.grayRf[j] = B.gray_pix_f;
+            ma.raysR[j] = B.rays;
+        }
+        ma.raysL = A.rays;
+        memcpy(ma.camR, ctx->cams[ref].R, sizeof(ma.camR));
+        memcpy(ma.camT, ctx->cams[ref].t, sizeof(ma.camT));
+        ma.curve = 1;
+        ma.taps = ctx->d_taps;
+        ma.depth_table = ctx->d_depth_table;
+        ma.out_index = A.index;
+        ma.out_depth = A.depth;
+        ma.out_best = A.best;
+        ma.w = w;
+        ma.h = h;
+        ma.row0 = b0;
+        ma.rows = rows;
+        ma.D = L;
+        ma.num_nbrs = nn;
+        ma.select_kind = P.select_kind;
+        ma.depth_up = 1;
+        ma.use_screen = 1;
+        ma.stats = ctx->d_stats;
+        ma.second_best_factor = P.second_best_factor;
+        ma.ncc_threshold = P.ncc_threshold;
+        cudaError_t e = launch_match(P.radius, P.cost_kind, ma, st);
+        ++ctx->launches;
+        if (e != cudaSuccess) return fail(ctx, SR_ERR_CUDA, std::string("match kernel: ") + cudaGetErrorString(e));
+        b0 += rows;
+    }
+    return SR_OK;
 }
 
 int sr_select_neighbours(sr_ctx *ctx, int max_nbrs, int32_t *out, int32_t *counts) {

@@ -324,6 +324,12 @@ struct MatchArgs {
     int w, h, row0, rows, D, num_nbrs;
     int select_kind;
     int depth_up;                   // depth_table is increasing in the label (max_depth > min_depth)
+    // curve mode (sr_curve.cuh): the "labels" are the candidates of the rasterised epipolar curve and
+    // a candidate's depth is the closest approach of the two viewing rays
+    int curve;
+    const double *raysL;               // [6][h][w] rays of the reference view
+    const double *raysR[SR_MAX_NBRS];  // [6][h][w] rays of the neighbour views
+    double camR[9], camT[3];           // reference camera: fromGlobalToLocal (camera.cpp:346-348)
     unsigned long long *stats;      // optional [8]: pixels, screened, forced, verified, all_slow (debug)
     int use_screen;                 // MVS selection: FP32 screen + FP64 verify (sr_match_screen.cuh)
     double second_best_factor, ncc_threshold;
@@ -402,6 +408,9 @@ __device__ __noinline__ double slow_cost(const MatchArgs &a, const double *__res
     const double v = 255.0 * (1.0 - fabs(q1) / sqrt(q2 * q3));
     return (v < 120.0) ? v : 120.0;
 }
+
+__device__ double curve_depth(const double *__restrict__ raysA, const double *__restrict__ raysB, size_t n, size_t pixA,
+                              size_t pixB, const double *R, const double *t);  // sr_curve.cuh
 
 #ifndef SR_MATCH_MINBLOCKS
 #define SR_MATCH_MINBLOCKS 3
@@ -608,6 +617,7 @@ __global__ void __launch_bounds__(128, (R <= 2) ? SR_MATCH_MINBLOCKS : 2) match_
     double minCost = dinf(), secondBest = dinf();  // two-view selection
     double bestC = 0.0;                            // MVS selection
     int bestIdx = SR_INDEX_NONE;
+    int32_t bestTap = TAP_NONE;                    // curve mode: the winning candidate's pixel
     const bool mvs = a.select_kind == SR_SELECT_MVS;
     const int D = a.D;
     const bool depth_up = a.depth_up != 0;
@@ -677,6 +687,7 @@ __global__ void __launch_bounds__(128, (R <= 2) ? SR_MATCH_MINBLOCKS : 2) match_
                         secondBest = minCost;
                         minCost = cost;
                         bestIdx = d;
+                        bestTap = tap;
                     }
                 }
             }
@@ -691,7 +702,11 @@ __global__ void __launch_bounds__(128, (R <= 2) ? SR_MATCH_MINBLOCKS : 2) match_
             a.out_depth[pix] = (bestIdx >= 0) ? a.depth_table[bestIdx] : -1.0;
             a.out_best[pix] = bestC;
         } else {
-            double depth = (bestIdx >= 0) ? a.depth_table[bestIdx] : qnan();
+            double depth = (bestIdx >= 0) ? a.depth_table[a.curve ? 0 : bestIdx] : qnan();
+            if (a.curve && bestIdx >= 0) {  // twoviewstereo.cpp:286-299: z of the rays' closest approach
+                const int tx = (int)(short)(bestTap & 0xffff), ty = (int)(short)((uint32_t)bestTap >> 16);
+                depth = curve_depth(a.raysL, a.raysR[0], (size_t)w * h, pix, (size_t)ty * w + tx, a.camR, a.camT);
+            }
             if (a.second_best_factor > 0.0 && minCost > a.second_best_factor * secondBest) {  // :304-305
                 depth = dinf();
                 bestIdx = SR_INDEX_REJECTED;

@@ -130,6 +130,7 @@ __global__ void __launch_bounds__(SCREEN_BLOCK, ((R <= 2) ? SR_SCREEN_MINBLOCKS 
     // in the reference's summation order, and the verified winner so far.
     __shared__ double px_meanL[SCREEN_BLOCK], px_totW[SCREEN_BLOCK], px_s2[SCREEN_BLOCK], px_bestC[SCREEN_BLOCK];
     __shared__ int px_bestIdx[SCREEN_BLOCK];
+    __shared__ double px_bestZ[SCREEN_BLOCK];  // curve mode: depth hypothesis of the verified winner
     __shared__ unsigned long long px_act[SCREEN_BLOCK];  // bit i: this lane's i-th tap is active (TPL <= 35)
 
     const int tid = threadIdx.x;
@@ -209,6 +210,7 @@ __global__ void __launch_bounds__(SCREEN_BLOCK, ((R <= 2) ? SR_SCREEN_MINBLOCKS 
         px_act[tid] = actmask;
         px_bestC[tid] = 0.0;
         px_bestIdx[tid] = SR_INDEX_NONE;
+        px_bestZ[tid] = -1.0;
     }
     // keep the FP32 copies as values of their own (otherwise they are re-derived from the FP64
     // ones with an F2F / DSETP inside the label loop)
@@ -321,10 +323,22 @@ __global__ void __launch_bounds__(SCREEN_BLOCK, ((R <= 2) ? SR_SCREEN_MINBLOCKS 
                     if (err > e) ++n_viol;
                 }
                 if (cost > a.ncc_threshold) {  // multiviewstereo.cpp:589-602,654-660
-                    const bool deeper = depth_up ? (d > bestIdx) : (d < bestIdx);
-                    if (bestIdx == SR_INDEX_NONE || cost > bestC || (cost == bestC && deeper)) {
-                        bestC = cost;
-                        bestIdx = d;
+                    if (a.curve) {
+                        // candidates are (ncc, z) pairs, the winner is the largest pair (:600-602,:654-660)
+                        if (bestIdx == SR_INDEX_NONE || cost >= bestC) {
+                            const double z = curve_depth(a.raysL, a.raysR[j], (size_t)w * h, pix, (size_t)ty * w + tx, a.camR, a.camT);
+                            if (bestIdx == SR_INDEX_NONE || cost > bestC || z > px_bestZ[tid]) {
+                                bestC = cost;
+                                bestIdx = d;
+                                px_bestZ[tid] = z;
+                            }
+                        }
+                    } else {
+                        const bool deeper = depth_up ? (d > bestIdx) : (d < bestIdx);
+                        if (bestIdx == SR_INDEX_NONE || cost > bestC || (cost == bestC && deeper)) {
+                            bestC = cost;
+                            bestIdx = d;
+                        }
                     }
                 }
             }
@@ -412,8 +426,9 @@ __global__ void __launch_bounds__(SCREEN_BLOCK, ((R <= 2) ? SR_SCREEN_MINBLOCKS 
                     const int d = d0 + l;
                     const int lab = ((eps == SCREEN_EPS_TIGHT) ? (1 << 30) : 0) | (j << 16) | d;
                     if (qn > 0 && q_tap[qn - 1][tid] == tap && ((q_lab[qn - 1][tid] >> 16) & 0xff) == j) {
-                        // equal cost by construction: the tie-break picks the deeper label
-                        if (depth_up) q_lab[qn - 1][tid] = lab;
+                        // equal cost by construction: the tie-break picks the deeper label (in curve
+                        // mode the same pixel is the same (ncc, z) pair: nothing to add)
+                        if (depth_up && !a.curve) q_lab[qn - 1][tid] = lab;
                     } else {
                         const float lb = c32 - eps;
                         if (c32 != SCREEN_FORCE && lb > lower32) {
@@ -458,7 +473,7 @@ __global__ void __launch_bounds__(SCREEN_BLOCK, ((R <= 2) ? SR_SCREEN_MINBLOCKS 
     if (alive && sub == 0) {
         const int bestIdx = px_bestIdx[tid];
         a.out_index[pix] = bestIdx;
-        a.out_depth[pix] = (bestIdx >= 0) ? a.depth_table[bestIdx] : -1.0;
+        a.out_depth[pix] = (bestIdx >= 0) ? (a.curve ? px_bestZ[tid] : a.depth_table[bestIdx]) : -1.0;
         a.out_best[pix] = px_bestC[tid];
     }
 }

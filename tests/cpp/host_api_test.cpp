@@ -61,6 +61,15 @@ int main(int argc, char **argv) {
         }
         std::printf("mvs: last stage '%s', last progress %d, unknown view -> null image: %d\n", lastStage.c_str(), lastProgress,
                     (int)mvs.depthMap(CameraPtr(new Camera("nope", "nope"))).isNull());
+        {   // the reference's live formulation: curve-mode search, same task object re-run
+            mvs.setCurveMode(true);
+            mvs.run();
+            for (size_t v = 0; v < mvs.numViews(); ++v)
+                dump(out + "/mvs_curve_v" + std::to_string(v) + "_depth.bin", mvs.depths(v).data(), mvs.depths(v).size());
+            std::printf("mvs (curve mode): %.1f%% of view 0 has depth after cross-check\n", 100 * mvs.coverageAfterCrossCheck()[0]);
+            mvs.setCurveMode(false);
+            mvs.run();
+        }
         const std::vector<PLYPoint> cloud = mvs.pointCloud();
         outputPLYFile(out + "/cloud.ply", cloud);
         std::printf("mvs: point cloud of %zu points written\n", cloud.size());

@@ -117,6 +117,17 @@ def test_cpp_class_api_end_to_end(tmp_path):
         assert (img[..., 0][~fin] == 255).all()
         assert np.isfinite(gd).sum() > 0
 
+    # MultiViewStereo in curve mode (the reference's live search) == sr_run_view_curve directly
+    ctx.set_views(pods, rgba, masks)
+    ctx.set_params(P)
+    for v in range(V):
+        ctx.run_view_curve(v, nb[v])
+    ctx.cross_check(False, cross)
+    for v in range(V):
+        gd = np.fromfile(os.path.join(out, f"mvs_curve_v{v}_depth.bin"), dtype=np.float64).reshape(h, w)
+        d = ctx.depth(v)
+        assert ((gd == d) | (np.isnan(gd) & np.isnan(d))).all()
+
     # TwoViewStereo (no masks, radius 2, cross-check 30) == the C ABI directly
     two = [pods[0], pods[1]]
     plain = [rgba[0], rgba[1]]  # QImage(file) keeps the alpha byte; the mask argument was null
