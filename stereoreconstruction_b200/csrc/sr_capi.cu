@@ -291,7 +291,7 @@ int sr_set_views(sr_ctx *ctx, int V, const sr_camera *cams, const uint8_t *const
             CK(cudaMalloc(&v.rgba, n * 4));
             CK(cudaMalloc(&v.mask, n));
             CK(cudaMalloc(&v.gray_pix, n * 8));
-            CK(cudaMalloc(&v.gray_pix_f, n * 4));
+            CK(cudaMalloc(&v.gray_pix_f, (size_t)screen_pitch(w) * h * 4));
             CK(cudaMalloc(&v.gray_two, n * 8));
             CK(cudaMalloc(&v.gray_msk, n * 8));
             CK(cudaMalloc(&v.edges, n * 8 * 4));
@@ -321,7 +321,7 @@ int sr_set_views(sr_ctx *ctx, int V, const sr_camera *cams, const uint8_t *const
         if (!v.all_white) CK(cudaMemcpyAsync(v.mask, mask8[i], n, cudaMemcpyHostToDevice, ctx->stream));
         else CK(cudaMemsetAsync(v.mask, 255, n, ctx->stream));
         prep_view_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(v.rgba, v.mask, w, h, v.gray_pix,
-                                                                             v.gray_two, v.gray_msk, v.edges, v.gray_pix_f);
+                                                                             v.gray_two, v.gray_msk, v.edges, v.gray_pix_f, screen_pitch(w));
         CKL();
         // results start as "not computed": NaN depth (twoviewstereo.cpp:118-119), index NONE
         CK(cudaMemsetAsync(v.depth, 0xff, n * 8, ctx->stream));
@@ -517,6 +517,7 @@ int sr_run_view(sr_ctx *ctx, int ref, const int32_t *nbrs, int nn) {
                           : (P.cost_kind == SR_COST_NCC_TWOVIEW) ? B.gray_two : B.gray_msk;
             ma.grayRf[j] = B.gray_pix_f;
         }
+        ma.pitch_f = screen_pitch(w);
         ma.taps = ctx->d_taps;
         ma.depth_table = ctx->d_depth_table;
         ma.out_index = A.index;
@@ -764,6 +765,7 @@ int sr_run_view_curve(sr_ctx *ctx, int ref, const int32_t *nbrs, int nn) {
             ma.grayRf[j] = B.gray_pix_f;
             ma.raysR[j] = B.rays;
         }
+        ma.pitch_f = screen_pitch(w);
         ma.raysL = A.rays;
         memcpy(ma.camR, ctx->cams[ref].R, sizeof(ma.camR));
         memcpy(ma.camT, ctx->cams[ref].t, sizeof(ma.camT));

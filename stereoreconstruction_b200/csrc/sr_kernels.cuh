@@ -31,6 +31,8 @@
 namespace sr {
 
 constexpr int SR_MAX_NBRS = 8;
+// Row pitch of the FP32 gray planes: the smallest of 1024/2048/4096/16384 that holds a row.
+inline int screen_pitch(int w) { return w <= 1024 ? 1024 : w <= 2048 ? 2048 : w <= 4096 ? 4096 : 16384; }
 constexpr int32_t TAP_NONE = INT32_MIN;
 constexpr int TAP_CLAMP = 20000;  // |coordinate| beyond this is outside any image for any window
 
@@ -58,7 +60,7 @@ __device__ __forceinline__ double color_dist(uchar4 a, uchar4 b) {
 __global__ void prep_view_kernel(const uchar4 *__restrict__ rgba, const uint8_t *__restrict__ mask, int w, int h,
                                  double *__restrict__ gray_pix, double *__restrict__ gray_two,
                                  double *__restrict__ gray_msk, double *__restrict__ edges,
-                                 float *__restrict__ gray_pix_f) {
+                                 float *__restrict__ gray_pix_f, int pitch_f) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= w * h) return;
     const int x = i % w, y = i / w;
@@ -66,7 +68,9 @@ __global__ void prep_view_kernel(const uchar4 *__restrict__ rgba, const uint8_t 
     const double g = gray_of(c);
     const bool white = mask[i] == 255;
     gray_pix[i] = g;
-    gray_pix_f[i] = (float)g;  // FP32 copy read by the screening pass of match_mvs_screen_kernel
+    // FP32 copy read by the screening pass of match_mvs_screen_kernel; its row pitch is a power of
+    // two (screen_pitch) so that the 25 window loads are one base register + immediate offsets
+    gray_pix_f[(size_t)y * pitch_f + x] = (float)g;
     gray_msk[i] = white ? g : qnan();
     gray_two[i] = (white && x + 1 < w && y + 1 < h) ? g : qnan();
     const size_t n = (size_t)w * h;
@@ -314,6 +318,7 @@ struct MatchArgs {
     const double *grayL;            // reference taps  (gray_pix for C1, gray_two for C2/C3)
     const double *grayR[SR_MAX_NBRS];  // neighbour taps (gray_pix C1, gray_two C2, gray_msk C3)
     const float *grayRf[SR_MAX_NBRS];  // FP32 copies of gray_pix (screening pass, MVS selection only)
+    int pitch_f;                       // row pitch of the FP32 planes, in floats (screen_pitch(w))
     const double *W;                // [WN][rows*w] support weights of this band
     const int32_t *taps;            // [nbr][D][rows][w]
     const double *depth_table;      // [D]

@@ -28,8 +28,18 @@ cudaError_t launch_match_screen(const MatchArgs &a, cudaStream_t st) {
     constexpr int PPB = SCREEN_BLOCK / G;
     const size_t npix = (size_t)a.rows * a.w;
     const unsigned grid = (unsigned)((npix + PPB - 1) / PPB);
-    if (a.stats) match_mvs_screen_kernel<R, G, true><<<grid, SCREEN_BLOCK, 0, st>>>(a);
-    else match_mvs_screen_kernel<R, G, false><<<grid, SCREEN_BLOCK, 0, st>>>(a);
+    if (a.stats) {
+        match_mvs_screen_kernel<R, G, true, 0><<<grid, SCREEN_BLOCK, 0, st>>>(a);
+    } else if (G == 1) {  // thread-per-pixel radii: the row pitch is a compile-time constant
+        switch (a.pitch_f) {
+            case 1024: match_mvs_screen_kernel<R, G, false, (G == 1) ? 1024 : 0><<<grid, SCREEN_BLOCK, 0, st>>>(a); break;
+            case 2048: match_mvs_screen_kernel<R, G, false, (G == 1) ? 2048 : 0><<<grid, SCREEN_BLOCK, 0, st>>>(a); break;
+            case 4096: match_mvs_screen_kernel<R, G, false, (G == 1) ? 4096 : 0><<<grid, SCREEN_BLOCK, 0, st>>>(a); break;
+            default: match_mvs_screen_kernel<R, G, false, 0><<<grid, SCREEN_BLOCK, 0, st>>>(a); break;
+        }
+    } else {
+        match_mvs_screen_kernel<R, G, false, 0><<<grid, SCREEN_BLOCK, 0, st>>>(a);
+    }
     return cudaGetLastError();
 }
 

@@ -113,7 +113,8 @@ constexpr int SCREEN_BLOCK = SR_SCREEN_BLOCK;
 #define SR_SCREEN_PREFETCH 0    // labels of look-ahead for an L1 prefetch of the window's sectors
 #endif
 
-template <int R, int G, bool STATS>
+// PITCH: compile-time row pitch of the FP32 gray planes (0: run-time a.pitch_f).
+template <int R, int G, bool STATS, int PITCH>
 __global__ void __launch_bounds__(SCREEN_BLOCK, ((R <= 2) ? SR_SCREEN_MINBLOCKS : 2) * (128 / SCREEN_BLOCK))
     match_mvs_screen_kernel(const __grid_constant__ MatchArgs a) {
     constexpr int COST = SR_COST_NCC_MVS;
@@ -138,6 +139,7 @@ __global__ void __launch_bounds__(SCREEN_BLOCK, ((R <= 2) ? SR_SCREEN_MINBLOCKS 
     const int sub = tid % G;
     const unsigned gmask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << (lane & ~(G - 1)));
     const int w = a.w, h = a.h;
+    const int fp = PITCH ? PITCH : a.pitch_f;
     const int npix_i = a.rows * w;
     const size_t npix = (size_t)npix_i;
     const int pid_raw = blockIdx.x * PIX_PER_BLOCK + tid / G;
@@ -228,7 +230,7 @@ __global__ void __launch_bounds__(SCREEN_BLOCK, ((R <= 2) ? SR_SCREEN_MINBLOCKS 
         if (G == 1) {
 #pragma unroll
             for (int row = 0; row < WS; ++row) {
-                const float *__restrict__ rp = base + (row - R) * w;
+                const float *__restrict__ rp = base + (row - R) * fp;
 #pragma unroll
                 for (int col = 0; col < WS; ++col) g[row * WS + col] = rp[col - R];
             }
@@ -237,7 +239,7 @@ __global__ void __launch_bounds__(SCREEN_BLOCK, ((R <= 2) ? SR_SCREEN_MINBLOCKS 
             for (int i = 0; i < TPL; ++i) {
                 const int k = sub + G * i;
                 g[i] = 0.0f;
-                if (k < WN) g[i] = base[(k / WS - R) * w + (k % WS - R)];
+                if (k < WN) g[i] = base[(k / WS - R) * fp + (k % WS - R)];
             }
         }
         // three independent accumulator pairs per sum: the dependent FFMA2 chains stay short
@@ -385,17 +387,17 @@ __global__ void __launch_bounds__(SCREEN_BLOCK, ((R <= 2) ? SR_SCREEN_MINBLOCKS 
                 const int32_t tp = tap_ring[c & 1][l + SR_SCREEN_PREFETCH][tid];
                 const int px = (int)(short)(tp & 0xffff), py = (int)(short)((uint32_t)tp >> 16);
                 if (tp != TAP_NONE && tp != tap && px >= R && py >= R && px < w - R && py < h - R) {
-                    const float *pb = gRf + ((size_t)(py - R) * w + px);
+                    const float *pb = gRf + ((size_t)(py - R) * fp + px);
                     if (G == 1) {
 #pragma unroll
                         for (int row = 0; row < WS; ++row) {
-                            prefetch_l1(pb + row * w - R);
-                            prefetch_l1(pb + row * w + R);
+                            prefetch_l1(pb + row * fp - R);
+                            prefetch_l1(pb + row * fp + R);
                         }
                     } else {
                         for (int row = sub; row < WS; row += G) {
-                            prefetch_l1(pb + row * w - R);
-                            prefetch_l1(pb + row * w + R);
+                            prefetch_l1(pb + row * fp - R);
+                            prefetch_l1(pb + row * fp + R);
                         }
                     }
                 }
@@ -410,7 +412,7 @@ __global__ void __launch_bounds__(SCREEN_BLOCK, ((R <= 2) ? SR_SCREEN_MINBLOCKS 
                     c32 = SCREEN_FORCE;
                     eps = 0.0f;
                     if (!all_slow && tx >= R && ty >= R && tx < w - R && ty < h - R) {
-                        const float *base = gRf + ((size_t)ty * w + tx);
+                        const float *base = gRf + ((size_t)ty * fp + tx);
                         c32 = has_inactive ? screen_one(base, eps, std::true_type{}) : screen_one(base, eps, std::false_type{});
                     }
                     prevTap = tap;
