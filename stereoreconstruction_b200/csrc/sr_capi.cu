@@ -336,7 +336,7 @@ int sr_set_params(sr_ctx *ctx, const sr_params *p) {
     if (p->num_levels < 2 || p->num_levels > 65536) return fail(ctx, SR_ERR_INVALID, "num_levels must be in [2,65536]");
     if (!(p->image_scale > 0)) return fail(ctx, SR_ERR_INVALID, "image_scale must be > 0");
     if (!match_supported(p->radius))
-        return fail(ctx, SR_ERR_INVALID, "unsupported window radius (supported: 1-8, 10, 12, 16)");
+        return fail(ctx, SR_ERR_INVALID, "unsupported window radius (supported: " SR_RADII_TEXT ")");
     if (p->weight_kind < 0 || p->weight_kind > 1 || p->cost_kind < 0 || p->cost_kind > 2 || p->depth_kind < 0 ||
         p->depth_kind > 1 || p->select_kind < 0 || p->select_kind > 1)
         return fail(ctx, SR_ERR_INVALID, "bad enum in sr_params");

@@ -9,7 +9,15 @@ namespace sr {
 
 template <int R> struct LanesFor { static constexpr int G = (R <= 2) ? 1 : (R == 3) ? 2 : (R <= 5) ? 4 : (R <= 7) ? 8 : (R <= 10) ? 16 : 32; };
 
+// Radii with a compiled match kernel.  SR_FEW_RADII (the default build, capi.py) leaves out 6-12 to
+// keep the nvcc time of the (radius x cost x pitch) instantiations in check.
+#ifdef SR_FEW_RADII
+inline bool match_supported(int r) { return (r >= 1 && r <= 5) || r == 16; }
+#define SR_RADII_TEXT "1-5, 16 (build without -DSR_FEW_RADII for 6-8, 10, 12)"
+#else
 inline bool match_supported(int r) { return (r >= 1 && r <= 8) || r == 10 || r == 12 || r == 16; }
+#define SR_RADII_TEXT "1-8, 10, 12, 16"
+#endif
 
 template <int R, int COST>
 cudaError_t launch_match_rc(const MatchArgs &a, cudaStream_t st) {
