@@ -122,15 +122,19 @@ def cpu_sample(wl, imgs, rows, steps=1, warmup=0, target_s=12.0):
     nb = neighbours_for(wl)
     P = T.SrParams.from_buffer_copy(wl["params"])
 
+    last = {}
+
     def run(nrows):
         r0 = (wl["h"] - nrows) // 2
         P.row_begin, P.row_end = r0, r0 + nrows
         t0 = time.perf_counter()
         if wl["name"] == "cfg3":
-            sc.twoview_label(P, 0, 1)
+            od, oi, ob, _ = sc.twoview_label(P, 0, 1)
         else:
-            sc.mvs_view(P, 0, nb[0])
-        return time.perf_counter() - t0, r0
+            od, oi, ob, _, _ = sc.mvs_view(P, 0, nb[0])
+        dt = time.perf_counter() - t0
+        last.update(depth=od[r0:r0 + nrows], index=oi[r0:r0 + nrows], best=ob[r0:r0 + nrows], r0=r0, rows=nrows)
+        return dt, r0
 
     if rows <= 0:
         probe = max(2, min(wl["h"], O.num_threads()))  # one row per thread
@@ -146,6 +150,7 @@ def cpu_sample(wl, imgs, rows, steps=1, warmup=0, target_s=12.0):
             times.append(dt)
     units = rows * wl["w"] * wl["D"]
     t = sum(times) / len(times)
+    cpu_sample.last = last  # the band's outputs: compared with the GPU's for the same rows (parity at full size)
     return units / t / 1e6, t, O.num_threads(), f"{rows} rows x {wl['w']} px x {wl['D']} labels of reference view 0 (rows {r0}..{r0 + rows})"
 
 
@@ -321,6 +326,20 @@ def main():
     if not args.no_cpu:
         val, t, cores, sample = cpu_sample(wl, imgs, cpu_rows)
         cpu = {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample, "seconds": t}
+        # The oracle's outputs for that band are the checker of the GPU's at the benchmark's full size.
+        o = cpu_sample.last
+        if 0 in my_views and o:
+            ra, rb = o["r0"], o["r0"] + o["rows"]
+            gi, gd, gb = ctx.depth_index(0)[ra:rb], ctx.depth(0)[ra:rb], ctx.best_cost(0)[ra:rb]
+            mism = gi != o["index"]
+            lab = ~mism & (o["index"] >= 0)
+            with np.errstate(invalid="ignore"):
+                rel = np.abs(gb[lab] - o["best"][lab]) / np.maximum(np.abs(o["best"][lab]), 1e-300)
+            cpu["parity"] = {
+                "pixels": int(mism.size), "index_mismatch_rate": float(mism.mean()),
+                "depth_equal_where_index_equal": bool(((gd == o["depth"]) | (np.isnan(gd) & np.isnan(o["depth"])))[~mism].all()),
+                "max_rel_cost_diff": float(rel.max()) if rel.size else None, "labelled_fraction": float(lab.mean()),
+            }
 
     h2d = V * h * w * 4 * (len(my_views) / V if world > 1 else 1)
     line = {
