@@ -202,6 +202,13 @@ int sr_project_points(sr_ctx *ctx, int view, int n, const double *xyz, double *o
 /* AdaptiveWeight/GeodesicWeight::init_weights for n window centres
  * (stereo/adaptiveweight.cpp:47-58, stereo/geodesicweight.cpp:59-131):
  * out = n * (2r+1)^2 doubles, [row+r][col+r] as operator()(row,col) indexes. */
+/* The residual of the refractive-interface calibration, RefractiveCalibrationFunction::diff
+ * (stereo/refractioncalibration.cpp:175-201), for n correspondences: view_pairs = 2n camera
+ * indices into cams[num_cams], pixels = n * (x1, y1, x2, y2); out[i] = distance of the two
+ * unprojected rays scaled by 0.5*fx/z in both views.  Independent of sr_set_views; the
+ * Levenberg-Marquardt loop around it (util/lm.cpp) stays on the host. */
+int sr_calibration_residuals(sr_ctx *ctx, int num_cams, const sr_camera *cams, int n,
+                             const int32_t *view_pairs, const double *pixels, double *out);
 int sr_compute_weights(sr_ctx *ctx, int view, int weight_kind, int radius, int n,
                        const int32_t *cx, const int32_t *cy, double *out);
 

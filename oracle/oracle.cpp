@@ -1324,6 +1324,24 @@ void orc_unproject_grid(const Camera *cam, int w, int h, double scale, double *o
         for (int x = 0; x < w; ++x)
             orc_unproject(cam, (x + 0.5) / scale, (y + 0.5) / scale, out + ((size_t)y * w + x) * 6);
 }
+// stereo/refractioncalibration.cpp:175-201 (RefractiveCalibrationFunction::diff): distance of the
+// two unprojected rays, scaled by 0.5*fx/z in each view to approximate an image-space distance.
+void orc_calibration_residuals(const Camera *cams, int n, const int32_t *pairs, const double *pix, double *out) {
+    for (int i = 0; i < n; ++i) {
+        const Camera &v1 = cams[pairs[2 * i]], &v2 = cams[pairs[2 * i + 1]];
+        Ray R1 = v1.unproject(pix[4 * i], pix[4 * i + 1]);
+        Ray R2 = v2.unproject(pix[4 * i + 2], pix[4 * i + 3]);
+        V3 p1, p2;
+        closestPoints(R1, R2, p1, p2);
+        V3 df = p1 - p2;
+        const double dist = std::sqrt(dot(df, df));
+        V3 mid = (p1 + p2) * 0.5;
+        V3 mid1 = v1.fromGlobalToLocal(mid), mid2 = v2.fromGlobalToLocal(mid);
+        const double e1 = (0.5 * v1.K[0] * dist) / mid1.z;
+        const double e2 = (0.5 * v2.K[0] * dist) / mid2.z;
+        out[i] = e1 + e2;
+    }
+}
 int orc_project(const Camera *cam, const double *xyz, int rootMode, double *out2) {
     V3 p = {xyz[0], xyz[1], xyz[2]};
     bool ok = cam->project(p, rootMode);

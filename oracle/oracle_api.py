@@ -236,6 +236,15 @@ class Scene:
         return ds
 
 
+def calibration_residuals(cams, pairs, pixels):
+    """RefractiveCalibrationFunction::diff (stereo/refractioncalibration.cpp:175-201) per correspondence."""
+    pairs = np.ascontiguousarray(pairs, dtype=np.int32).reshape(-1, 2)
+    pixels = np.ascontiguousarray(pixels, dtype=np.float64).reshape(-1, 4)
+    out = np.empty(pairs.shape[0], dtype=np.float64)
+    lib().orc_calibration_residuals(as_cam_array(cams), pairs.shape[0], _ip(pairs), _dp(pixels), _dp(out))
+    return out
+
+
 def stats_reset():
     lib().orc_stats_reset()
 

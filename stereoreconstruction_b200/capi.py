@@ -26,7 +26,7 @@ EXPORTS = [
     "sr_set_stream", "sr_params_default", "sr_launch_count", "sr_set_profiling", "sr_get_stage_ms", "sr_get_match_stats", "sr_get_build_stats", "sr_set_views", "sr_set_params",
     "sr_run_view", "sr_run_view_curve", "sr_select_neighbours", "sr_cross_check", "sr_synchronize",
     "sr_get_depth_index", "sr_get_depth", "sr_get_best_cost", "sr_get_cost_volume", "sr_set_depth",
-    "sr_get_depth_image", "sr_unproject_grid", "sr_project_points", "sr_compute_weights",
+    "sr_get_depth_image", "sr_unproject_grid", "sr_project_points", "sr_compute_weights", "sr_calibration_residuals",
     "sr_comm_unique_id", "sr_comm_init", "sr_comm_allgather_views", "sr_comm_allgather_rows",
 ]
 
@@ -108,6 +108,14 @@ class Context:
     def _ck(self, rc):
         if rc != 0:
             raise SrError(f"sr error {rc}: {self._L.sr_last_error(self._h).decode()}")
+
+    def calibration_residuals(self, cams, pairs, pixels):
+        pairs = np.ascontiguousarray(pairs, dtype=np.int32).reshape(-1, 2)
+        pixels = np.ascontiguousarray(pixels, dtype=np.float64).reshape(-1, 4)
+        out = np.empty(pairs.shape[0], dtype=np.float64)
+        arr = (SrCamera * len(cams))(*cams)
+        self._ck(self._L.sr_calibration_residuals(self._h, len(cams), arr, pairs.shape[0], _p(pairs), _p(pixels), _p(out)))
+        return out
 
     def build_stats(self):
         out = np.zeros(4, np.uint64)

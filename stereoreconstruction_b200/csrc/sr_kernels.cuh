@@ -792,6 +792,31 @@ __global__ void __launch_bounds__(128) cross_check_kernel(const CrossArgs a) {
     }
 }
 
+// RefractiveCalibrationFunction::diff (stereo/refractioncalibration.cpp:175-201): the residual the
+// interface calibration minimises, one thread per correspondence.  (The Levenberg-Marquardt outer
+// loop, util/lm.cpp, stays on the host: a handful of parameters.)
+__global__ void calibration_residual_kernel(const sr_camera *__restrict__ cams, int n, const int32_t *__restrict__ pairs,
+                                            const double *__restrict__ pix, double *__restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const sr_camera &v1 = cams[pairs[2 * i]], &v2 = cams[pairs[2 * i + 1]];
+    d3 s1, d1, s2, d2;
+    cam_unproject(v1, pix[4 * i], pix[4 * i + 1], s1, d1);
+    cam_unproject(v2, pix[4 * i + 2], pix[4 * i + 3], s2, d2);
+    const d3 w0 = s1 - s2;  // Ray3d::closestPoints, util/ray.cpp:53-74
+    const double aa = dot(d1, d1), bb = dot(d1, d2), cc = dot(d2, d2), dd = dot(d1, w0), ee = dot(d2, w0);
+    const double den = 1.0 / (aa * cc - bb * bb);
+    const double tl = (bb * ee - cc * dd) * den, tr = (aa * ee - bb * dd) * den;
+    d3 p1 = s1, p2 = s2;
+    if (tl > 0) p1 = p1 + tl * d1;
+    if (tr > 0) p2 = p2 + tr * d2;
+    const d3 df = p1 - p2;
+    const double dist = sqrt(dot(df, df));
+    const d3 mid = 0.5 * (p1 + p2);
+    const double z1 = (mul3(v1.R, mid) + ld3(v1.t)).z, z2 = (mul3(v2.R, mid) + ld3(v2.t)).z;
+    out[i] = (0.5 * v1.K[0] * dist) / z1 + (0.5 * v2.K[0] * dist) / z2;
+}
+
 // colorFromDepth of MultiViewStereo (multiviewstereo.cpp:257-278) + the WHITE fill for masked
 // pixels (:381-395) -> RGBA8.
 __global__ void depth_image_mvs_kernel(const double *__restrict__ depth, const uint8_t *__restrict__ mask, int n,

@@ -272,3 +272,29 @@ def test_build_interpolation_self_check(monkeypatch):
     assert st["interpolated"] > 1e6
     assert st["tap_mismatches"] == 0
     assert st["guard_fallbacks"] < 0.01 * st["interpolated"]
+
+
+def test_calibration_residuals_match_oracle(arc, ctx):
+    """RefractiveCalibrationFunction::diff (stereo/refractioncalibration.cpp:175-201) on the GPU."""
+    cams, imgs, ms, sc = arc
+    rng = np.random.RandomState(21)
+    n = 5000
+    pairs = np.stack([rng.randint(0, 4, n), rng.randint(0, 4, n)], axis=1)
+    pairs[pairs[:, 0] == pairs[:, 1], 1] = (pairs[pairs[:, 0] == pairs[:, 1], 0] + 1) % 4
+    # true correspondences (projections of points on the scene surface) plus pixel noise
+    rays = sc.unproject_grid(0)
+    pts = (rays[..., :3] + rng.uniform(450, 550, rays.shape[:2] + (1,)) * rays[..., 3:]).reshape(-1, 3)
+    pts = pts[rng.randint(0, pts.shape[0], n)]
+    pix = np.empty((n, 4))
+    for v in range(4):
+        xy, ok = sc.project_points(v, pts)
+        for side in (0, 1):
+            m = pairs[:, side] == v
+            pix[m, 2 * side:2 * side + 2] = xy[m]
+    pix += rng.normal(scale=0.3, size=pix.shape)
+    g = ctx.calibration_residuals(cams, pairs, pix)
+    o = O.calibration_residuals(cams, pairs, pix)
+    fin = np.isfinite(o)
+    assert fin.mean() > 0.9 and (np.isfinite(g) == fin).all()
+    assert np.allclose(g[fin], o[fin], rtol=1e-10, atol=1e-12)
+    assert np.median(o[fin]) < 2.0  # sub-pixel noise gives pixel-scale residuals: the metric is what it claims
