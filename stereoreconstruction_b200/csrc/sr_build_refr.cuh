@@ -150,10 +150,14 @@ struct RefrProjector {
 // surrounding ANCHOR labels (every BUILD_STRIDE-th label, projected exactly as above).  What
 // must be exact is only trunc(U), trunc(V): the interpolated value is accepted when it is farther
 // from the nearest integer than a guard, otherwise that label is projected exactly as well.
-//   guard = |cubic - quadratic| + 1e-6 px = |third difference| * L2(x) + 1e-6
-// i.e. the full error of the NEXT-LOWER-order interpolant, ~100x the cubic's own error for these
-// functions (each higher difference shrinks by ~BUILD_STRIDE*dDepth/Depth ~ 1e-2).  With the
-// guard ~1e-4 px a label falls back with probability ~4e-4.
+//   guard = |third difference| * L2(x)  +  0.1 * |fourth difference|  +  1e-6 px
+// The first term is |cubic - quadratic|, the full error of the NEXT-LOWER-order interpolant (~100x
+// the cubic's own error where the differences decay, each by ~BUILD_STRIDE*dDepth/Depth ~ 1e-2).
+// The second bounds the cubic's own error, <= 0.0234 * |fourth difference| + higher orders, with a
+// 4x margin; it is what protects the labels near a sign change of the third difference, where the
+// first term vanishes (found with stride 8: 2 differing taps in 2.5e9 without it).  The fourth
+// difference is the change of the third difference from one interval to the next.  With the guard
+// ~1e-4 px a label falls back with probability ~4e-4.
 #ifndef SR_BUILD_STRIDE
 #define SR_BUILD_STRIDE 4
 #endif
@@ -218,6 +222,8 @@ __global__ void __launch_bounds__(128) build_refr_kernel(const __grid_constant__
         lw[s][3] = (xq + 1) * xq * (xq - 1) / 6;
         l2[s] = fabs(lw[s][3]);
     }
+    double d3u_prev = 0.0, d3v_prev = 0.0;  // signed third differences of the previous interval
+    bool have_d3 = false;
     const double CL = 30000.0;  // beyond any image: |c| >= TAP_CLAMP is outside every window
 #pragma unroll 1
     for (int kk = kfirst; kk * S < d1; ++kk) {
@@ -230,11 +236,20 @@ __global__ void __launch_bounds__(128) build_refr_kernel(const __grid_constant__
         }
         const int db = kk * S;
         const bool full = asane[0] && asane[1] && asane[2] && asane[3];
-        double d3u = 0.0, d3v = 0.0;
+        double d3u = 0.0, d3v = 0.0, d4u = 0.0, d4v = 0.0;
         if (full) {
-            d3u = fabs((au[3] - au[0]) - 3.0 * (au[2] - au[1]));
-            d3v = fabs((av_[3] - av_[0]) - 3.0 * (av_[2] - av_[1]));
+            const double su = (au[3] - au[0]) - 3.0 * (au[2] - au[1]);  // signed third differences
+            const double sv = (av_[3] - av_[0]) - 3.0 * (av_[2] - av_[1]);
+            d3u = fabs(su);
+            d3v = fabs(sv);
+            // fourth difference = change of the third difference between consecutive intervals; the
+            // first full interval of a sweep has no predecessor and takes |third difference| instead
+            d4u = have_d3 ? fabs(su - d3u_prev) : d3u;
+            d4v = have_d3 ? fabs(sv - d3v_prev) : d3v;
+            d3u_prev = su;
+            d3v_prev = sv;
         }
+        have_d3 = full;
         // ---- stage 1: coordinates of the S labels of this interval (branch-free) ----
         int tx[S], ty[S];
         bool ok[S];
@@ -253,7 +268,7 @@ __global__ void __launch_bounds__(128) build_refr_kernel(const __grid_constant__
             tx[s] = trunc_magic(U, du);  // |U|,|V| < 2^31 when `full`; otherwise recomputed below
             ty[s] = trunc_magic(V, dv);
             ok[s] = true;
-            const bool safe = full && du > fma(l2[s], d3u, 1e-6) && dv > fma(l2[s], d3v, 1e-6);
+            const bool safe = full && du > fma(l2[s], d3u, fma(0.1, d4u, 1e-6)) && dv > fma(l2[s], d3v, fma(0.1, d4v, 1e-6));
             if (!safe && db + s < d1) need_exact |= 1u << s;
         }
         // ---- stage 2 (rare): labels too close to a pixel boundary, or without a full stencil ----
