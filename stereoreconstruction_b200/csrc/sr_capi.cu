@@ -26,7 +26,7 @@ struct ViewDev {
     uchar4 *rgba = nullptr;
     uint8_t *mask = nullptr;
     double *gray_pix = nullptr, *gray_two = nullptr, *gray_msk = nullptr, *edges = nullptr;
-    float *gray_pix_f = nullptr, *gray_two_f = nullptr;
+    float *gray_pix_f = nullptr;
     bool all_white = false;  // no mask was passed for this view: every pixel is WHITE
     double *rays = nullptr;  // [6][h][w] Camera::unproject of every pixel centre (curve mode), lazily
     double rays_scale = 0.0; // image_scale the table was computed for (0: stale)
@@ -104,8 +104,6 @@ struct sr_ctx {
     size_t weights_cap = 0;
     float *d_volume = nullptr;
     size_t vol_cap = 0, vol_elems = 0;
-    float *d_c32 = nullptr;  // screened two-view cost volume of the current band
-    size_t c32_cap = 0;
     void *d_scratch = nullptr;
     size_t scratch_cap = 0;
     int64_t launches = 0;
@@ -154,7 +152,6 @@ void free_views(sr_ctx *c) {
         dfree(v.mask);
         dfree(v.gray_pix);
         dfree(v.gray_pix_f);
-        dfree(v.gray_two_f);
         dfree(v.rays);
         dfree(v.gray_two);
         dfree(v.gray_msk);
@@ -237,7 +234,6 @@ void sr_ctx_destroy(sr_ctx *c) {
     dfree(c->d_taps);
     dfree(c->d_weights);
     dfree(c->d_volume);
-    dfree(c->d_c32);
     dfree(c->d_stats);
     if (c->d_scratch) cudaFree(c->d_scratch);
     cudaStreamDestroy(c->own_stream);
@@ -296,7 +292,6 @@ int sr_set_views(sr_ctx *ctx, int V, const sr_camera *cams, const uint8_t *const
             CK(cudaMalloc(&v.mask, n));
             CK(cudaMalloc(&v.gray_pix, n * 8));
             CK(cudaMalloc(&v.gray_pix_f, (size_t)screen_pitch(w) * h * 4));
-            CK(cudaMalloc(&v.gray_two_f, (size_t)screen_pitch(w) * h * 4));
             CK(cudaMalloc(&v.gray_two, n * 8));
             CK(cudaMalloc(&v.gray_msk, n * 8));
             CK(cudaMalloc(&v.edges, n * 8 * 4));
@@ -326,7 +321,7 @@ int sr_set_views(sr_ctx *ctx, int V, const sr_camera *cams, const uint8_t *const
         if (!v.all_white) CK(cudaMemcpyAsync(v.mask, mask8[i], n, cudaMemcpyHostToDevice, ctx->stream));
         else CK(cudaMemsetAsync(v.mask, 255, n, ctx->stream));
         prep_view_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(v.rgba, v.mask, w, h, v.gray_pix,
-                                                                             v.gray_two, v.gray_msk, v.edges, v.gray_pix_f, v.gray_two_f, screen_pitch(w));
+                                                                             v.gray_two, v.gray_msk, v.edges, v.gray_pix_f, screen_pitch(w));
         CKL();
         // results start as "not computed": NaN depth (twoviewstereo.cpp:118-119), index NONE
         CK(cudaMemsetAsync(v.depth, 0xff, n * 8, ctx->stream));
@@ -388,11 +383,7 @@ int sr_run_view(sr_ctx *ctx, int ref, const int32_t *nbrs, int nn) {
     const size_t wn = (size_t)(2 * P.radius + 1) * (2 * P.radius + 1);
     const size_t per_row = (size_t)nn * D * w * 4;
     const size_t per_row_w = wn * w * 8;
-    // TwoViewStereo NCC without a kept volume: FP32 screen -> FP32 cost volume -> exact resolve
-    const bool two_screen = ctx->use_screen && P.select_kind == SR_SELECT_TWOVIEW && P.cost_kind == SR_COST_NCC_TWOVIEW &&
-                            !P.keep_cost_volume;
-    const size_t per_row_c = two_screen ? (size_t)D * w * 4 : 0;
-    int band = (int)std::min<size_t>((size_t)(r1 - r0), std::max<size_t>(1, ctx->tap_budget / (per_row + per_row_w + per_row_c)));
+    int band = (int)std::min<size_t>((size_t)(r1 - r0), std::max<size_t>(1, ctx->tap_budget / (per_row + per_row_w)));
     if (P.keep_cost_volume) band = r1 - r0;
     const size_t need = per_row * band;
     const size_t need_w = per_row_w * band;
@@ -409,13 +400,6 @@ int sr_run_view(sr_ctx *ctx, int ref, const int32_t *nbrs, int nn) {
         ctx->taps_cap = 0;
         CK(cudaMalloc(&ctx->d_taps, need));
         ctx->taps_cap = need;
-    }
-    if (two_screen && per_row_c * band > ctx->c32_cap) {
-        CK(cudaStreamSynchronize(st));
-        dfree(ctx->d_c32);
-        ctx->c32_cap = 0;
-        CK(cudaMalloc(&ctx->d_c32, per_row_c * band));
-        ctx->c32_cap = per_row_c * band;
     }
     ctx->vol_elems = 0;
     if (P.keep_cost_volume) {
@@ -531,10 +515,9 @@ int sr_run_view(sr_ctx *ctx, int ref, const int32_t *nbrs, int nn) {
             const ViewDev &B = ctx->views[nbrs[j]];
             ma.grayR[j] = (P.cost_kind == SR_COST_NCC_MVS) ? B.gray_pix
                           : (P.cost_kind == SR_COST_NCC_TWOVIEW) ? B.gray_two : B.gray_msk;
-            ma.grayRf[j] = two_screen ? B.gray_two_f : B.gray_pix_f;
+            ma.grayRf[j] = B.gray_pix_f;
         }
         ma.pitch_f = screen_pitch(w);
-        ma.screen_volume = two_screen ? ctx->d_c32 : nullptr;
         ma.taps = ctx->d_taps;
         ma.depth_table = ctx->d_depth_table;
         ma.out_index = A.index;

@@ -60,7 +60,7 @@ __device__ __forceinline__ double color_dist(uchar4 a, uchar4 b) {
 __global__ void prep_view_kernel(const uchar4 *__restrict__ rgba, const uint8_t *__restrict__ mask, int w, int h,
                                  double *__restrict__ gray_pix, double *__restrict__ gray_two,
                                  double *__restrict__ gray_msk, double *__restrict__ edges,
-                                 float *__restrict__ gray_pix_f, float *__restrict__ gray_two_f, int pitch_f) {
+                                 float *__restrict__ gray_pix_f, int pitch_f) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= w * h) return;
     const int x = i % w, y = i / w;
@@ -71,7 +71,6 @@ __global__ void prep_view_kernel(const uchar4 *__restrict__ rgba, const uint8_t 
     // FP32 copy read by the screening pass of match_mvs_screen_kernel; its row pitch is a power of
     // two (screen_pitch) so that the 25 window loads are one base register + immediate offsets
     gray_pix_f[(size_t)y * pitch_f + x] = (float)g;
-    gray_two_f[(size_t)y * pitch_f + x] = (white && x + 1 < w && y + 1 < h) ? (float)g : __int_as_float(0x7fc00000);
     gray_msk[i] = white ? g : qnan();
     gray_two[i] = (white && x + 1 < w && y + 1 < h) ? g : qnan();
     const size_t n = (size_t)w * h;
@@ -320,7 +319,6 @@ struct MatchArgs {
     const double *grayR[SR_MAX_NBRS];  // neighbour taps (gray_pix C1, gray_two C2, gray_msk C3)
     const float *grayRf[SR_MAX_NBRS];  // FP32 copies of gray_pix (screening pass, MVS selection only)
     int pitch_f;                       // row pitch of the FP32 planes, in floats (screen_pitch(w))
-    float *screen_volume;              // [nbr][D][rows][w] screened two-view costs (SCREEN_MODE_VOLUME)
     const double *W;                // [WN][rows*w] support weights of this band
     const int32_t *taps;            // [nbr][D][rows][w]
     const double *depth_table;      // [D]

@@ -51,29 +51,8 @@ cudaError_t launch_match_screen(const MatchArgs &a, cudaStream_t st) {
     return cudaGetLastError();
 }
 
-// TwoViewStereo selection with its NCC and no kept cost volume: FP32 screen into an FP32 cost
-// volume, then the sequential selection rule resolved exactly (twoview_resolve_kernel).
-template <int R>
-cudaError_t launch_match_twoview_screen(const MatchArgs &a, cudaStream_t st) {
-    constexpr int G = LanesFor<R>::G;
-    const size_t npix = (size_t)a.rows * a.w;
-    {
-        constexpr int PPB = SCREEN_BLOCK / G;
-        const unsigned grid = (unsigned)((npix + PPB - 1) / PPB);
-        match_mvs_screen_kernel<R, G, false, 0, SCREEN_MODE_VOLUME><<<grid, SCREEN_BLOCK, 0, st>>>(a);
-        cudaError_t e = cudaGetLastError();
-        if (e != cudaSuccess) return e;
-    }
-    constexpr int PPB2 = 128 / G;
-    twoview_resolve_kernel<R, G, SR_COST_NCC_TWOVIEW><<<(unsigned)((npix + PPB2 - 1) / PPB2), 128, 0, st>>>(a);
-    return cudaGetLastError();
-}
-
 template <int R>
 cudaError_t launch_match_r(int cost, const MatchArgs &a, cudaStream_t st) {
-    if (cost == SR_COST_NCC_TWOVIEW && a.select_kind == SR_SELECT_TWOVIEW && !a.out_volume && a.use_screen && !a.curve &&
-        a.screen_volume)
-        return launch_match_twoview_screen<R>(a, st);
     if (cost == SR_COST_NCC_MVS && a.select_kind == SR_SELECT_MVS && !a.out_volume && (a.use_screen || a.curve))
         return launch_match_screen<R>(a, st);
     switch (cost) {

@@ -114,17 +114,7 @@ constexpr int SCREEN_BLOCK = SR_SCREEN_BLOCK;
 #endif
 
 // PITCH: compile-time row pitch of the FP32 gray planes (0: run-time a.pitch_f).
-// MODE:  SCREEN_MODE_MVS     the MultiViewStereo selection described above;
-//        SCREEN_MODE_VOLUME  the same screening arithmetic for the TwoViewStereo cost: the
-//                            screened cost of every label goes to an FP32 volume (a.screen_volume)
-//                            and twoview_resolve_kernel applies the sequential selection rule.
-constexpr int SCREEN_MODE_MVS = 0, SCREEN_MODE_VOLUME = 1;
-// Error bars of the screened two-view cost min(120, 255 (1 - |ncc|)): 255 * eps(ncc) plus the
-// ulp of 120 that the class bit in the stored value's LSB costs.
-constexpr float SCREEN_COST_EPS_TIGHT = 255.0f * SCREEN_EPS_TIGHT + 2e-5f;
-constexpr float SCREEN_COST_EPS_LOOSE = 255.0f * SCREEN_EPS_LOOSE + 2e-5f;
-
-template <int R, int G, bool STATS, int PITCH, int MODE = SCREEN_MODE_MVS>
+template <int R, int G, bool STATS, int PITCH>
 __global__ void __launch_bounds__(SCREEN_BLOCK, ((R <= 2) ? SR_SCREEN_MINBLOCKS : 2) * (128 / SCREEN_BLOCK))
     match_mvs_screen_kernel(const __grid_constant__ MatchArgs a) {
     constexpr int COST = SR_COST_NCC_MVS;
@@ -159,7 +149,7 @@ __global__ void __launch_bounds__(SCREEN_BLOCK, ((R <= 2) ? SR_SCREEN_MINBLOCKS 
     const size_t pix = (size_t)y * w + x;
     // Lanes stay in the loops (warp-wide votes below); `alive` gates all work and all writes.
     const bool alive = in_band && a.maskL[pix] == 255;
-    if (MODE == SCREEN_MODE_MVS && in_band && !alive && sub == 0) {  // multiviewstereo.cpp:559,565: masked-out pixels stay INF
+    if (in_band && !alive && sub == 0) {  // multiviewstereo.cpp:559,565: masked-out pixels stay INF
         a.out_index[pix] = SR_INDEX_MASKED;
         a.out_depth[pix] = dinf();
         a.out_best[pix] = qnan();
@@ -433,18 +423,6 @@ __global__ void __launch_bounds__(SCREEN_BLOCK, ((R <= 2) ? SR_SCREEN_MINBLOCKS 
                         else ++n_screened;
                     }
                 }
-                if (MODE == SCREEN_MODE_VOLUME) {
-                    // two-view cost of the label; NaN = "evaluate exactly" for the resolve kernel; the
-                    // LSB of the stored value carries the error-bar class (1 = loose)
-                    float v = __int_as_float(0x7fc00000);
-                    if (c32 != SCREEN_FORCE) {
-                        v = fminf(120.0f, 255.0f * (1.0f - fabsf(c32)));
-                        const int bits = (__float_as_int(v) & ~1) | ((eps == SCREEN_EPS_TIGHT) ? 0 : 1);
-                        v = __int_as_float(bits);
-                    }
-                    if (sub == 0) a.screen_volume[((size_t)j * D + d0 + l) * npix + pid] = v;
-                    continue;
-                }
                 const float ub = c32 + eps;  // FORCE stays FORCE
                 if (ub >= lower32) {         // candidate
                     const int d = d0 + l;
@@ -479,14 +457,10 @@ __global__ void __launch_bounds__(SCREEN_BLOCK, ((R <= 2) ? SR_SCREEN_MINBLOCKS 
                     }
                 }
             }
-            else if (MODE == SCREEN_MODE_VOLUME) {
-                if (alive && sub == 0) a.screen_volume[((size_t)j * D + d0 + l) * npix + pid] = __int_as_float(0x7f800000);  // +INF: no tap
-            }
-            if (MODE == SCREEN_MODE_MVS && __any_sync(0xffffffffu, qn == SCREEN_QCAP)) flush();
+            if (__any_sync(0xffffffffu, qn == SCREEN_QCAP)) flush();
         }
     }
     cp_async_wait<0>();
-    if (MODE == SCREEN_MODE_VOLUME) return;
     flush();
 
     if (STATS && a.stats && alive && sub == 0) {
@@ -503,79 +477,6 @@ __global__ void __launch_bounds__(SCREEN_BLOCK, ((R <= 2) ? SR_SCREEN_MINBLOCKS 
         a.out_index[pix] = bestIdx;
         a.out_depth[pix] = (bestIdx >= 0) ? (a.curve ? px_bestZ[tid] : a.depth_table[bestIdx]) : -1.0;
         a.out_best[pix] = px_bestC[tid];
-    }
-}
-
-// TwoViewStereo selection over the screened cost volume (stereo/twoviewstereo.cpp:293-305,320-325):
-//     for d in order:  if (cost_d + 1e-10 < minCost) { second = minCost; minCost = cost_d; best = d }
-//     reject if minCost > SECOND_BEST_FACTOR * second
-// Only two labels matter: the LAST record r_m (best, minCost) and the record before it (second).
-// With [lb_d, ub_d] the screened interval of label d and U = min_d ub_d, every label that can be
-// r_m has lb_d <= U (+1e-9 for the 1e-10 margin); those few are evaluated exactly (slow_cost, the
-// reference's own tap filter in FP64) and replayed in label order, which reproduces r_m because no
-// label outside the set can come within the margin of the minimum.  `second` is the same problem
-// on the prefix [0, r_m).  Labels the screen could not bound (NaN) are always evaluated exactly.
-template <int R, int G, int COST>
-__global__ void __launch_bounds__(128) twoview_resolve_kernel(const __grid_constant__ MatchArgs a) {
-    const int lane = threadIdx.x & 31;
-    const int sub = threadIdx.x % G;
-    const unsigned gmask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << (lane & ~(G - 1)));
-    const int pid = blockIdx.x * (128 / G) + threadIdx.x / G;
-    if (pid >= a.rows * a.w) return;  // whole group leaves together
-    const int w = a.w;
-    const int x = pid % w, y = a.row0 + pid / w;
-    const size_t pix = (size_t)y * w + x;
-    const size_t npix = (size_t)a.rows * w;
-    if (a.maskL[pix] != 255) {  // twoviewstereo.cpp:269-271
-        if (sub == 0) {
-            a.out_index[pix] = SR_INDEX_MASKED;
-            a.out_depth[pix] = qnan();
-            a.out_best[pix] = qnan();
-        }
-        return;
-    }
-    const int D = a.D;
-    const float *__restrict__ vol = a.screen_volume + pid;
-    const int32_t *__restrict__ taps = a.taps + pid;
-    const double *__restrict__ gR = a.grayR[0];
-    auto eps_of = [](float v) { return (__float_as_int(v) & 1) ? SCREEN_COST_EPS_LOOSE : SCREEN_COST_EPS_TIGHT; };
-    // replays labels [0, end): returns the last record's label and cost
-    auto last_record = [&](int end, int &idx, double &cost_out) {
-        float U = __int_as_float(0x7f800000);
-        for (int d = 0; d < end; ++d) {
-            const float v = vol[(size_t)d * npix];
-            if (v == v && v < 1e30f) U = fminf(U, fminf(120.0f, v + eps_of(v)));
-        }
-        idx = SR_INDEX_NONE;
-        double minCost = dinf();
-        for (int d = 0; d < end; ++d) {
-            const float v = vol[(size_t)d * npix];
-            const bool cand = (v != v) || (v < 1e30f && v - eps_of(v) <= U + 1e-6f);  // (+INF = no tap: never)
-            if (cand) {
-                const int32_t tap = taps[(size_t)d * npix];
-                const int tx = (int)(short)(tap & 0xffff), ty = (int)(short)((uint32_t)tap >> 16);
-                const double cost = slow_cost<R, G, COST>(a, gR, x, y, tx, ty, pid, sub, gmask);
-                if (cost + 1e-10 < minCost) {
-                    minCost = cost;
-                    idx = d;
-                }
-            }
-        }
-        cost_out = minCost;
-    };
-    int bestIdx, prevIdx;
-    double minCost, secondBest;
-    last_record(D, bestIdx, minCost);
-    last_record(bestIdx >= 0 ? bestIdx : 0, prevIdx, secondBest);
-    if (sub == 0) {
-        double depth = (bestIdx >= 0) ? a.depth_table[bestIdx] : qnan();
-        if (a.second_best_factor > 0.0 && minCost > a.second_best_factor * secondBest) {  // :304-305
-            depth = dinf();
-            bestIdx = SR_INDEX_REJECTED;
-        }
-        a.out_index[pix] = bestIdx;
-        a.out_depth[pix] = depth;
-        a.out_best[pix] = minCost;
     }
 }
 

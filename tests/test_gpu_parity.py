@@ -298,59 +298,3 @@ def test_calibration_residuals_match_oracle(arc, ctx):
     assert fin.mean() > 0.9 and (np.isfinite(g) == fin).all()
     assert np.allclose(g[fin], o[fin], rtol=1e-10, atol=1e-12)
     assert np.median(o[fin]) < 2.0  # sub-pixel noise gives pixel-scale residuals: the metric is what it claims
-
-
-@pytest.mark.parametrize("weight", [T.SR_WEIGHT_ADAPTIVE, T.SR_WEIGHT_GEODESIC])
-@pytest.mark.parametrize("radius", [2, 3, 5])
-def test_twoview_screen_path_matches_oracle(arc, ctx, weight, radius):
-    """The production two-view NCC path (no kept volume): FP32 screen into an FP32 cost volume,
-    then the sequential selection rule resolved with exact FP64 evaluations of the few labels that
-    can be the last two records (twoview_resolve_kernel)."""
-    cams, imgs, ms, sc = arc
-    ctx.set_views(cams, imgs, ms)
-    P = T.default_params(False, 420.0, 580.0, 48, radius=radius, weight_kind=weight)
-    ctx.set_params(P)
-    for (a, b) in ((1, 2), (2, 1)):
-        ctx.run_view(a, [b])
-        gi, gd, gb = ctx.depth_index(a), ctx.depth(a), ctx.best_cost(a)
-        od, oi, ob, _ = sc.twoview_label(P, a, b, root_mode=1)
-        mism = gi != oi
-        assert mism.mean() <= 1e-4, f"index mismatch rate {mism.mean()}"
-        same = ~mism
-        assert ((gd == od) | (np.isnan(gd) & np.isnan(od)))[same].all()
-        lab = same & np.isfinite(ob)
-        assert (gi >= 0).mean() > 0.1
-        assert np.abs(gb[lab] - ob[lab]).max() <= 1e-9 * 120
-
-
-def test_twoview_screen_rectified_r16(ctx):
-    cams, imgs, ms, surf = rectified_scene(w=112, h=40)
-    sc = O.Scene(cams, imgs)
-    ctx.set_views(cams, imgs, None)
-    P = T.default_params(False, 100.0, 500.0, 32, radius=16, weight_kind=T.SR_WEIGHT_ADAPTIVE)
-    ctx.set_params(P)
-    for (a, b) in ((0, 1), (1, 0)):
-        ctx.run_view(a, [b])
-        gi, gd = ctx.depth_index(a), ctx.depth(a)
-        od, oi, ob, _ = sc.twoview_label(P, a, b, root_mode=1)
-        assert (gi != oi).mean() <= 1e-4
-        assert ((gd == od) | (np.isnan(gd) & np.isnan(od)))[gi == oi].all()
-
-
-def test_twoview_screen_equals_all_fp64_kernel(monkeypatch):
-    cams, imgs, ms, surf = refractive_arc_scene(V=4, w=320, h=200, arc_deg=25.0, cell=6.0)
-    P = T.default_params(False, 420.0, 580.0, 96, radius=5)
-    out = []
-    for flag in ("0", "1"):
-        monkeypatch.setenv("SR_MATCH_SCREEN", flag)
-        c = capi.Context(0)
-        c.set_views(cams, imgs, None)
-        c.set_params(P)
-        c.run_view(1, [2])
-        out.append((c.depth_index(1).copy(), c.best_cost(1).copy()))
-        c.close()
-    (i0, b0), (i1, b1) = out
-    assert (i0 >= 0).mean() > 0.1
-    assert (i0 != i1).mean() <= 1e-5, f"{(i0 != i1).sum()} pixels differ"
-    same = i0 == i1
-    assert np.abs(b0[same] - b1[same]).max() <= 1e-6
