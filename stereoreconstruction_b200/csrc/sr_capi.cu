@@ -212,6 +212,12 @@ int sr_ctx_create(int device, sr_ctx **out) {
         return fail(nullptr, SR_ERR_CUDA, cudaGetErrorString(e));
     }
     c->stream = c->own_stream;
+    {   // scratch budget of one row band: a quarter of the device memory, at most 32 GiB (a B200 has
+        // 180 GB: cfg5's 51 GB tap volume runs in 2 bands), at least 1 GiB
+        size_t free_b = 0, total_b = 0;
+        if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess && total_b > 0)
+            c->tap_budget = std::max<size_t>((size_t)1 << 30, std::min<size_t>((size_t)32 << 30, total_b / 4));
+    }
     if (const char *mb = getenv("SR_TAP_BUDGET_MB")) c->tap_budget = (size_t)atoll(mb) << 20;
     if (const char *sc = getenv("SR_MATCH_SCREEN")) c->use_screen = atoi(sc) != 0;
     if (const char *sb = getenv("SR_BUILD_REFR")) c->use_refr_build = atoi(sb) != 0;
