@@ -95,7 +95,8 @@ typedef struct sr_params {
     int32_t select_kind;  /* SR_SELECT_*                                          */
     double second_best_factor; /* SECOND_BEST_FACTOR 0.95; <= 0 disables the test */
     double ncc_threshold;      /* 0.95, stereo/multiviewstereo.cpp:589            */
-    int32_t keep_cost_volume;  /* 1: keep the FP32 cost volume for sr_get_cost_volume */
+    int32_t keep_cost_volume;  /* bit 0: keep the FP32 cost volume for sr_get_cost_volume;
+                                * bit 1: keep the K = 9 peak lists for sr_get_peaks (MVS selection) */
     int32_t row_begin;    /* rows [row_begin,row_end) of the reference view are     */
     int32_t row_end;      /* processed (row sharding); row_end <= 0 means height  */
 } sr_params;
@@ -185,6 +186,11 @@ int sr_get_best_cost(sr_ctx *ctx, int view, double *out);
 int sr_get_cost_volume(sr_ctx *ctx, float *out, size_t out_elems);
 /* Replaces depth upload for cross-check under view sharding (each rank receives
  * the other ranks' depth maps before sr_cross_check). */
+/* The K = 9 largest (ncc, depth) pairs of every pixel of the last sr_run_view with
+ * keep_cost_volume & 2, ascending, padded with (0, -1): CostFunction::peakPairs, the input of
+ * the reference's MRF stage (stereo/multiviewstereo.cpp:479-482,562,589-602).  out = h*w*9*2
+ * doubles, [pixel][k][ncc, depth].  Label mode; evaluates every label in FP64. */
+int sr_get_peaks(sr_ctx *ctx, int view, double *out);
 int sr_set_depth(sr_ctx *ctx, int view, const double *depth);
 /* colorFromDepth + depthMap(view): stereo/multiviewstereo.cpp:257-286 (mvs != 0,
  * gray ramp, masked -> WHITE) or stereo/twoviewstereo.cpp:128-146 (HSV ramp).

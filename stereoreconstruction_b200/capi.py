@@ -25,7 +25,7 @@ EXPORTS = [
     "sr_ctx_create", "sr_ctx_destroy", "sr_last_error", "sr_request_cancel", "sr_clear_cancel",
     "sr_set_stream", "sr_params_default", "sr_launch_count", "sr_set_profiling", "sr_get_stage_ms", "sr_get_match_stats", "sr_get_build_stats", "sr_set_views", "sr_set_params",
     "sr_run_view", "sr_run_view_curve", "sr_select_neighbours", "sr_cross_check", "sr_synchronize",
-    "sr_get_depth_index", "sr_get_depth", "sr_get_best_cost", "sr_get_cost_volume", "sr_set_depth",
+    "sr_get_depth_index", "sr_get_depth", "sr_get_best_cost", "sr_get_cost_volume", "sr_get_peaks", "sr_set_depth",
     "sr_get_depth_image", "sr_unproject_grid", "sr_project_points", "sr_compute_weights", "sr_calibration_residuals",
     "sr_comm_unique_id", "sr_comm_init", "sr_comm_allgather_views", "sr_comm_allgather_rows",
 ]
@@ -115,6 +115,11 @@ class Context:
         out = np.empty(pairs.shape[0], dtype=np.float64)
         arr = (SrCamera * len(cams))(*cams)
         self._ck(self._L.sr_calibration_residuals(self._h, len(cams), arr, pairs.shape[0], _p(pairs), _p(pixels), _p(out)))
+        return out
+
+    def peaks(self, view):
+        out = np.empty((self.h, self.w, 9, 2), dtype=np.float64)
+        self._ck(self._L.sr_get_peaks(self._h, int(view), _p(out)))
         return out
 
     def build_stats(self):

@@ -104,6 +104,8 @@ struct sr_ctx {
     size_t weights_cap = 0;
     float *d_volume = nullptr;
     size_t vol_cap = 0, vol_elems = 0;
+    double *d_peaks = nullptr;  // [9][2][h*w] of the last view run with keep_cost_volume & 2
+    int peaks_view = -1;
     void *d_scratch = nullptr;
     size_t scratch_cap = 0;
     int64_t launches = 0;
@@ -240,6 +242,7 @@ void sr_ctx_destroy(sr_ctx *c) {
     dfree(c->d_taps);
     dfree(c->d_weights);
     dfree(c->d_volume);
+    dfree(c->d_peaks);
     dfree(c->d_stats);
     if (c->d_scratch) cudaFree(c->d_scratch);
     cudaStreamDestroy(c->own_stream);
@@ -390,7 +393,7 @@ int sr_run_view(sr_ctx *ctx, int ref, const int32_t *nbrs, int nn) {
     const size_t per_row = (size_t)nn * D * w * 4;
     const size_t per_row_w = wn * w * 8;
     int band = (int)std::min<size_t>((size_t)(r1 - r0), std::max<size_t>(1, ctx->tap_budget / (per_row + per_row_w)));
-    if (P.keep_cost_volume) band = r1 - r0;
+    if (P.keep_cost_volume & 1) band = r1 - r0;
     const size_t need = per_row * band;
     const size_t need_w = per_row_w * band;
     if (need_w > ctx->weights_cap) {
@@ -407,8 +410,21 @@ int sr_run_view(sr_ctx *ctx, int ref, const int32_t *nbrs, int nn) {
         CK(cudaMalloc(&ctx->d_taps, need));
         ctx->taps_cap = need;
     }
+    ctx->peaks_view = -1;
+    if (P.keep_cost_volume & 2) {  // the K = 9 peak pairs per pixel, initialised to (0, -1) (multiviewstereo.cpp:562)
+        if (P.select_kind != SR_SELECT_MVS) return fail(ctx, SR_ERR_INVALID, "peak lists belong to the multi-view selection");
+        if (!ctx->d_peaks) CK(cudaMalloc(&ctx->d_peaks, n * 18 * 8));
+        std::vector<double> init(n * 18);
+        for (int k = 0; k < 9; ++k) {
+            std::fill(init.begin() + (size_t)(2 * k) * n, init.begin() + (size_t)(2 * k + 1) * n, 0.0);
+            std::fill(init.begin() + (size_t)(2 * k + 1) * n, init.begin() + (size_t)(2 * k + 2) * n, -1.0);
+        }
+        CK(cudaMemcpyAsync(ctx->d_peaks, init.data(), n * 18 * 8, cudaMemcpyHostToDevice, st));
+        CK(cudaStreamSynchronize(st));
+        ctx->peaks_view = ref;
+    }
     ctx->vol_elems = 0;
-    if (P.keep_cost_volume) {
+    if (P.keep_cost_volume & 1) {
         if (need > ctx->vol_cap) {
             CK(cudaStreamSynchronize(st));
             dfree(ctx->d_volume);
@@ -529,7 +545,8 @@ int sr_run_view(sr_ctx *ctx, int ref, const int32_t *nbrs, int nn) {
         ma.out_index = A.index;
         ma.out_depth = A.depth;
         ma.out_best = A.best;
-        ma.out_volume = P.keep_cost_volume ? ctx->d_volume : nullptr;
+        ma.out_volume = (P.keep_cost_volume & 1) ? ctx->d_volume : nullptr;
+        ma.out_peaks = (P.keep_cost_volume & 2) ? ctx->d_peaks : nullptr;
         ma.w = w;
         ma.h = h;
         ma.row0 = b0;
@@ -889,6 +906,19 @@ int sr_get_cost_volume(sr_ctx *ctx, float *out, size_t out_elems) {
     if (ctx->vol_elems == 0) return fail(ctx, SR_ERR_STATE, "no cost volume kept (set keep_cost_volume and run)");
     if (out_elems < ctx->vol_elems) return fail(ctx, SR_ERR_INVALID, "output buffer too small");
     return d2h(ctx, out, ctx->d_volume, ctx->vol_elems * 4);
+}
+int sr_get_peaks(sr_ctx *ctx, int view, double *out) {
+    int rc = check_view(ctx, view);
+    if (rc) return rc;
+    if (!out) return SR_ERR_INVALID;
+    if (ctx->peaks_view != view) return fail(ctx, SR_ERR_STATE, "no peak lists kept for this view (set keep_cost_volume |= 2 and run it)");
+    const size_t n = (size_t)ctx->w * ctx->h;
+    std::vector<double> planar(n * 18);
+    rc = d2h(ctx, planar.data(), ctx->d_peaks, n * 18 * 8);
+    if (rc) return rc;
+    for (size_t i = 0; i < n; ++i)  // device layout [9][2][pixel] -> the [pixel][9][2] the API documents
+        for (int k = 0; k < 18; ++k) out[i * 18 + k] = planar[(size_t)k * n + i];
+    return SR_OK;
 }
 int sr_set_depth(sr_ctx *ctx, int view, const double *depth) {
     int rc = check_view(ctx, view);

@@ -326,6 +326,8 @@ struct MatchArgs {
     double *out_depth;              // [h][w]
     double *out_best;               // [h][w]
     float *out_volume;              // [nbr][D][rows][w] or null
+    double *out_peaks;              // [9][2][h*w] or null: the K = 9 largest (ncc, depth) pairs per pixel,
+                                    // ascending (CostFunction::peakPairs, multiviewstereo.cpp:479-482,600-602)
     int w, h, row0, rows, D, num_nbrs;
     int select_kind;
     int depth_up;                   // depth_table is increasing in the label (max_depth > min_depth)
@@ -676,6 +678,28 @@ __global__ void __launch_bounds__(128, (R <= 2) ? SR_MATCH_MINBLOCKS : 2) match_
                 if (cost != cost) cost = slow_cost<R, G, COST>(a, gR, x, y, tx, ty, pid, sub, gmask);
                 // ---- stage (3): winner-take-all, fused ----
                 const int d = d0 + l;
+                if (mvs && a.out_peaks && sub == 0 && cost > a.ncc_threshold) {
+                    // peaks.push_back(pair(ncc, depth)); sort; keep the last K (multiviewstereo.cpp:589-602):
+                    // kept incrementally as an ascending list, smallest entry first
+                    const size_t n = (size_t)w * h;
+                    double *pk = a.out_peaks + pix;  // entry k: pk[(2k)*n] = ncc, pk[(2k+1)*n] = depth
+                    const double dep = a.depth_table[d0 + l];
+                    const double c0 = pk[0], z0 = pk[n];
+                    if (cost > c0 || (cost == c0 && dep > z0)) {
+                        int k = 0;  // drop entry 0, shift smaller entries down, insert in order
+                        for (; k + 1 < 9; ++k) {
+                            const double ck = pk[(size_t)(2 * k + 2) * n], zk = pk[(size_t)(2 * k + 3) * n];
+                            if (cost > ck || (cost == ck && dep > zk)) {
+                                pk[(size_t)(2 * k) * n] = ck;
+                                pk[(size_t)(2 * k + 1) * n] = zk;
+                            } else {
+                                break;
+                            }
+                        }
+                        pk[(size_t)(2 * k) * n] = cost;
+                        pk[(size_t)(2 * k + 1) * n] = dep;
+                    }
+                }
                 if (mvs) {  // multiviewstereo.cpp:589-602,654-660: max over (ncc, depth) pairs
                     // depthFromLabel is strictly monotone in the label, so "depth > bestD" is decided
                     // on the indices (deeper == d > bestIdx iff depth_up); the table is read once at

@@ -53,7 +53,7 @@ cudaError_t launch_match_screen(const MatchArgs &a, cudaStream_t st) {
 
 template <int R>
 cudaError_t launch_match_r(int cost, const MatchArgs &a, cudaStream_t st) {
-    if (cost == SR_COST_NCC_MVS && a.select_kind == SR_SELECT_MVS && !a.out_volume && (a.use_screen || a.curve))
+    if (cost == SR_COST_NCC_MVS && a.select_kind == SR_SELECT_MVS && !a.out_volume && !a.out_peaks && (a.use_screen || a.curve))
         return launch_match_screen<R>(a, st);
     switch (cost) {
         case SR_COST_NCC_TWOVIEW: return launch_match_rc<R, SR_COST_NCC_TWOVIEW>(a, st);

@@ -298,3 +298,28 @@ def test_calibration_residuals_match_oracle(arc, ctx):
     assert fin.mean() > 0.9 and (np.isfinite(g) == fin).all()
     assert np.allclose(g[fin], o[fin], rtol=1e-10, atol=1e-12)
     assert np.median(o[fin]) < 2.0  # sub-pixel noise gives pixel-scale residuals: the metric is what it claims
+
+
+@pytest.mark.parametrize("radius", [2, 3])
+def test_mvs_peak_lists_match_oracle(arc, ctx, radius):
+    """CostFunction::peakPairs (multiviewstereo.cpp:479-482,589-602): the 9 largest (ncc, depth) pairs."""
+    cams, imgs, ms, sc = arc
+    ctx.set_views(cams, imgs, ms)
+    nb = ctx.select_neighbours(3)
+    P = T.default_params(True, 420.0, 580.0, 40, radius=radius, keep_cost_volume=2)
+    ctx.set_params(P)
+    ctx.run_view(1, nb[1])
+    gp = ctx.peaks(1)
+    gi = ctx.depth_index(1)
+    od, oi, ob, _, op = sc.mvs_view(P, 1, nb[1], want_peaks=True)
+    assert (gi != oi).mean() <= 1e-4
+    white = ms[1] == 255
+    assert (gp[..., 1][white] == op[..., 1][white]).mean() > 1 - 1e-3  # depths of the kept pairs
+    assert not cost_close(gp[..., 0][white], op[..., 0][white]).any() or \
+        cost_close(gp[..., 0][white], op[..., 0][white]).mean() <= 1e-3
+    assert (gp[..., 0][white][:, -1] > 0.95).mean() > 0.1  # the last entry is the winner
+    P.keep_cost_volume = 0
+    ctx.set_params(P)
+    with pytest.raises(capi.SrError):
+        ctx.run_view(1, nb[1])
+        ctx.peaks(1)
