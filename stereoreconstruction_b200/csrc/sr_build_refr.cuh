@@ -250,6 +250,7 @@ __global__ void __launch_bounds__(128) build_refr_kernel(const __grid_constant__
             d3v_prev = sv;
         }
         have_d3 = full;
+        const double g0u = fma(0.1, d4u, 1e-6), g0v = fma(0.1, d4v, 1e-6);  // label-independent part of the guard
         // ---- stage 1: coordinates of the S labels of this interval (branch-free) ----
         int tx[S], ty[S];
         bool ok[S];
@@ -268,7 +269,7 @@ __global__ void __launch_bounds__(128) build_refr_kernel(const __grid_constant__
             tx[s] = trunc_magic(U, du);  // |U|,|V| < 2^31 when `full`; otherwise recomputed below
             ty[s] = trunc_magic(V, dv);
             ok[s] = true;
-            const bool safe = full && du > fma(l2[s], d3u, fma(0.1, d4u, 1e-6)) && dv > fma(l2[s], d3v, fma(0.1, d4v, 1e-6));
+            const bool safe = full && du > fma(l2[s], d3u, g0u) && dv > fma(l2[s], d3v, g0v);
             if (!safe && db + s < d1) need_exact |= 1u << s;
         }
         // ---- stage 2 (rare): labels too close to a pixel boundary, or without a full stencil ----

@@ -178,6 +178,14 @@ int ensure_scratch(sr_ctx *ctx, size_t bytes) {
     return SR_OK;
 }
 
+void launch_geodesic(const WeightArgs &wa, unsigned gx, cudaStream_t st) {
+    const size_t cells = (size_t)(2 * wa.radius + 1) * (2 * wa.radius + 1);
+    if (cells * 128 * sizeof(double) <= 48 * 1024)
+        weights_geodesic_kernel<true><<<gx, 128, cells * 128 * sizeof(double), st>>>(wa);
+    else
+        weights_geodesic_kernel<false><<<gx, 128, 0, st>>>(wa);
+}
+
 double depth_from_label(const sr_params &p, int label) {
     double t = label / (p.num_levels - 1.0);
     if (p.depth_kind == SR_DEPTH_INV5) t /= (5 - 4 * t);  // stereo/twoviewstereo.cpp:981-985
@@ -525,7 +533,7 @@ int sr_run_view(sr_ctx *ctx, int ref, const int32_t *nbrs, int nn) {
             if (P.weight_kind == SR_WEIGHT_ADAPTIVE)
                 weights_adaptive_kernel<<<gx, 128, (P.radius + 1) * sizeof(double), st>>>(wa);
             else
-                weights_geodesic_kernel<<<gx, 128, 0, st>>>(wa);
+                launch_geodesic(wa, gx, st);
             CKL();
         }
         MatchArgs ma;
@@ -773,7 +781,7 @@ int sr_run_view_curve(sr_ctx *ctx, int ref, const int32_t *nbrs, int nn) {
             if (P.weight_kind == SR_WEIGHT_ADAPTIVE)
                 weights_adaptive_kernel<<<gx, 128, (P.radius + 1) * sizeof(double), st>>>(wa);
             else
-                weights_geodesic_kernel<<<gx, 128, 0, st>>>(wa);
+                launch_geodesic(wa, gx, st);
             CKL();
         }
         MatchArgs ma;
@@ -1008,7 +1016,7 @@ int sr_compute_weights(sr_ctx *ctx, int view, int kind, int radius, int n, const
     if (kind == SR_WEIGHT_ADAPTIVE)
         weights_adaptive_kernel<<<(n + 127) / 128, 128, (radius + 1) * sizeof(double), ctx->stream>>>(wa);
     else
-        weights_geodesic_kernel<<<(n + 127) / 128, 128, 0, ctx->stream>>>(wa);
+        launch_geodesic(wa, (unsigned)((n + 127) / 128), ctx->stream);
     CKL();
     std::vector<double> tmp((size_t)n * wn);
     rc = d2h(ctx, tmp.data(), dW, (size_t)n * wn * 8);

@@ -251,13 +251,21 @@ __global__ void __launch_bounds__(128) weights_adaptive_kernel(const WeightArgs 
 // reference's, and the colour distances come from the precomputed edge planes, so the result is
 // the reference's up to the final exp().  Cells whose pixel is outside the image are never
 // updated and every edge into them is +INF, which reproduces the reference's validity tests.
+// SMEM: the grid lives in shared memory ([cell][thread], conflict-free) during the sweeps and is
+// written to W once at the end — used when (2R+1)^2 * 128 doubles fit (R <= 2); otherwise the grid
+// is the thread's column of W itself.
+template <bool SMEM>
 __global__ void __launch_bounds__(128) weights_geodesic_kernel(const WeightArgs a) {
+    extern __shared__ double grid_s[];
     const int R = a.radius, WS = 2 * R + 1;
     const int pid = blockIdx.x * blockDim.x + threadIdx.x;
     size_t npix;
     int cx, cy;
     if (!weight_centre(a, pid, npix, cx, cy)) return;
-    double *c = a.W + pid;
+    double *const out = a.W + pid;
+    const size_t out_stride = npix;
+    double *c = SMEM ? (grid_s + threadIdx.x) : out;
+    if (SMEM) npix = 128;  // stride of the grid the sweeps walk on
     for (int k = 0; k < WS * WS; ++k) c[(size_t)k * npix] = 1000000.0;
     c[(size_t)(R * WS + R) * npix] = 0.0;
     const size_t n = (size_t)a.w * a.h;
@@ -308,7 +316,7 @@ __global__ void __launch_bounds__(128) weights_geodesic_kernel(const WeightArgs 
             }
         }
     }
-    for (int k = 0; k < WS * WS; ++k) c[(size_t)k * npix] = exp(-c[(size_t)k * npix] / 50.0);
+    for (int k = 0; k < WS * WS; ++k) out[(size_t)k * out_stride] = exp(-c[(size_t)k * npix] / 50.0);
 }
 
 // ---------------------------------------------------------------------------------------------
