@@ -91,27 +91,36 @@ class ClockSampler(threading.Thread):
             for line in self.proc.stdout:
                 if self.stop_flag:
                     break
-                self.rows.append([c.strip() for c in line.split(",")])
+                self.rows.append([time.time()] + [c.strip() for c in line.split(",")])
         except Exception:
             pass
 
-    def finish(self):
+    def finish(self, t_begin=None, t_end=None):
+        """Samples inside [t_begin, t_end] (the timed region); when the region is shorter than two
+        sampling periods, all samples since the sampler started (warm-up steps + timed region, the
+        same load) are used and `window` says so."""
         self.stop_flag = True
         if self.proc:
             self.proc.terminate()
+        rows, window = self.rows, "warmup+timed"
+        if t_begin is not None:
+            inside = [r for r in self.rows if t_begin <= r[0] <= t_end]
+            if len(inside) >= 2:
+                rows, window = inside, "timed"
         sm, mx, reasons = [], [], set()
-        for r in self.rows:
+        for r in rows:
             try:
-                sm.append(float(r[0]))
-                mx.append(float(r[1]))
+                sm.append(float(r[1]))
+                mx.append(float(r[2]))
             except (ValueError, IndexError):
                 continue
-            for name, val in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], r[3:7]):
+            for name, val in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], r[4:8]):
                 if val.lower().startswith("active"):
                     reasons.add(name)
         if not sm:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
-        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0, "window": window}
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm),
+                "window": window}
 
 
 def cpu_sample(wl, imgs, rows, steps=1, warmup=0, target_s=12.0):
@@ -226,22 +235,24 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    sampler = ClockSampler(local_rank)
+    sampler.start()
     for _ in range(args.warmup):
         step()
     barrier()
     launches0 = ctx.launch_count()
     ctx.set_profiling(True)
-    sampler = ClockSampler(local_rank)
-    sampler.start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    t_begin = time.time()
     ev0.record(stream)
     for _ in range(args.steps):
         step()
     ev1.record(stream)
     barrier()
+    t_end = time.time()
     ms = ev0.elapsed_time(ev1)
-    clocks = sampler.finish()
+    clocks = sampler.finish(t_begin, t_end)
     stages = ctx.stage_ms()
     if os.environ.get("SR_MATCH_STATS"):
         print("match stats:", ctx.match_stats(), file=sys.stderr)
@@ -348,7 +359,10 @@ def main():
         "dtype": "f64", "data": "synthetic",
         "config": {"workload": wl["desc"], "views_per_rank": len(my_views), "neighbours": n_nbr,
                    "l2": "inputs larger than L2 (tap volume %.1f GB per view streams through HBM)" % (n_nbr * h * w * D * 4 / 1e9),
-                   "partition": "reference views round-robin over ranks"},
+                   "partition": "reference views round-robin over ranks",
+                   "precision": ("every output (index, depth, winning cost) is decided in FP64; FP32 only screens labels "
+                                 "that provably cannot win, and labels between exactly projected anchors are interpolated "
+                                 "under a pixel-boundary guard (DESIGN.md section 3)")},
         "clocks": clocks,
         "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": int(V * h * w * 4),
                 "d2h_bytes_per_step": int(len(my_views) * h * w * 4), "seconds_per_step": e2e_s},
