@@ -47,3 +47,19 @@ def test_no_device_fails_loudly():
         pass
     with pytest.raises(capi.SrError):
         capi.Context(0)
+
+
+def test_product_never_references_the_oracle():
+    """oracle/ is test infrastructure: nothing of the shipped path (package, CUDA sources, C++
+    headers) may import, include, link or load it."""
+    offenders = []
+    for top in ("stereoreconstruction_b200", "include"):
+        for dirpath, _, files in os.walk(os.path.join(ROOT, top)):
+            for f in files:
+                if not f.endswith((".py", ".cu", ".cuh", ".h", ".hpp", ".cpp")):
+                    continue
+                text = open(os.path.join(dirpath, f), errors="ignore").read()
+                for pat in (r"^\s*(from|import)\s+oracle", r'#include\s*[<"].*oracle', r"liboracle", r"oracle_api", r"_ref/libref"):
+                    if re.search(pat, text, flags=re.M):
+                        offenders.append((os.path.join(dirpath, f), pat))
+    assert not offenders, offenders
