@@ -167,3 +167,97 @@ def test_row_band_equals_full_run():
     P.row_begin, P.row_end = 10, 20
     d, i, _, vol = sc.twoview_label(P, 0, 1, want_volume=True)
     assert (i[10:20] == full_i[10:20]).all() and vol.shape == (10, 48, 12)
+
+
+def _numpy_costs(img_l, img_r, mask_l, mask_r, W, x1, y1, x2, y2, R):
+    """An independent restatement (written from the reference text, numpy, no shared code with
+    oracle.cpp) of cost_ncc of MultiViewStereo (stereo/multiviewstereo.cpp:113-189), cost_ncc and
+    cost_sad of TwoViewStereo (stereo/twoviewstereo.cpp:909-977, 864-905).  W[row+R][col+R] are the
+    support weights of the reference pixel (pinned against the reference's own sources elsewhere)."""
+    h, w = img_l.shape[:2]
+
+    def gray(img, x, y):  # RGBA::toGray, util/vectorimage.hpp:60-62
+        r, g, b = (float(v) for v in img[y, x, :3])
+        return 0.11 * r + 0.59 * g + 0.3 * b
+
+    def pixel_ok(x, y):  # VectorImage::pixel
+        return 0 <= x < w and 0 <= y < h
+
+    def sample_ok(x, y):  # VectorImage::sample at integer coordinates
+        return x >= 0 and y >= 0 and x + 1 < w and y + 1 < h
+
+    def white(m, x, y):
+        return pixel_ok(x, y) and m[y, x] == 255
+
+    def taps(kind):
+        out = []
+        for row in range(-R, R + 1):
+            for col in range(-R, R + 1):
+                xl, yl, xr, yr = x1 + col, y1 + row, x2 + col, y2 + row
+                if kind == "mvs":
+                    if not (pixel_ok(xl, yl) and pixel_ok(xr, yr)):
+                        continue
+                else:
+                    if not (white(mask_l, xl, yl) and white(mask_r, xr, yr)):
+                        continue
+                    if not sample_ok(xl, yl):
+                        continue
+                    if not (sample_ok(xr, yr) if kind == "ncc2" else pixel_ok(xr, yr)):
+                        continue
+                wt = W[row + R, col + R]
+                if wt > 1e-10:
+                    out.append((wt, gray(img_l, xl, yl), gray(img_r, xr, yr)))
+        return out
+
+    def ncc(kind):
+        t = taps(kind)
+        tot = sum(wt for wt, _, _ in t)
+        if tot < 1e-10:
+            return None
+        mL = sum(wt * gl for wt, gl, _ in t) / tot
+        mR = sum(wt * gr for wt, _, gr in t) / tot
+        s1 = sum((wt * gl - mL) * (wt * gr - mR) for wt, gl, gr in t)
+        s2 = sum((wt * gl - mL) ** 2 for wt, gl, _ in t)
+        s3 = sum((wt * gr - mR) ** 2 for wt, _, gr in t)
+        return s1, s2, s3
+
+    r = ncc("mvs")
+    c_mvs = 0.0 if r is None or r[1] * r[2] < 1e-10 else r[0] / np.sqrt(r[1] * r[2])
+    r = ncc("ncc2")
+    if r is None:
+        c_two = 1000.0
+    else:
+        with np.errstate(invalid="ignore", divide="ignore"):
+            v = 255 * (1.0 - abs(r[0]) / np.sqrt(np.float64(r[1] * r[2])))
+        c_two = 120.0 if not (v < 120.0) else float(v)  # std::min(120.0, NaN) is 120
+    t = taps("sad")
+    tot = sum(wt for wt, _, _ in t)
+    c_sad = 1000.0 if (len(t) <= 4 or tot <= 1e-10) else sum(wt * min(120.0, abs(gl - gr)) for wt, gl, gr in t) / tot
+    return c_mvs, c_two, c_sad
+
+
+def test_costs_against_independent_numpy_restatement():
+    rng = np.random.RandomState(17)
+    h, w = 40, 56
+    base = rng.randint(0, 256, size=(h, w, 3))
+    imgs = []
+    for k in range(2):
+        im = np.empty((h, w, 4), np.uint8)
+        im[..., :3] = np.clip(base + rng.randint(-12, 13, size=base.shape) + 3 * k, 0, 255)
+        im[..., 3] = 255
+        imgs.append(im)
+    masks = [np.where(rng.rand(h, w) > 0.1, 255, 0).astype(np.uint8) for _ in range(2)]
+    cams = [T.make_camera(np.eye(3), np.eye(3), np.zeros(3)), T.make_camera(np.eye(3), np.eye(3), np.array([-1.0, 0, 0]))]
+    sc = O.Scene(cams, imgs, masks)
+    for R, kind in ((2, T.SR_WEIGHT_GEODESIC), (2, T.SR_WEIGHT_ADAPTIVE), (5, T.SR_WEIGHT_GEODESIC)):
+        pts = [(rng.randint(-1, w + 1), rng.randint(-1, h + 1), rng.randint(-3, w + 3), rng.randint(-3, h + 3)) for _ in range(120)]
+        pts += [(0, 0, 0, 0), (w - 1, h - 1, w - 1, h - 1), (w - 2, h - 2, 1, 1), (R, R, w - 1 - R, h - 1 - R)]
+        for (x1, y1, x2, y2) in pts:
+            if not (0 <= x1 < w and 0 <= y1 < h):
+                continue  # the reference never centres a window outside the reference image
+            W = sc.weights(0, kind, R, [x1], [y1])[0]
+            want = _numpy_costs(imgs[0], imgs[1], masks[0], masks[1], W, x1, y1, x2, y2, R)
+            for cost_kind, ref in ((T.SR_COST_NCC_MVS, want[0]), (T.SR_COST_NCC_TWOVIEW, want[1]), (T.SR_COST_SAD_TWOVIEW, want[2])):
+                P = T.default_params(cost_kind == T.SR_COST_NCC_MVS, 1.0, 2.0, 4, radius=R, weight_kind=kind, cost_kind=cost_kind)
+                got = sc.cost(P, 0, 1, x1, y1, x2, y2)
+                assert abs(got - ref) <= 1e-9 * max(1.0, abs(ref)), (R, kind, cost_kind, x1, y1, x2, y2, got, ref)
