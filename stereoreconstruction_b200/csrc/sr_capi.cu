@@ -710,26 +710,38 @@ int sr_run_view_curve(sr_ctx *ctx, int ref, const int32_t *nbrs, int nn) {
         else curve_build_kernel<false><<<gx, 128, 0, st>>>(ca);
     };
 
-    int band = r1 - r0;
-    {   // first guess of the band height from a typical curve length of 2 D candidates
-        const size_t per_row = (size_t)nn * (size_t)std::max(64, 2 * D) * w * 4;
-        band = (int)std::min<size_t>((size_t)band, std::max<size_t>(1, ctx->tap_budget / (per_row + per_row_w)));
-    }
+    int cap = 2 * D + 64;  // planes per neighbour: curves are rarely longer than the label count
+    int band = (int)std::min<size_t>((size_t)(r1 - r0), std::max<size_t>(1, ctx->tap_budget / ((size_t)nn * cap * w * 4 + per_row_w)));
     for (int b0 = r0; b0 < r1;) {
         if (ctx->cancel.load()) return fail(ctx, SR_ERR_CANCELLED, "cancelled");
         int rows = std::min(band, r1 - b0);
         int L = 1;
-        for (;;) {  // count pass: the longest curve of this band over all neighbours
+        for (int attempt = 0;; ++attempt) {
             const size_t plane = (size_t)rows * w;
-            rc = ensure_scratch(ctx, plane * 4 + 16);
+            const size_t need = (size_t)nn * cap * plane * 4, need_w = per_row_w * rows;
+            if (need_w > ctx->weights_cap) {
+                CK(cudaStreamSynchronize(st));
+                dfree(ctx->d_weights);
+                ctx->weights_cap = 0;
+                CK(cudaMalloc(&ctx->d_weights, need_w));
+                ctx->weights_cap = need_w;
+            }
+            if (need > ctx->taps_cap) {
+                CK(cudaStreamSynchronize(st));
+                dfree(ctx->d_taps);
+                ctx->taps_cap = 0;
+                CK(cudaMalloc(&ctx->d_taps, need));
+                ctx->taps_cap = need;
+            }
+            rc = ensure_scratch(ctx, 16);
             if (rc) return rc;
-            int32_t *d_counts = (int32_t *)ctx->d_scratch;
-            int32_t *d_max = d_counts + plane;
+            int32_t *d_max = (int32_t *)ctx->d_scratch;
             CK(cudaMemsetAsync(d_max, 0, 4, st));
             const unsigned gx = (unsigned)((plane + 127) / 128);
             for (int j = 0; j < nn; ++j) {
                 CurveArgs ca = curve_args(j, b0, rows);
-                ca.counts = d_counts;
+                ca.taps = ctx->d_taps + (size_t)j * cap * plane;
+                ca.capacity = cap;
                 ca.max_count = d_max;
                 launch_curve(ca, gx);
                 CKL();
@@ -738,34 +750,13 @@ int sr_run_view_curve(sr_ctx *ctx, int ref, const int32_t *nbrs, int nn) {
             CK(cudaMemcpyAsync(&hmax, d_max, 4, cudaMemcpyDeviceToHost, st));
             CK(cudaStreamSynchronize(st));
             L = std::max(1, (int)hmax);
-            const size_t need_all = (size_t)nn * L * plane * 4 + per_row_w * rows;
-            if (need_all <= ctx->tap_budget || rows == 1) break;
-            rows = (int)std::max<size_t>(1, ctx->tap_budget / ((size_t)nn * L * w * 4 + per_row_w));
+            if (L <= cap) break;
+            if (attempt >= 1) return fail(ctx, SR_ERR_STATE, "curve volume: inconsistent curve lengths");
+            cap = L;  // a longer curve than the volume holds: size the volume to it and fill again
+            rows = (int)std::min<size_t>((size_t)rows, std::max<size_t>(1, ctx->tap_budget / ((size_t)nn * cap * w * 4 + per_row_w)));
         }
         const size_t plane = (size_t)rows * w;
-        const size_t need = (size_t)nn * L * plane * 4, need_w = per_row_w * rows;
-        if (need_w > ctx->weights_cap) {
-            CK(cudaStreamSynchronize(st));
-            dfree(ctx->d_weights);
-            ctx->weights_cap = 0;
-            CK(cudaMalloc(&ctx->d_weights, need_w));
-            ctx->weights_cap = need_w;
-        }
-        if (need > ctx->taps_cap) {
-            CK(cudaStreamSynchronize(st));
-            dfree(ctx->d_taps);
-            ctx->taps_cap = 0;
-            CK(cudaMalloc(&ctx->d_taps, need));
-            ctx->taps_cap = need;
-        }
         const unsigned gx = (unsigned)((plane + 127) / 128);
-        for (int j = 0; j < nn; ++j) {  // fill pass
-            CurveArgs ca = curve_args(j, b0, rows);
-            ca.taps = ctx->d_taps + (size_t)j * L * plane;
-            ca.capacity = L;
-            launch_curve(ca, gx);
-            CKL();
-        }
         {
             WeightArgs wa;
             memset(&wa, 0, sizeof(wa));
@@ -811,6 +802,7 @@ int sr_run_view_curve(sr_ctx *ctx, int ref, const int32_t *nbrs, int nn) {
         ma.row0 = b0;
         ma.rows = rows;
         ma.D = L;
+        ma.tap_planes = cap;
         ma.num_nbrs = nn;
         ma.select_kind = P.select_kind;
         ma.depth_up = 1;

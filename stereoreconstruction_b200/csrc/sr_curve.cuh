@@ -12,8 +12,9 @@
 // plane per candidate ordinal: taps[ordinal][rows][w], TAP_NONE after the end of a pixel's curve.
 // The match kernels then stream it exactly like a label volume; what differs downstream is only
 // where the depth of a candidate comes from (closest approach of the two viewing rays, S2/S3).
-// Curve lengths vary per pixel: the host runs the kernel once with capacity 0 to get the maximum
-// length (count pass), sizes the volume, and runs it again to fill.
+// Curve lengths vary per pixel: the host fills a volume of 2 D + 64 planes (curves are rarely longer
+// than the label count), reads back the longest curve, and only if that exceeds the capacity
+// sizes the volume to it and runs the kernel again.
 #pragma once
 #include "sr_build_refr.cuh"
 
@@ -29,9 +30,8 @@ struct CurveArgs {
     const double *depth_table;   // [D]
     const uint8_t *ref_mask;
     const uint8_t *nbr_mask;     // never null here (a null mask is a plane of 255)
-    int32_t *taps;               // [capacity][rows][w] for this neighbour, or null (count pass)
-    int32_t *counts;             // [rows][w]: curve length of each pixel (count pass output)
-    int32_t *max_count;          // device scalar, atomicMax over all pixels
+    int32_t *taps;               // [capacity][rows][w] for this neighbour (null: only measure the curve lengths)
+    int32_t *max_count;          // device scalar, atomicMax of the curve lengths over all pixels
     int w, h, row0, rows, D, capacity;
     int mvs;                     // 1: clipped iterator + consecutive-duplicate removal; 0: two-view flavour
 };
@@ -194,12 +194,9 @@ __global__ void __launch_bounds__(128) curve_build_kernel(const __grid_constant_
             }
         }
     }
-    if (a.taps) {
+    if (a.taps)
         for (int l = min(count, a.capacity); l < a.capacity; ++l) a.taps[(size_t)l * plane + pid] = TAP_NONE;
-    } else {
-        a.counts[pid] = count;
-        if (count > 0) atomicMax(a.max_count, count);
-    }
+    if (count > 0) atomicMax(a.max_count, count);  // the longest curve: > capacity means "run again, larger"
 }
 
 // Depth hypothesis of a curve candidate (multiviewstereo.cpp:584-593, twoviewstereo.cpp:286-299):

@@ -337,6 +337,7 @@ struct MatchArgs {
     double *out_peaks;              // [9][2][h*w] or null: the K = 9 largest (ncc, depth) pairs per pixel,
                                     // ascending (CostFunction::peakPairs, multiviewstereo.cpp:479-482,600-602)
     int w, h, row0, rows, D, num_nbrs;
+    int tap_planes;                 // planes per neighbour in `taps` when it is larger than D (curve mode), else 0
     int select_kind;
     int depth_up;                   // depth_table is increasing in the label (max_depth > min_depth)
     // curve mode (sr_curve.cuh): the "labels" are the candidates of the rasterised epipolar curve and
@@ -644,7 +645,7 @@ __global__ void __launch_bounds__(128, (R <= 2) ? SR_MATCH_MINBLOCKS : 2) match_
     auto issue_chunk = [&](int c) {
         if (c < total_chunks) {
             const int j = c / nchunks, d0 = (c % nchunks) * TAP_CHUNK;
-            const int32_t *src = a.taps + ((size_t)j * D + d0) * npix + pid;
+            const int32_t *src = a.taps + ((size_t)j * (a.tap_planes ? a.tap_planes : D) + d0) * npix + pid;
             const int nl = min(TAP_CHUNK, D - d0);
             for (int l = 0; l < nl; ++l) cp_async4(&tap_ring[c & 1][l][tid], src + (size_t)l * npix, pol);
         }

@@ -360,7 +360,7 @@ __global__ void __launch_bounds__(SCREEN_BLOCK, ((R <= 2) ? SR_SCREEN_MINBLOCKS 
     auto issue_chunk = [&](int c) {
         if (c < total_chunks && alive) {
             const int j = c / nchunks, d0 = (c % nchunks) * TAP_CHUNK;
-            const int32_t *src = a.taps + ((size_t)j * D + d0) * npix + pid;
+            const int32_t *src = a.taps + ((size_t)j * (a.tap_planes ? a.tap_planes : D) + d0) * npix + pid;
             const int nl = min(TAP_CHUNK, D - d0);
             for (int l = 0; l < nl; ++l) cp_async4(&tap_ring[c & 1][l][tid], src + (size_t)l * npix, pol);
         }
