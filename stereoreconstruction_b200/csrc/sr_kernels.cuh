@@ -447,10 +447,6 @@ __device__ __forceinline__ void cp_async4(void *smem_dst, const void *gmem_src, 
     asm volatile("cp.async.ca.shared.global.L2::cache_hint [%0], [%1], 4, %2;" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)),
                  "l"(gmem_src), "l"(pol));
 }
-__device__ __forceinline__ void prefetch_l1(const void *p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
-#ifndef SR_MATCH_PREFETCH
-#define SR_MATCH_PREFETCH 0  // labels of look-ahead for an explicit L1 window prefetch (measured: no gain, off)
-#endif
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;"); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() {
@@ -664,21 +660,6 @@ __global__ void __launch_bounds__(128, (R <= 2) ? SR_MATCH_MINBLOCKS : 2) match_
 #pragma unroll 1
         for (int l = 0; l < nl; ++l) {
             const int32_t tap = tap_ring[c & 1][l][tid];
-            if (SR_MATCH_PREFETCH > 0 && l + SR_MATCH_PREFETCH < nl) {
-                // the window of a label a few steps ahead: pull its rows into L1 now, so that the
-                // L2/HBM latency of a window entering a new cache line is off the critical path
-                const int32_t tp = tap_ring[c & 1][l + SR_MATCH_PREFETCH][tid];
-                const int px = (int)(short)(tp & 0xffff), py = (int)(short)((uint32_t)tp >> 16);
-                if (tp != TAP_NONE && px >= R && py >= R && px < w - R && py < h - R) {
-                    const double *pb = gR + ((size_t)(py - R) * w + (px - R));
-                    if (G == 1) {
-#pragma unroll
-                        for (int row = 0; row < WS; ++row) prefetch_l1(pb + row * w);
-                    } else {
-                        for (int row = sub; row < WS; row += G) prefetch_l1(pb + row * w);
-                    }
-                }
-            }
             double cost = qnan();
             if (tap != TAP_NONE) {
                 const int tx = (int)(short)(tap & 0xffff), ty = (int)(short)((uint32_t)tap >> 16);

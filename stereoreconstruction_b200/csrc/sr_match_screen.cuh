@@ -109,9 +109,6 @@ __device__ __noinline__ double verify_cost_mvs(const MatchArgs &a, const double 
                                 // other warp's slot
 #endif
 constexpr int SCREEN_BLOCK = SR_SCREEN_BLOCK;
-#ifndef SR_SCREEN_PREFETCH
-#define SR_SCREEN_PREFETCH 0    // labels of look-ahead for an L1 prefetch of the window's sectors
-#endif
 
 // PITCH: compile-time row pitch of the FP32 gray planes (0: run-time a.pitch_f).
 template <int R, int G, bool STATS, int PITCH>
@@ -381,27 +378,6 @@ __global__ void __launch_bounds__(SCREEN_BLOCK, ((R <= 2) ? SR_SCREEN_MINBLOCKS 
 #pragma unroll 1
         for (int l = 0; l < nl; ++l) {
             const int32_t tap = alive ? tap_ring[c & 1][l][tid] : TAP_NONE;
-            if (SR_SCREEN_PREFETCH > 0 && alive && l + SR_SCREEN_PREFETCH < nl) {
-                // the window slides along the epipolar curve: its leading sectors come from L2;
-                // pull them into L1 a few labels early so that no LDG of the label loop misses
-                const int32_t tp = tap_ring[c & 1][l + SR_SCREEN_PREFETCH][tid];
-                const int px = (int)(short)(tp & 0xffff), py = (int)(short)((uint32_t)tp >> 16);
-                if (tp != TAP_NONE && tp != tap && px >= R && py >= R && px < w - R && py < h - R) {
-                    const float *pb = gRf + ((size_t)(py - R) * fp + px);
-                    if (G == 1) {
-#pragma unroll
-                        for (int row = 0; row < WS; ++row) {
-                            prefetch_l1(pb + row * fp - R);
-                            prefetch_l1(pb + row * fp + R);
-                        }
-                    } else {
-                        for (int row = sub; row < WS; row += G) {
-                            prefetch_l1(pb + row * fp - R);
-                            prefetch_l1(pb + row * fp + R);
-                        }
-                    }
-                }
-            }
             if (tap != TAP_NONE) {
                 float c32, eps;
                 if (tap == prevTap) {
