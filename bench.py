@@ -173,6 +173,8 @@ def main():
     ap.add_argument("--cpu-rows", type=int, default=0, help="rows of the CPU sample (0 = auto)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--views", type=int, default=0, help="only the first N reference views (profiling aid; 0 = all)")
+    ap.add_argument("--partition", default="views", choices=["views", "rows"],
+                    help="multi-GPU: deal reference views to ranks (default) or give every rank a row band of every view")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -223,7 +225,13 @@ def main():
     ctx.set_views(cams, imgs_p, None)
     nbrs = neighbours_for(wl)
     ref_views = list(range(V if args.views <= 0 else min(V, args.views)))
-    my_views = [v for v in sharding.partition_views(V, world)[rank] if v in ref_views]
+    if args.partition == "rows" and world > 1:  # every rank: rows [b0, b1) of every reference view
+        my_views = list(ref_views)
+        b0, b1 = sharding.row_bands(h, world)[rank]
+        wl["params"].row_begin, wl["params"].row_end = b0, b1
+        ctx.set_params(wl["params"])
+    else:
+        my_views = [v for v in sharding.partition_views(V, world)[rank] if v in ref_views]
     units_total = len(ref_views) * h * w * D
 
     def step():
@@ -359,7 +367,8 @@ def main():
         "dtype": "f64", "data": "synthetic",
         "config": {"workload": wl["desc"], "views_per_rank": len(my_views), "neighbours": n_nbr,
                    "l2": "inputs larger than L2 (tap volume %.1f GB per view streams through HBM)" % (n_nbr * h * w * D * 4 / 1e9),
-                   "partition": "reference views round-robin over ranks",
+                   "partition": ("row bands of every reference view" if (args.partition == "rows" and world > 1)
+                                 else "reference views round-robin over ranks"),
                    "precision": ("every output (index, depth, winning cost) is decided in FP64; FP32 only screens labels "
                                  "that provably cannot win, and labels between exactly projected anchors are interpolated "
                                  "under a pixel-boundary guard (DESIGN.md section 3)")},
