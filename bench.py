@@ -342,7 +342,7 @@ def main():
     }
 
     cpu = None
-    if not args.no_cpu:
+    if not args.no_cpu and world == 1:  # the CPU baseline leg runs on rank 0 at N = 1 only
         val, t, cores, sample = cpu_sample(wl, imgs, cpu_rows)
         cpu = {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample, "seconds": t}
         # The oracle's outputs for that band are the checker of the GPU's at the benchmark's full size.
