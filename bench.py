@@ -277,8 +277,12 @@ def main():
     # end-to-end through the C ABI with host buffers: H2D of all images + run + D2H of the index maps
     idx_host = [torch.empty((h, w), dtype=torch.int32).pin_memory().numpy() for _ in my_views]
 
+    # a rank uploads the views it computes and their neighbours; the others stay camera-only
+    needed = set(my_views) | {n for v in my_views for n in nbrs[v]}
+    imgs_e2e = [imgs_p[v] if v in needed else None for v in range(V)]
+
     def e2e_step():
-        ctx.set_views(cams, imgs_p, None)
+        ctx.set_views(cams, imgs_e2e, None)
         ctx.set_params(wl["params"])
         for v in my_views:
             ctx.run_view(v, nbrs[v])
@@ -360,7 +364,6 @@ def main():
                 "max_rel_cost_diff": float(rel.max()) if rel.size else None, "labelled_fraction": float(lab.mean()),
             }
 
-    h2d = V * h * w * 4 * (len(my_views) / V if world > 1 else 1)
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
@@ -373,7 +376,7 @@ def main():
                                  "that provably cannot win, and labels between exactly projected anchors are interpolated "
                                  "under a pixel-boundary guard (DESIGN.md section 3)")},
         "clocks": clocks,
-        "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": int(V * h * w * 4),
+        "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": int(len(needed) * h * w * 4),
                 "d2h_bytes_per_step": int(len(my_views) * h * w * 4), "seconds_per_step": e2e_s},
         "gpu_launches": launches,
         "roofline": roofline,

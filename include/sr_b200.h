@@ -140,7 +140,9 @@ int sr_get_build_stats(sr_ctx *ctx, uint64_t *out4);
  * (stereo/multiviewstereo.cpp:193-247): V views of w*h RGBA8 (byte order R,G,B,A,
  * the channels VectorImage::fromQImage extracts, util/vectorimage.cpp:57-64) and
  * one mask byte per pixel (255 == WHITE, anything else is not).  mask8[i] may be
- * NULL (all WHITE).  Copies to the device (async on the context stream from pinned
+ * NULL (all WHITE).  rgba8[i] may be NULL for a view this context only needs the
+ * camera of (multi-GPU: a view another rank computes and that is no neighbour of this
+ * rank's views); using such a view as reference or neighbour is an error.  Copies to the device (async on the context stream from pinned
  * staging) and runs the per-view preparation kernels. */
 int sr_set_views(sr_ctx *ctx, int num_views, const sr_camera *cams,
                  const uint8_t *const *rgba8, const uint8_t *const *mask8, int w, int h);

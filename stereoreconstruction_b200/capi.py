@@ -141,12 +141,12 @@ class Context:
 
     def set_views(self, cams, images, masks=None):
         V = len(cams)
-        h, w = images[0].shape[:2]
-        imgs = [np.ascontiguousarray(im, dtype=np.uint8) for im in images]
+        h, w = next(im for im in images if im is not None).shape[:2]
+        imgs = [None if im is None else np.ascontiguousarray(im, dtype=np.uint8) for im in images]
         for im in imgs:
-            assert im.shape == (h, w, 4)
+            assert im is None or im.shape == (h, w, 4)
         arr = (SrCamera * V)(*cams)
-        ip = (C.c_void_p * V)(*[im.ctypes.data for im in imgs])
+        ip = (C.c_void_p * V)(*[None if im is None else im.ctypes.data for im in imgs])  # None: camera only
         mp = None
         ms = None
         if masks is not None:

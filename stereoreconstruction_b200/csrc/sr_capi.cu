@@ -27,6 +27,7 @@ struct ViewDev {
     uint8_t *mask = nullptr;
     double *gray_pix = nullptr, *gray_two = nullptr, *gray_msk = nullptr, *edges = nullptr;
     float *gray_pix_f = nullptr;
+    bool have_image = false; // sr_set_views received pixels for this view
     bool all_white = false;  // no mask was passed for this view: every pixel is WHITE
     double *rays = nullptr;  // [6][h][w] Camera::unproject of every pixel centre (curve mode), lazily
     double rays_scale = 0.0; // image_scale the table was computed for (0: stale)
@@ -331,9 +332,10 @@ int sr_set_views(sr_ctx *ctx, int V, const sr_camera *cams, const uint8_t *const
     CK(cudaMemcpyAsync(ctx->d_cams, ctx->cams.data(), sizeof(sr_camera) * V, cudaMemcpyHostToDevice, ctx->stream));
     for (int i = 0; i < V; ++i) {
         ViewDev &v = ctx->views[i];
-        if (!rgba8[i]) return fail(ctx, SR_ERR_INVALID, "sr_set_views: null image");
-        CK(cudaMemcpyAsync(v.rgba, rgba8[i], n * 4, cudaMemcpyHostToDevice, ctx->stream));
         v.rays_scale = 0.0;  // cameras may have changed
+        v.have_image = rgba8[i] != nullptr;
+        if (!v.have_image) continue;  // a view this context only knows the camera of (another rank computes it)
+        CK(cudaMemcpyAsync(v.rgba, rgba8[i], n * 4, cudaMemcpyHostToDevice, ctx->stream));
         v.all_white = !(mask8 && mask8[i]);
         if (!v.all_white) CK(cudaMemcpyAsync(v.mask, mask8[i], n, cudaMemcpyHostToDevice, ctx->stream));
         else CK(cudaMemsetAsync(v.mask, 255, n, ctx->stream));
@@ -380,6 +382,9 @@ int sr_run_view(sr_ctx *ctx, int ref, const int32_t *nbrs, int nn) {
     if (!nbrs || nn <= 0 || nn > SR_MAX_NBRS) return fail(ctx, SR_ERR_INVALID, "1..8 neighbour views required");
     for (int j = 0; j < nn; ++j)
         if (nbrs[j] < 0 || nbrs[j] >= ctx->V || nbrs[j] == ref) return fail(ctx, SR_ERR_INVALID, "bad neighbour index");
+    if (!ctx->views[ref].have_image) return fail(ctx, SR_ERR_STATE, "the reference view was given no image in sr_set_views");
+    for (int j = 0; j < nn; ++j)
+        if (!ctx->views[nbrs[j]].have_image) return fail(ctx, SR_ERR_STATE, "a neighbour view was given no image in sr_set_views");
     const sr_params &P = ctx->params;
     if (P.select_kind == SR_SELECT_TWOVIEW && nn != 1)
         return fail(ctx, SR_ERR_INVALID, "two-view selection takes exactly one neighbour");
@@ -648,6 +653,9 @@ int sr_run_view_curve(sr_ctx *ctx, int ref, const int32_t *nbrs, int nn) {
     if (!nbrs || nn <= 0 || nn > SR_MAX_NBRS) return fail(ctx, SR_ERR_INVALID, "1..8 neighbour views required");
     for (int j = 0; j < nn; ++j)
         if (nbrs[j] < 0 || nbrs[j] >= ctx->V || nbrs[j] == ref) return fail(ctx, SR_ERR_INVALID, "bad neighbour index");
+    if (!ctx->views[ref].have_image) return fail(ctx, SR_ERR_STATE, "the reference view was given no image in sr_set_views");
+    for (int j = 0; j < nn; ++j)
+        if (!ctx->views[nbrs[j]].have_image) return fail(ctx, SR_ERR_STATE, "a neighbour view was given no image in sr_set_views");
     const sr_params &P = ctx->params;
     const bool mvs = (P.select_kind == SR_SELECT_MVS);
     if (!mvs && nn != 1) return fail(ctx, SR_ERR_INVALID, "two-view selection takes exactly one neighbour");

@@ -142,3 +142,21 @@ def test_bad_arguments_fail_loudly(ctx):
     with pytest.raises(capi.SrError):
         ctx.set_params(T.default_params(False, 420.0, 580.0, 8))
         ctx.run_view(0, [1, 2])  # two-view selection takes exactly one neighbour
+
+
+def test_camera_only_views(ctx):
+    """rgba8[i] == NULL: a view this context only needs the camera of (another rank computes it)."""
+    cams, imgs, ms, _ = refractive_arc_scene(V=5, w=64, h=40, masks=False)
+    P = T.default_params(True, 420.0, 580.0, 16)
+    ctx.set_views(cams, imgs, None)
+    ctx.set_params(P)
+    ctx.run_view(1, [0, 2])
+    want = ctx.depth_index(1).copy()
+    ctx.set_views(cams, [imgs[0], imgs[1], imgs[2], None, None], None)
+    ctx.set_params(P)
+    ctx.run_view(1, [0, 2])
+    assert (ctx.depth_index(1) == want).all()
+    with pytest.raises(capi.SrError):
+        ctx.run_view(1, [0, 3])
+    with pytest.raises(capi.SrError):
+        ctx.run_view(4, [0, 2])
