@@ -25,8 +25,9 @@
 //                  FP64 cost; the screening precision never reaches the output.
 //
 // Consecutive labels whose projections truncate to the same integer tap have the same cost by
-// construction; the screening pass re-uses the previous value and the queue keeps one entry per
-// distinct tap (carrying the label the tie-break would pick).
+// construction; the queue keeps one entry per distinct tap (carrying the label the tie-break would
+// pick).  The screen itself re-evaluates them: skipping only pays when all 32 lanes of a warp
+// repeat at once, and the bookkeeping cost three live registers and ~5 % of the kernel.
 #pragma once
 #include <type_traits>
 #include "sr_kernels.cuh"
@@ -365,8 +366,6 @@ __global__ void __launch_bounds__(SCREEN_BLOCK, ((R <= 2) ? SR_SCREEN_MINBLOCKS 
     };
     issue_chunk(0);
 
-    int prevTap = TAP_NONE;
-    float prevC = 0.0f, prevEps = 0.0f;
 #pragma unroll 1
     for (int c = 0; c < total_chunks; ++c) {
         issue_chunk(c + 1);
@@ -374,26 +373,20 @@ __global__ void __launch_bounds__(SCREEN_BLOCK, ((R <= 2) ? SR_SCREEN_MINBLOCKS 
         const int j = c / nchunks, d0 = (c % nchunks) * TAP_CHUNK;
         const int nl = min(TAP_CHUNK, D - d0);
         const float *__restrict__ gRf = a.grayRf[j];
-        if (d0 == 0) prevTap = TAP_NONE;  // a new neighbour view starts
 #pragma unroll 1
         for (int l = 0; l < nl; ++l) {
             const int32_t tap = alive ? tap_ring[c & 1][l][tid] : TAP_NONE;
             if (tap != TAP_NONE) {
-                float c32, eps;
-                if (tap == prevTap) {
-                    c32 = prevC;  // same integer tap as the previous label: same cost
-                    eps = prevEps;
-                } else {
+                // (Consecutive labels often share a tap; re-using the previous value only pays when all
+                // 32 lanes repeat at once, which is rare, and costs three live registers: not done.
+                // The queue below still keeps one entry per distinct tap.)
+                float c32 = SCREEN_FORCE, eps = 0.0f;
+                {
                     const int tx = (int)(short)(tap & 0xffff), ty = (int)(short)((uint32_t)tap >> 16);
-                    c32 = SCREEN_FORCE;
-                    eps = 0.0f;
                     if (!all_slow && tx >= R && ty >= R && tx < w - R && ty < h - R) {
                         const float *base = gRf + ((size_t)ty * fp + tx);
                         c32 = has_inactive ? screen_one(base, eps, std::true_type{}) : screen_one(base, eps, std::false_type{});
                     }
-                    prevTap = tap;
-                    prevC = c32;
-                    prevEps = eps;
                     if (STATS) {
                         if (c32 == SCREEN_FORCE) ++n_forced;
                         else ++n_screened;
