@@ -301,6 +301,11 @@ __global__ void __launch_bounds__(SCREEN_BLOCK, ((R <= 2) ? SR_SCREEN_MINBLOCKS 
 
     auto flush = [&]() {
         const int nmax = __reduce_max_sync(0xffffffffu, qn);
+        // the pixel's coordinates are re-derived here (rare path) instead of living in registers
+        // across the label loop
+        const int pid = min((int)(blockIdx.x * PIX_PER_BLOCK + threadIdx.x / G), a.rows * a.w - 1);
+        const int x = pid % a.w, y = a.row0 + pid / a.w;
+        const size_t pix = (size_t)y * a.w + x;
         double bestC = px_bestC[tid];
         int bestIdx = px_bestIdx[tid];
         const double meanL_x = px_meanL[tid], totW_x = px_totW[tid], s2_x = px_s2[tid];
@@ -352,30 +357,39 @@ __global__ void __launch_bounds__(SCREEN_BLOCK, ((R <= 2) ? SR_SCREEN_MINBLOCKS 
 
     // ---- label sweep -------------------------------------------------------------------------
     const int D = a.D;
-    const int nchunks = (D + TAP_CHUNK - 1) / TAP_CHUNK;
-    const int total_chunks = nchunks * a.num_nbrs;
     const uint64_t pol = l2_evict_first_policy();
-    auto issue_chunk = [&](int c) {
-        if (c < total_chunks && alive) {
-            const int j = c / nchunks, d0 = (c % nchunks) * TAP_CHUNK;
-            const int32_t *src = a.taps + ((size_t)j * (a.tap_planes ? a.tap_planes : D) + d0) * npix + pid;
-            const int nl = min(TAP_CHUNK, D - d0);
-            for (int l = 0; l < nl; ++l) cp_async4(&tap_ring[c & 1][l][tid], src + (size_t)l * npix, pol);
+    // The tap stream: chunk k (TAP_CHUNK labels of one neighbour) lands in ring buffer k & 1 while
+    // chunk k-1 is processed.  (jn, dn) is the next chunk to request.
+    int jn = 0, dn = 0, bufn = 0;
+    auto issue_next = [&]() {
+        if (jn < a.num_nbrs && alive) {
+            const int32_t *src = a.taps + ((size_t)jn * (a.tap_planes ? a.tap_planes : D) + dn) * npix + pid;
+            const int nl = min(TAP_CHUNK, D - dn);
+            for (int l = 0; l < nl; ++l) cp_async4(&tap_ring[bufn][l][tid], src + (size_t)l * npix, pol);
         }
         cp_async_commit();
+        bufn ^= 1;
+        dn += TAP_CHUNK;
+        if (dn >= D) {
+            dn = 0;
+            ++jn;
+        }
     };
-    issue_chunk(0);
+    issue_next();
 
+    int buf = 0;
 #pragma unroll 1
-    for (int c = 0; c < total_chunks; ++c) {
-        issue_chunk(c + 1);
+    for (int j = 0; j < a.num_nbrs; ++j) {
+      const float *__restrict__ gRf = a.grayRf[j];
+#pragma unroll 1
+      for (int d0 = 0; d0 < D; d0 += TAP_CHUNK, buf ^= 1) {
+        issue_next();
         cp_async_wait<1>();
-        const int j = c / nchunks, d0 = (c % nchunks) * TAP_CHUNK;
         const int nl = min(TAP_CHUNK, D - d0);
-        const float *__restrict__ gRf = a.grayRf[j];
+        const int32_t *ring = &tap_ring[buf][0][tid];
 #pragma unroll 1
         for (int l = 0; l < nl; ++l) {
-            const int32_t tap = alive ? tap_ring[c & 1][l][tid] : TAP_NONE;
+            const int32_t tap = alive ? ring[l * SCREEN_BLOCK] : TAP_NONE;
             if (tap != TAP_NONE) {
                 // (Consecutive labels often share a tap; re-using the previous value only pays when all
                 // 32 lanes repeat at once, which is rare, and costs three live registers: not done.
@@ -428,6 +442,7 @@ __global__ void __launch_bounds__(SCREEN_BLOCK, ((R <= 2) ? SR_SCREEN_MINBLOCKS 
             }
             if (__any_sync(0xffffffffu, qn == SCREEN_QCAP)) flush();
         }
+      }
     }
     cp_async_wait<0>();
     flush();
