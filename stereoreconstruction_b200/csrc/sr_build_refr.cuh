@@ -163,6 +163,10 @@ struct RefrProjector {
 #endif
 constexpr int BUILD_STRIDE = SR_BUILD_STRIDE;
 
+// MVS: the multi-view tap rule (tap inside the image and WHITE in the neighbour's mask);
+// HAS_MASK: the neighbour has a mask plane (a.nbr_mask != null).  Compile-time so that the other
+// variant's clamps, mask address arithmetic and loads do not occupy (predicated-off) issue slots.
+template <bool MVS, bool HAS_MASK>
 __global__ void __launch_bounds__(128) build_refr_kernel(const __grid_constant__ BuildRefrArgs a) {
     const int pid = blockIdx.x * blockDim.x + threadIdx.x;
     if (pid >= a.rows * a.w) return;
@@ -308,9 +312,9 @@ __global__ void __launch_bounds__(128) build_refr_kernel(const __grid_constant__
         for (int s = 0; s < S; ++s) {
             keep[s] = ok[s];
             mk[s] = 255;
-            if (a.mvs) {  // multiviewstereo.cpp:787: only WHITE neighbour-mask pixels are candidates
+            if (MVS) {  // multiviewstereo.cpp:787: only WHITE neighbour-mask pixels are candidates
                 keep[s] = keep[s] && (unsigned)tx[s] < (unsigned)a.w && (unsigned)ty[s] < (unsigned)a.h;
-                if (keep[s] && a.nbr_mask) mk[s] = a.nbr_mask[(size_t)ty[s] * a.w + tx[s]];
+                if (HAS_MASK && keep[s]) mk[s] = a.nbr_mask[(size_t)ty[s] * a.w + tx[s]];
             }
         }
 #pragma unroll
@@ -318,9 +322,9 @@ __global__ void __launch_bounds__(128) build_refr_kernel(const __grid_constant__
             const int d = db + s;
             if (d >= d1) break;
             int32_t tap = TAP_NONE;
-            if (keep[s] && mk[s] == 255) {
+            if (keep[s] && (!HAS_MASK || mk[s] == 255)) {
                 int cx = tx[s], cy = ty[s];
-                if (!a.mvs) {  // (with the MVS rule the tap is inside the image already)
+                if (!MVS) {  // (with the MVS rule the tap is inside the image already)
                     cx = max(-TAP_CLAMP, min(TAP_CLAMP, cx));
                     cy = max(-TAP_CLAMP, min(TAP_CLAMP, cy));
                 }

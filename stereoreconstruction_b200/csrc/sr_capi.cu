@@ -498,7 +498,10 @@ int sr_run_view(sr_ctx *ctx, int ref, const int32_t *nbrs, int nn) {
                 ra.d_chunk = std::max(BUILD_STRIDE, ctx->refr_chunk - ctx->refr_chunk % BUILD_STRIDE);
                 ra.mvs = mvs;
                 ra.check = ctx->d_stats ? ctx->d_stats + 8 : nullptr;
-                build_refr_kernel<<<dim3(gx, (D + ra.d_chunk - 1) / ra.d_chunk), 128, 0, st>>>(ra);
+                const dim3 grid(gx, (D + ra.d_chunk - 1) / ra.d_chunk);
+                if (!mvs) build_refr_kernel<false, false><<<grid, 128, 0, st>>>(ra);
+                else if (ra.nbr_mask) build_refr_kernel<true, true><<<grid, 128, 0, st>>>(ra);
+                else build_refr_kernel<true, false><<<grid, 128, 0, st>>>(ra);
                 CKL();
                 continue;
             }
