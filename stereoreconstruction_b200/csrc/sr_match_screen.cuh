@@ -286,7 +286,10 @@ __global__ void __launch_bounds__(SCREEN_BLOCK, ((R <= 2) ? SR_SCREEN_MINBLOCKS 
         // ill-conditioned or non-finite neighbour window: FP64 decides
         if (!(s3 >= (float)WN) || !(s3 < 1e30f)) return SCREEN_FORCE;
         eps = (s3 >= 100.0f * WN) ? eps_pix : SCREEN_EPS_LOOSE;
-        return s1 * rsqrtf(s2f * s3);
+        // s2f*s3 >= WN^2 here: the flush-to-zero rsqrt needs no denormal fix-up (3 issue slots less)
+        float rs;
+        asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(rs) : "f"(s2f * s3));
+        return s1 * rs;
     };
 
     // ---- exact state (FP64) and candidate queue -----------------------------------------------
