@@ -188,10 +188,12 @@ int sr_get_best_cost(sr_ctx *ctx, int view, double *out);
 int sr_get_cost_volume(sr_ctx *ctx, float *out, size_t out_elems);
 /* Replaces depth upload for cross-check under view sharding (each rank receives
  * the other ranks' depth maps before sr_cross_check). */
-/* The K = 9 largest (ncc, depth) pairs of every pixel of the last sr_run_view with
- * keep_cost_volume & 2, ascending, padded with (0, -1): CostFunction::peakPairs, the input of
- * the reference's MRF stage (stereo/multiviewstereo.cpp:479-482,562,589-602).  out = h*w*9*2
- * doubles, [pixel][k][ncc, depth].  Label mode; evaluates every label in FP64. */
+/* The K = 9 largest (ncc, depth) pairs of every pixel of the last sr_run_view or
+ * sr_run_view_curve with keep_cost_volume & 2, ascending, padded with (0, -1):
+ * CostFunction::peakPairs, the input of the reference's MRF stage
+ * (stereo/multiviewstereo.cpp:479-482,562,583-602).  out = h*w*9*2 doubles,
+ * [pixel][k][ncc, depth]; in curve mode depth is the z of the rays' closest approach (:583-588).
+ * Evaluates every candidate in FP64. */
 int sr_get_peaks(sr_ctx *ctx, int view, double *out);
 int sr_set_depth(sr_ctx *ctx, int view, const double *depth);
 /* colorFromDepth + depthMap(view): stereo/multiviewstereo.cpp:257-286 (mvs != 0,

@@ -97,6 +97,13 @@ public:
     //! the reference's live formulation (multiviewstereo.cpp:574-602); false (default): the
     //! depth-label cost volume + WTA of the same rule (SURVEY §8a S4 applied to S2).
     void setCurveMode(bool on) { curveMode_ = on; }
+    //! true: also keep, per pixel, the K = 9 largest (ncc, depth) candidates of the search — the
+    //! reference's CostFunction::peakPairs (multiviewstereo.cpp:479-482,589-602), the input of its
+    //! MRF stage; read with peakPairs() after run().  Works in label and in curve mode.
+    void setKeepPeaks(bool on) { params_.keep_cost_volume = on ? (params_.keep_cost_volume | 2) : (params_.keep_cost_volume & ~2); }
+    //! [h][w][9][2] (ncc, depth), ascending, padded with (0, -1); the last pair is the pixel's result
+    //! before the cross-check.  Empty unless setKeepPeaks(true).
+    const std::vector<double> &peakPairs(size_t viewIndex) const { return peakPairs_[viewIndex]; }
     size_t numViews() const { return views.size(); }
     const std::vector<double> &depths(size_t viewIndex) const { return computedDepths[viewIndex]; }
     const std::vector<int32_t> &indices(size_t viewIndex) const { return depthIndices[viewIndex]; }
@@ -157,6 +164,10 @@ protected:
             if (cnt[v] > 0) {
                 if (curveMode_) s.check(sr_run_view_curve(s.get(), v, &nb[(size_t)v * maxN], cnt[v]), "sr_run_view_curve");
                 else s.check(sr_run_view(s.get(), v, &nb[(size_t)v * maxN], cnt[v]), "sr_run_view");
+                if (params_.keep_cost_volume & 2) {  // the library keeps the lists of the last view only
+                    peakPairs_[v].resize((size_t)w * h * 18);
+                    s.check(sr_get_peaks(s.get(), v, peakPairs_[v].data()), "sr_get_peaks");
+                }
             }
         }
         stageUpdate("Constructing depth maps");
@@ -190,6 +201,7 @@ private:
         results.push_back(VectorImage(image.width(), image.height()));
         computedDepths.push_back(std::vector<double>((size_t)image.width() * image.height(), std::numeric_limits<double>::quiet_NaN()));
         depthIndices.push_back(std::vector<int32_t>((size_t)image.width() * image.height(), -1));
+        peakPairs_.push_back(std::vector<double>());
         views.push_back(view);
     }
 
@@ -226,6 +238,7 @@ private:
     std::vector<VectorImage> images, masks, results;
     std::vector<std::vector<double> > computedDepths;
     std::vector<std::vector<int32_t> > depthIndices;
+    std::vector<std::vector<double> > peakPairs_;
     std::vector<double> coverage_before_, coverage_after_;
     double minDepth, maxDepth;
     int numDepthLevels;

@@ -375,6 +375,26 @@ int sr_set_params(sr_ctx *ctx, const sr_params *p) {
     return SR_OK;
 }
 
+// The K = 9 peak pairs per pixel of the view about to run (keep_cost_volume & 2), initialised to
+// (0, -1) as multiviewstereo.cpp:562 does; label and curve mode share it.
+static int init_peaks(sr_ctx *ctx, int ref) {
+    const sr_params &P = ctx->params;
+    ctx->peaks_view = -1;
+    if (!(P.keep_cost_volume & 2)) return SR_OK;
+    if (P.select_kind != SR_SELECT_MVS) return fail(ctx, SR_ERR_INVALID, "peak lists belong to the multi-view selection");
+    const size_t n = (size_t)ctx->w * ctx->h;
+    if (!ctx->d_peaks) CK(cudaMalloc(&ctx->d_peaks, n * 18 * 8));
+    std::vector<double> init(n * 18);
+    for (int k = 0; k < 9; ++k) {
+        std::fill(init.begin() + (size_t)(2 * k) * n, init.begin() + (size_t)(2 * k + 1) * n, 0.0);
+        std::fill(init.begin() + (size_t)(2 * k + 1) * n, init.begin() + (size_t)(2 * k + 2) * n, -1.0);
+    }
+    CK(cudaMemcpyAsync(ctx->d_peaks, init.data(), n * 18 * 8, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->peaks_view = ref;
+    return SR_OK;
+}
+
 int sr_run_view(sr_ctx *ctx, int ref, const int32_t *nbrs, int nn) {
     int rc = check_view(ctx, ref);
     if (rc) return rc;
@@ -423,19 +443,8 @@ int sr_run_view(sr_ctx *ctx, int ref, const int32_t *nbrs, int nn) {
         CK(cudaMalloc(&ctx->d_taps, need));
         ctx->taps_cap = need;
     }
-    ctx->peaks_view = -1;
-    if (P.keep_cost_volume & 2) {  // the K = 9 peak pairs per pixel, initialised to (0, -1) (multiviewstereo.cpp:562)
-        if (P.select_kind != SR_SELECT_MVS) return fail(ctx, SR_ERR_INVALID, "peak lists belong to the multi-view selection");
-        if (!ctx->d_peaks) CK(cudaMalloc(&ctx->d_peaks, n * 18 * 8));
-        std::vector<double> init(n * 18);
-        for (int k = 0; k < 9; ++k) {
-            std::fill(init.begin() + (size_t)(2 * k) * n, init.begin() + (size_t)(2 * k + 1) * n, 0.0);
-            std::fill(init.begin() + (size_t)(2 * k + 1) * n, init.begin() + (size_t)(2 * k + 2) * n, -1.0);
-        }
-        CK(cudaMemcpyAsync(ctx->d_peaks, init.data(), n * 18 * 8, cudaMemcpyHostToDevice, st));
-        CK(cudaStreamSynchronize(st));
-        ctx->peaks_view = ref;
-    }
+    rc = init_peaks(ctx, ref);
+    if (rc) return rc;
     ctx->vol_elems = 0;
     if (P.keep_cost_volume & 1) {
         if (need > ctx->vol_cap) {
@@ -662,7 +671,7 @@ int sr_run_view_curve(sr_ctx *ctx, int ref, const int32_t *nbrs, int nn) {
     const sr_params &P = ctx->params;
     const bool mvs = (P.select_kind == SR_SELECT_MVS);
     if (!mvs && nn != 1) return fail(ctx, SR_ERR_INVALID, "two-view selection takes exactly one neighbour");
-    if (P.keep_cost_volume) return fail(ctx, SR_ERR_INVALID, "curve mode keeps no cost volume (candidates are not labels)");
+    if (P.keep_cost_volume & 1) return fail(ctx, SR_ERR_INVALID, "curve mode keeps no cost volume (candidates are not labels)");
     if (mvs && P.cost_kind != SR_COST_NCC_MVS) return fail(ctx, SR_ERR_INVALID, "multi-view curve search uses SR_COST_NCC_MVS");
     CK(cudaSetDevice(ctx->device));
     cudaStream_t st = ctx->stream;
@@ -677,6 +686,8 @@ int sr_run_view_curve(sr_ctx *ctx, int ref, const int32_t *nbrs, int nn) {
         rc = ensure_rays(ctx, nbrs[j]);
         if (rc) return rc;
     }
+    rc = init_peaks(ctx, ref);  // keep_cost_volume & 2: the candidates' (ncc, z) pairs, through the all-FP64 kernel
+    if (rc) return rc;
     const size_t wn = (size_t)(2 * P.radius + 1) * (2 * P.radius + 1);
     const size_t per_row_w = wn * w * 8;
 
@@ -803,6 +814,7 @@ int sr_run_view_curve(sr_ctx *ctx, int ref, const int32_t *nbrs, int nn) {
         memcpy(ma.camR, ctx->cams[ref].R, sizeof(ma.camR));
         memcpy(ma.camT, ctx->cams[ref].t, sizeof(ma.camT));
         ma.curve = 1;
+        ma.out_peaks = (P.keep_cost_volume & 2) ? ctx->d_peaks : nullptr;
         ma.taps = ctx->d_taps;
         ma.depth_table = ctx->d_depth_table;
         ma.out_index = A.index;

@@ -628,6 +628,7 @@ __global__ void __launch_bounds__(128, (R <= 2) ? SR_MATCH_MINBLOCKS : 2) match_
     // ---- label sweep -------------------------------------------------------------------------
     double minCost = dinf(), secondBest = dinf();  // two-view selection
     double bestC = 0.0;                            // MVS selection
+    double bestZ = -1.0;                           // MVS curve mode: depth of the winning candidate
     int bestIdx = SR_INDEX_NONE;
     int32_t bestTap = TAP_NONE;                    // curve mode: the winning candidate's pixel
     const bool mvs = a.select_kind == SR_SELECT_MVS;
@@ -668,12 +669,18 @@ __global__ void __launch_bounds__(128, (R <= 2) ? SR_MATCH_MINBLOCKS : 2) match_
                 if (cost != cost) cost = slow_cost<R, G, COST>(a, gR, x, y, tx, ty, pid, sub, gmask);
                 // ---- stage (3): winner-take-all, fused ----
                 const int d = d0 + l;
+                // curve mode (multiviewstereo.cpp:583-588): a candidate's depth is the camera-space z of
+                // the closest approach of the two viewing rays, computed only for the few candidates
+                // above the threshold
+                double zc = 0.0;
+                if (mvs && a.curve && cost > a.ncc_threshold)
+                    zc = curve_depth(a.raysL, a.raysR[j], (size_t)w * h, pix, (size_t)ty * w + tx, a.camR, a.camT);
                 if (mvs && a.out_peaks && sub == 0 && cost > a.ncc_threshold) {
                     // peaks.push_back(pair(ncc, depth)); sort; keep the last K (multiviewstereo.cpp:589-602):
                     // kept incrementally as an ascending list, smallest entry first
                     const size_t n = (size_t)w * h;
                     double *pk = a.out_peaks + pix;  // entry k: pk[(2k)*n] = ncc, pk[(2k+1)*n] = depth
-                    const double dep = a.depth_table[d0 + l];
+                    const double dep = a.curve ? zc : a.depth_table[d0 + l];
                     const double c0 = pk[0], z0 = pk[n];
                     if (cost > c0 || (cost == c0 && dep > z0)) {
                         int k = 0;  // drop entry 0, shift smaller entries down, insert in order
@@ -695,10 +702,11 @@ __global__ void __launch_bounds__(128, (R <= 2) ? SR_MATCH_MINBLOCKS : 2) match_
                     // on the indices (deeper == d > bestIdx iff depth_up); the table is read once at
                     // the end instead of once per label on the critical path.
                     if (cost > a.ncc_threshold) {
-                        const bool deeper = depth_up ? (d > bestIdx) : (d < bestIdx);
+                        const bool deeper = a.curve ? (zc > bestZ) : (depth_up ? (d > bestIdx) : (d < bestIdx));
                         if (bestIdx == SR_INDEX_NONE || cost > bestC || (cost == bestC && deeper)) {
                             bestC = cost;
                             bestIdx = d;
+                            bestZ = zc;
                         }
                     }
                 } else {  // twoviewstereo.cpp:320-325
@@ -718,7 +726,7 @@ __global__ void __launch_bounds__(128, (R <= 2) ? SR_MATCH_MINBLOCKS : 2) match_
     if (sub == 0) {
         if (mvs) {
             a.out_index[pix] = bestIdx;
-            a.out_depth[pix] = (bestIdx >= 0) ? a.depth_table[bestIdx] : -1.0;
+            a.out_depth[pix] = (bestIdx >= 0) ? (a.curve ? bestZ : a.depth_table[bestIdx]) : -1.0;
             a.out_best[pix] = bestC;
         } else {
             double depth = (bestIdx >= 0) ? a.depth_table[a.curve ? 0 : bestIdx] : qnan();

@@ -66,6 +66,11 @@ int main(int argc, char **argv) {
             mvs.run();
             for (size_t v = 0; v < mvs.numViews(); ++v)
                 dump(out + "/mvs_curve_v" + std::to_string(v) + "_depth.bin", mvs.depths(v).data(), mvs.depths(v).size());
+            // ... and once more keeping the K = 9 peak lists (CostFunction::peakPairs)
+            mvs.setKeepPeaks(true);
+            mvs.run();
+            dump(out + "/mvs_curve_v0_peaks.bin", mvs.peakPairs(0).data(), mvs.peakPairs(0).size());
+            mvs.setKeepPeaks(false);
             std::printf("mvs (curve mode): %.1f%% of view 0 has depth after cross-check\n", 100 * mvs.coverageAfterCrossCheck()[0]);
             mvs.setCurveMode(false);
             mvs.run();

@@ -79,6 +79,43 @@ def test_curve_banding_is_invisible(monkeypatch):
     assert ((b0 == b1) | (np.isnan(b0) & np.isnan(b1))).all()
 
 
+@pytest.mark.parametrize("interface", [True, False])
+def test_mvs_curve_peak_lists_match_oracle(ctx, interface):
+    """CostFunction::peakPairs in the reference's live (curve) formulation (multiviewstereo.cpp:479-482,
+    583-602): the 9 largest (ncc, z) pairs over the curve pixels of all neighbours, ascending, padded
+    with (0, -1); the last pair is the pixel's result.  keep_cost_volume & 2 routes the view through
+    the all-FP64 kernel, which must also agree with the screened kernel's winner."""
+    cams, imgs, ms, _ = refractive_arc_scene(V=4, w=96, h=64, masks=True, interface=interface)
+    ctx.set_views(cams, imgs, ms)
+    P = T.default_params(True, 420.0, 580.0, 40)
+    ctx.set_params(P)
+    nb = ctx.select_neighbours(3)
+    ctx.run_view_curve(1, nb[1])
+    sd, sb = ctx.depth(1).copy(), ctx.best_cost(1).copy()  # screened kernel
+    P.keep_cost_volume = 2
+    ctx.set_params(P)
+    ctx.run_view_curve(1, nb[1])
+    gp, gd, gb = ctx.peaks(1), ctx.depth(1), ctx.best_cost(1)
+    # winner of the all-FP64 kernel == winner of the screened kernel (costs of the streaming FP64 form
+    # and of the exact two-pass form differ at the 1e-13 level, so an exact tie may flip: rate bound)
+    assert _depth_equal(gd, sd).mean() >= 1 - 1e-3
+    same = _depth_equal(gd, sd) & np.isfinite(sb) & (sd > 0)
+    assert np.abs(gb[same] - sb[same]).max() <= 1e-9
+    sc = O.Scene(cams, imgs, ms)
+    od, _, ob, _, op = sc.mvs_view(P, 1, nb[1], curve_mode=True, want_peaks=True)
+    white = ms[1] == 255
+    gz, oz = gp[..., 1][white], op[..., 1][white]
+    assert _depth_equal(gz, oz).mean() >= 1 - 1e-3                    # depths of the kept pairs
+    assert cost_close(gp[..., 0][white], op[..., 0][white], rel=1e-9, abs_floor=1e-12).mean() <= 1e-3
+    assert (gp[..., 0][white][:, -1] > 0.95).mean() > 0.1            # the last entry is the winner
+    assert (np.diff(gp[..., 0][white], axis=-1) >= 0).all()          # ascending
+    filled = (gp[..., 0][white] > 0).sum(axis=-1)
+    assert filled.max() == 9 and (filled == 0).any()                 # full lists and empty lists both occur
+    assert (filled == (op[..., 0][white] > 0).sum(axis=-1)).mean() >= 1 - 1e-3
+    lab = white & (gd > 0) & np.isfinite(gd)
+    assert (gp[..., -1, 1][lab] == gd[lab]).all() and (gp[..., -1, 0][lab] == gb[lab]).all()
+
+
 def test_curve_mode_rejects_cost_volume(ctx):
     cams, imgs, ms, _ = refractive_arc_scene(V=3, w=32, h=24, masks=False)
     ctx.set_views(cams, imgs, None)

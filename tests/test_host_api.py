@@ -127,6 +127,13 @@ def test_cpp_class_api_end_to_end(tmp_path):
         gd = np.fromfile(os.path.join(out, f"mvs_curve_v{v}_depth.bin"), dtype=np.float64).reshape(h, w)
         d = ctx.depth(v)
         assert ((gd == d) | (np.isnan(gd) & np.isnan(d))).all()
+    # ... and its peak lists (setKeepPeaks) == sr_get_peaks directly
+    P.keep_cost_volume = 2
+    ctx.set_params(P)
+    ctx.run_view_curve(0, nb[0])
+    gp = np.fromfile(os.path.join(out, "mvs_curve_v0_peaks.bin"), dtype=np.float64).reshape(h, w, 9, 2)
+    assert (gp == ctx.peaks(0)).all() and (gp[..., -1, 0] > 0.95).any()
+    P.keep_cost_volume = 0
 
     # TwoViewStereo (no masks, radius 2, cross-check 30) == the C ABI directly
     two = [pods[0], pods[1]]
