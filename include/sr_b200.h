@@ -219,6 +219,14 @@ int sr_project_points(sr_ctx *ctx, int view, int n, const double *xyz, double *o
  * Levenberg-Marquardt loop around it (util/lm.cpp) stays on the host. */
 int sr_calibration_residuals(sr_ctx *ctx, int num_cams, const sr_camera *cams, int n,
                              const int32_t *view_pairs, const double *pixels, double *out);
+/* The same for num_models camera sets in one launch: cams = num_models * num_cams PODs
+ * (set m at cams + m*num_cams), out = num_models * n residuals.  One Levenberg-Marquardt
+ * step of the interface calibration evaluates the current model and the two finite-difference
+ * perturbations of every free parameter (RefractiveCalibrationFunction::gradient,
+ * stereo/refractioncalibration.cpp:203-236) this way; include/stereo/refractioncalibration.hpp
+ * is the caller. */
+int sr_calibration_residuals_batch(sr_ctx *ctx, int num_models, int num_cams, const sr_camera *cams,
+                                   int n, const int32_t *view_pairs, const double *pixels, double *out);
 int sr_compute_weights(sr_ctx *ctx, int view, int weight_kind, int radius, int n,
                        const int32_t *cx, const int32_t *cy, double *out);
 

@@ -1342,6 +1342,204 @@ void orc_calibration_residuals(const Camera *cams, int n, const int32_t *pairs, 
         out[i] = e1 + e2;
     }
 }
+// ---- interface calibration: util/lm.cpp:59-150 around stereo/refractioncalibration.cpp:127-253 ----
+// A literal restatement of the reference's loops (diff and gradient are called point by point and
+// parameter by parameter, the cameras are re-configured by update() for every finite difference),
+// with the two deviations documented in include/util/lm.hpp: fixed parameters are removed from
+// the linear system, and the sense of the solve test (:104) is selectable (literalCheck != 0 is
+// the text as written).  Model layout: [n, (px, py, dist) x V].
+namespace {
+struct CalibFunction {
+    Camera *views;
+    int V;
+    const int32_t *p2c;
+    const double *pix;
+    int exactAttribution;
+
+    bool update(const double *model) {  // refractioncalibration.cpp:238-251
+        for (int v = 0; v < V; ++v)
+            if (model[3 * v + 2] < 1e-4) return false;
+        for (int v = 0; v < V; ++v) {
+            Camera &view = views[v];
+            V3 normal = mul(view.Kinv, V3{model[3 * v + 1], model[3 * v + 2], 1.0});
+            normal = normalized(normal);
+            if (std::fabs(model[0] - view.n) > 1e-10) {  // Camera::setRefractiveIndex, camera.cpp:337-342
+                view.n = model[0];
+                view.is_refractive = (!iszero(view.n - 1) && !iszero(view.plane_d));
+            }
+            const V3 dn = normal - V3{view.plane_n[0], view.plane_n[1], view.plane_n[2]};
+            if (!(dot(dn, dn) + std::fabs(model[3 * v + 3] - view.plane_d) < 1e-10)) {  // plane != P: setPlane, camera.cpp:326-332
+                view.plane_n[0] = normal.x;
+                view.plane_n[1] = normal.y;
+                view.plane_n[2] = normal.z;
+                view.plane_d = model[3 * v + 3];
+                view.is_refractive = (!iszero(view.n - 1) && !iszero(view.plane_d));
+            }
+        }
+        return true;
+    }
+    double diff(int i) const {  // :170-201
+        double out;
+        const int32_t pair[2] = {p2c[2 * i], p2c[2 * i + 1]};
+        orc_calibration_residuals(views, 1, pair, pix + 4 * i, &out);
+        return out;
+    }
+    bool touches(int paramIndex, int i) const {
+        if (exactAttribution) {
+            if (paramIndex == 0) return true;
+            const int v = (paramIndex - 1) / 3;
+            return v == p2c[2 * i] || v == p2c[2 * i + 1];
+        }
+        return paramIndex / 3 == p2c[2 * i] || paramIndex / 3 == p2c[2 * i + 1];  // :205-207
+    }
+    double gradient(int i, const std::vector<double> &model, int paramIndex) {  // :203-236
+        if (!touches(paramIndex, i)) return 0.0;
+        std::vector<double> m1 = model, m2 = model;
+        if (paramIndex == 0) {
+            m1[paramIndex] = model[paramIndex] - 0.01;
+            m2[paramIndex] = model[paramIndex] + 0.01;
+        } else if ((paramIndex - 1) % 3 == 0) {
+            m1[paramIndex] = model[paramIndex] - 0.5;
+            m2[paramIndex] = model[paramIndex] + 0.5;
+        } else if ((paramIndex - 1) % 3 == 1) {
+            m1[paramIndex] = model[paramIndex] - 0.1;
+            m2[paramIndex] = model[paramIndex] + 0.1;
+        } else {
+            m1[paramIndex] = model[paramIndex];
+            m2[paramIndex] = model[paramIndex] + 0.0001;
+        }
+        update(m1.data());
+        const double val1 = diff(i);
+        update(m2.data());
+        const double val2 = diff(i);
+        update(model.data());
+        return (val2 - val1) / (m2[paramIndex] - m1[paramIndex]);
+    }
+    double chiSquared(int n) const {  // lm.cpp:50-55
+        double sum = 0.0;
+        for (int i = 0; i < n; ++i) {
+            const double d = diff(i);
+            sum += d * d;
+        }
+        return sum;
+    }
+};
+
+// LU with partial pivoting + substitution (Eigen's PartialPivLU in the reference, lm.cpp:101)
+void luSolveDense(std::vector<double> M, std::vector<double> y, std::vector<double> &x, int n) {
+    for (int k = 0; k < n; ++k) {
+        int piv = k;
+        double big = std::fabs(M[(size_t)k * n + k]);
+        for (int r = k + 1; r < n; ++r)
+            if (std::fabs(M[(size_t)r * n + k]) > big) {
+                big = std::fabs(M[(size_t)r * n + k]);
+                piv = r;
+            }
+        if (big == 0.0) continue;
+        if (piv != k) {
+            for (int c = 0; c < n; ++c) std::swap(M[(size_t)k * n + c], M[(size_t)piv * n + c]);
+            std::swap(y[k], y[piv]);
+        }
+        for (int r = k + 1; r < n; ++r) {
+            const double l = M[(size_t)r * n + k] / M[(size_t)k * n + k];
+            for (int c = k + 1; c < n; ++c) M[(size_t)r * n + c] -= l * M[(size_t)k * n + c];
+            y[r] -= l * y[k];
+        }
+    }
+    x.assign(n, 0.0);
+    for (int k = n - 1; k >= 0; --k) {
+        double s = y[k];
+        for (int c = k + 1; c < n; ++c) s -= M[(size_t)k * n + c] * x[c];
+        x[k] = s / M[(size_t)k * n + k];
+    }
+}
+}  // namespace
+
+// Returns the number of iterations; model (1 + 3V) is updated in place, chi2[0] / chi2[1] = the error
+// before / after.  cams is modified while running and restored (planes AND index) before returning.
+int orc_calibration_lm(const Camera *cams_in, int V, int n, const int32_t *pairs, const double *pix, double *model_io,
+                       const uint8_t *fixed, int maxIterations, double epsilon, int literalCheck, int exactAttribution,
+                       double *chi2) {
+    std::vector<Camera> cams(cams_in, cams_in + V);
+    CalibFunction f{cams.data(), V, pairs, pix, exactAttribution};
+    const int nparms = 1 + 3 * V;
+    std::vector<double> model(model_io, model_io + nparms);
+    std::vector<int> free_;
+    for (int p = 0; p < nparms; ++p)
+        if (!fixed[p]) free_.push_back(p);
+    const int nf = (int)free_.size();
+    f.update(model.data());
+    double e0 = f.chiSquared(n);
+    chi2[0] = chi2[1] = e0;
+    if (nf == 0 || n <= 0) return 0;
+    double lambda = 1;
+    int iter = 0, term = 0;
+    std::vector<double> H((size_t)nf * nf), g(nf), step;
+    do {
+        std::fill(H.begin(), H.end(), 0.0);
+        std::fill(g.begin(), g.end(), 0.0);
+        for (int i = 0; i < n; ++i) {  // lm.cpp:83-94
+            const double diff = f.diff(i);
+            for (int a = 0; a < nf; ++a) {
+                const double gradr = f.gradient(i, model, free_[a]);
+                for (int b = 0; b < nf; ++b) {
+                    const double gradc = f.gradient(i, model, free_[b]);
+                    H[(size_t)a * nf + b] += gradr * gradc;
+                }
+                g[a] += diff * gradr;
+            }
+        }
+        for (int a = 0; a < nf; ++a) H[(size_t)a * nf + a] *= 1.0 + lambda;
+        std::vector<double> rhs(nf);
+        for (int a = 0; a < nf; ++a) rhs[a] = -g[a];
+        luSolveDense(H, rhs, step, nf);
+        double d2 = 0.0, a2 = 0.0, b2 = 0.0;  // (H*new_model).isApprox(-g, 1e-10)
+        for (int r = 0; r < nf; ++r) {
+            double acc = 0.0;
+            for (int c = 0; c < nf; ++c) acc += H[(size_t)r * nf + c] * step[c];
+            d2 += (acc - rhs[r]) * (acc - rhs[r]);
+            a2 += acc * acc;
+            b2 += rhs[r] * rhs[r];
+        }
+        const bool solved = d2 <= 1e-20 * std::min(a2, b2);
+        if (literalCheck ? solved : !solved) {
+            ++term;
+            continue;
+        }
+        bool bad_model = false;
+        for (int p = 0; p < nparms; ++p)
+            if (std::isnan(model[p])) {
+                bad_model = true;
+                lambda *= 10.0;
+                ++term;
+            }
+        if (bad_model) continue;
+        std::vector<double> new_model = model;
+        for (int a = 0; a < nf; ++a) new_model[free_[a]] += step[a];
+        if (!f.update(new_model.data())) {
+            f.update(model.data());
+            lambda *= 10.0;
+            ++term;
+            continue;
+        }
+        const double e1 = f.chiSquared(n);
+        if (std::fabs(e1 - e0) > epsilon) term = 0;
+        else ++term;
+        const bool worse = (e0 - e1 < 0);
+        if (worse || std::isnan(e1)) {
+            lambda *= 10.0;
+            f.update(model.data());
+        } else {
+            lambda *= 0.1;
+            e0 = e1;
+            model = new_model;
+        }
+    } while (++iter < maxIterations && term < 5);
+    f.update(model.data());
+    chi2[1] = f.chiSquared(n);
+    for (int p = 0; p < nparms; ++p) model_io[p] = model[p];
+    return iter;
+}
 int orc_project(const Camera *cam, const double *xyz, int rootMode, double *out2) {
     V3 p = {xyz[0], xyz[1], xyz[2]};
     bool ok = cam->project(p, rootMode);

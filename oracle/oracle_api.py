@@ -245,6 +245,24 @@ def calibration_residuals(cams, pairs, pixels):
     return out
 
 
+def calibration_lm(cams, pairs, pixels, model, fixed, max_iterations=100, epsilon=1.0, literal_check=False,
+                   exact_attribution=True):
+    """RefractionCalibration::calibrate (stereo/refractioncalibration.cpp:363-378): util/lm.cpp's loop around
+    the residual above.  model = [n, (px, py, dist) x V].  Returns (model, iterations, chi2_before, chi2_after)."""
+    pairs = np.ascontiguousarray(pairs, dtype=np.int32).reshape(-1, 2)
+    pixels = np.ascontiguousarray(pixels, dtype=np.float64).reshape(-1, 4)
+    m = np.array(model, dtype=np.float64)
+    fx = np.ascontiguousarray(fixed, dtype=np.uint8)
+    assert m.size == 1 + 3 * len(cams) == fx.size
+    chi = np.zeros(2)
+    L = lib()
+    L.orc_calibration_lm.restype = C.c_int
+    it = L.orc_calibration_lm(as_cam_array(cams), len(cams), pairs.shape[0], _ip(pairs), _dp(pixels), _dp(m),
+                              fx.ctypes.data_as(C.c_void_p), int(max_iterations), C.c_double(epsilon),
+                              int(literal_check), int(exact_attribution), _dp(chi))
+    return m, it, chi[0], chi[1]
+
+
 def stats_reset():
     lib().orc_stats_reset()
 

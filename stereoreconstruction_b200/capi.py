@@ -27,6 +27,7 @@ EXPORTS = [
     "sr_run_view", "sr_run_view_curve", "sr_select_neighbours", "sr_cross_check", "sr_synchronize",
     "sr_get_depth_index", "sr_get_depth", "sr_get_best_cost", "sr_get_cost_volume", "sr_get_peaks", "sr_set_depth",
     "sr_get_depth_image", "sr_unproject_grid", "sr_project_points", "sr_compute_weights", "sr_calibration_residuals",
+    "sr_calibration_residuals_batch",
     "sr_comm_unique_id", "sr_comm_init", "sr_comm_allgather_views", "sr_comm_allgather_rows",
 ]
 
@@ -115,6 +116,16 @@ class Context:
         out = np.empty(pairs.shape[0], dtype=np.float64)
         arr = (SrCamera * len(cams))(*cams)
         self._ck(self._L.sr_calibration_residuals(self._h, len(cams), arr, pairs.shape[0], _p(pairs), _p(pixels), _p(out)))
+        return out
+
+    def calibration_residuals_batch(self, cam_sets, pairs, pixels):
+        """cam_sets: M lists of the same number of cameras -> (M, n) residuals in one launch."""
+        pairs = np.ascontiguousarray(pairs, dtype=np.int32).reshape(-1, 2)
+        pixels = np.ascontiguousarray(pixels, dtype=np.float64).reshape(-1, 4)
+        M, V = len(cam_sets), len(cam_sets[0])
+        out = np.empty((M, pairs.shape[0]), dtype=np.float64)
+        arr = (SrCamera * (M * V))(*[c for cs in cam_sets for c in cs])
+        self._ck(self._L.sr_calibration_residuals_batch(self._h, M, V, arr, pairs.shape[0], _p(pairs), _p(pixels), _p(out)))
         return out
 
     def peaks(self, view):

@@ -1041,29 +1041,38 @@ int sr_compute_weights(sr_ctx *ctx, int view, int kind, int radius, int n, const
     return SR_OK;
 }
 
-int sr_calibration_residuals(sr_ctx *ctx, int num_cams, const sr_camera *cams, int n, const int32_t *view_pairs,
-                             const double *pixels, double *out) {
-    if (!ctx || !cams || num_cams <= 0 || n < 0 || (n > 0 && (!view_pairs || !pixels || !out))) return SR_ERR_INVALID;
+int sr_calibration_residuals_batch(sr_ctx *ctx, int num_models, int num_cams, const sr_camera *cams, int n,
+                                   const int32_t *view_pairs, const double *pixels, double *out) {
+    if (!ctx || !cams || num_models <= 0 || num_models > 65535 || num_cams <= 0 || n < 0 ||
+        (n > 0 && (!view_pairs || !pixels || !out)))
+        return SR_ERR_INVALID;
     if (n == 0) return SR_OK;
     for (int i = 0; i < 2 * n; ++i)
         if (view_pairs[i] < 0 || view_pairs[i] >= num_cams) return fail(ctx, SR_ERR_INVALID, "camera index out of range");
     CK(cudaSetDevice(ctx->device));
-    const size_t cam_bytes = ((sizeof(sr_camera) * num_cams + 15) / 16) * 16;
-    int rc = ensure_scratch(ctx, cam_bytes + (size_t)n * (8 + 32 + 8));
+    const size_t ncam = (size_t)num_models * num_cams;
+    const size_t cam_bytes = ((sizeof(sr_camera) * ncam + 15) / 16) * 16;
+    int rc = ensure_scratch(ctx, cam_bytes + (size_t)n * (32 + 8) + (size_t)num_models * n * 8);
     if (rc) return rc;
     char *base = (char *)ctx->d_scratch;
     sr_camera *dc = (sr_camera *)base;
     double *dpix = (double *)(base + cam_bytes);
     double *dout = dpix + (size_t)4 * n;
-    int32_t *dpairs = (int32_t *)(dout + n);
-    CK(cudaMemcpyAsync(dc, cams, sizeof(sr_camera) * num_cams, cudaMemcpyHostToDevice, ctx->stream));
+    int32_t *dpairs = (int32_t *)(dout + (size_t)num_models * n);
+    CK(cudaMemcpyAsync(dc, cams, sizeof(sr_camera) * ncam, cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemcpyAsync(dpix, pixels, (size_t)n * 32, cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemcpyAsync(dpairs, view_pairs, (size_t)n * 8, cudaMemcpyHostToDevice, ctx->stream));
-    calibration_residual_kernel<<<(n + 127) / 128, 128, 0, ctx->stream>>>(dc, n, dpairs, dpix, dout);
+    calibration_residual_kernel<<<dim3((unsigned)((n + 127) / 128), (unsigned)num_models), 128, 0, ctx->stream>>>(
+        dc, num_cams, n, dpairs, dpix, dout);
     CKL();
-    CK(cudaMemcpyAsync(out, dout, (size_t)n * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(out, dout, (size_t)num_models * n * 8, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     return SR_OK;
+}
+
+int sr_calibration_residuals(sr_ctx *ctx, int num_cams, const sr_camera *cams, int n, const int32_t *view_pairs,
+                             const double *pixels, double *out) {
+    return sr_calibration_residuals_batch(ctx, 1, num_cams, cams, n, view_pairs, pixels, out);
 }
 
 // ---- multi-GPU ---------------------------------------------------------------------------

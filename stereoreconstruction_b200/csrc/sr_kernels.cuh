@@ -817,10 +817,15 @@ __global__ void __launch_bounds__(128) cross_check_kernel(const CrossArgs a) {
 // RefractiveCalibrationFunction::diff (stereo/refractioncalibration.cpp:175-201): the residual the
 // interface calibration minimises, one thread per correspondence.  (The Levenberg-Marquardt outer
 // loop, util/lm.cpp, stays on the host: a handful of parameters.)
-__global__ void calibration_residual_kernel(const sr_camera *__restrict__ cams, int n, const int32_t *__restrict__ pairs,
-                                            const double *__restrict__ pix, double *__restrict__ out) {
+// blockIdx.y selects one of gridDim.y camera sets (the base model of the Levenberg-Marquardt step
+// and its finite-difference perturbations are evaluated in one launch).
+__global__ void calibration_residual_kernel(const sr_camera *__restrict__ cams, int num_cams, int n,
+                                            const int32_t *__restrict__ pairs, const double *__restrict__ pix,
+                                            double *__restrict__ out) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
+    cams += (size_t)blockIdx.y * num_cams;
+    out += (size_t)blockIdx.y * n;
     const sr_camera &v1 = cams[pairs[2 * i]], &v2 = cams[pairs[2 * i + 1]];
     d3 s1, d1, s2, d2;
     cam_unproject(v1, pix[4 * i], pix[4 * i + 1], s1, d1);

@@ -4,6 +4,10 @@
 // results for tests/test_host_api.py to compare against the C ABI called directly and the oracle.
 //
 //   host_api_test <project.xml> <imageSetId> <outdir> <minDepth> <maxDepth> <levels> <crossCheck>
+//   host_api_test --calibrate <project.xml> <problem.bin> <outdir>
+//       RefractionCalibration over the project's cameras; problem.bin = int32 n, int32 flags
+//       (1: reference gradient attribution, 2: literal solve check), int32 pairs[2n],
+//       double pixels[4n], double model[1+3V], uint8 fixed[1+3V]
 #include <cstdio>
 #include <fstream>
 #include <iostream>
@@ -12,6 +16,7 @@
 #include "stereo/adaptiveweight.hpp"
 #include "stereo/geodesicweight.hpp"
 #include "stereo/multiviewstereo.hpp"
+#include "stereo/refractioncalibration.hpp"
 #include "stereo/twoviewstereo.hpp"
 
 template <typename T>
@@ -20,7 +25,67 @@ static void dump(const std::string &path, const T *data, size_t n) {
     f.write(reinterpret_cast<const char *>(data), (std::streamsize)(n * sizeof(T)));
 }
 
+static int calibrate_main(const char *xml, const char *problem, const std::string &out) {
+    ProjectPtr project(new Project(xml));
+    std::vector<CameraPtr> views;
+    for (const auto &kv : project->cameras()) views.push_back(kv.second);
+    const size_t V = views.size(), np_ = 1 + 3 * V;
+    std::ifstream f(problem, std::ios::binary);
+    int32_t n = 0, flags = 0;
+    f.read(reinterpret_cast<char *>(&n), 4);
+    f.read(reinterpret_cast<char *>(&flags), 4);
+    std::vector<int32_t> pairs((size_t)2 * n);
+    std::vector<double> pix((size_t)4 * n), model(np_);
+    std::vector<uint8_t> fx(np_);
+    f.read(reinterpret_cast<char *>(pairs.data()), (std::streamsize)(pairs.size() * 4));
+    f.read(reinterpret_cast<char *>(pix.data()), (std::streamsize)(pix.size() * 8));
+    f.read(reinterpret_cast<char *>(model.data()), (std::streamsize)(np_ * 8));
+    f.read(reinterpret_cast<char *>(fx.data()), (std::streamsize)np_);
+    if (!f) throw std::runtime_error("short calibration problem file");
+    LevenbergMarquardt::Points points;
+    std::vector<IntPair> p2c;
+    for (int i = 0; i < n; ++i) {
+        LevenbergMarquardt::Point a(2), b(2);
+        a[0] = pix[4 * i]; a[1] = pix[4 * i + 1]; b[0] = pix[4 * i + 2]; b[1] = pix[4 * i + 3];
+        points.push_back(LevenbergMarquardt::PointPair(a, b));
+        p2c.push_back(IntPair(pairs[2 * i], pairs[2 * i + 1]));
+    }
+    RefractionCalibration calib;
+    calib.setViews(views);
+    calib.setCorrespondences(points, p2c);
+    calib.setModel(model, LevenbergMarquardt::FixedParams(fx.begin(), fx.end()));
+    calib.setReferenceAttribution((flags & 1) != 0);
+    calib.setLiteralSolveCheck((flags & 2) != 0);
+    const Plane3d before = views[0]->plane();
+    const bool ok = calib.calibrate();
+    double avg = 0.0;
+    const double total = calib.totalError(&avg);
+    std::vector<double> res = calib.model();
+    res.push_back((double)calib.iterations());
+    res.push_back(calib.initialError());
+    res.push_back(calib.finalError());
+    res.push_back(total);
+    res.push_back(avg);
+    res.push_back(calib.error(points[0], views[p2c[0].first], views[p2c[0].second]));
+    res.push_back(ok ? 1.0 : 0.0);
+    // the function's destructor puts back the planes it saw at its LAST initialize() (:151-162) — LM calls
+    // initialize() again after the caller's update(model), so that is the start model's plane, as in the reference
+    res.push_back(views[0]->plane() == before ? 1.0 : 0.0);
+    dump(out + "/calib.bin", res.data(), res.size());
+    std::printf("calibrate: %d correspondences, %zu views, %d iterations, chi2 %.6g -> %.6g, ok=%d\n", n, V, calib.iterations(),
+                calib.initialError(), calib.finalError(), (int)ok);
+    return 0;
+}
+
 int main(int argc, char **argv) {
+    if (argc == 5 && std::string(argv[1]) == "--calibrate") {
+        try {
+            return calibrate_main(argv[2], argv[3], argv[4]);
+        } catch (const std::exception &e) {
+            std::fprintf(stderr, "host_api_test: %s\n", e.what());
+            return 1;
+        }
+    }
     if (argc < 8) {
         std::fprintf(stderr, "usage: %s project.xml imageSetId outdir minDepth maxDepth levels crossCheck\n", argv[0]);
         return 2;

@@ -164,3 +164,76 @@ def test_cpp_class_api_end_to_end(tmp_path):
     assert np.allclose(wv[0], sc1.weights(0, T.SR_WEIGHT_GEODESIC, 2, cx, cy)[0], rtol=1e-13, atol=1e-300)
     assert np.allclose(wv[1], sc1.weights(0, T.SR_WEIGHT_ADAPTIVE, 2, cx, cy)[0], rtol=1e-13, atol=1e-300)
     ctx.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("fix_index", [True, False])
+def test_refraction_calibration_matches_oracle(tmp_path, fix_index):
+    """RefractionCalibration::calibrate (stereo/refractioncalibration.cpp:289-404; util/lm.cpp): the C++
+    class — LM loop on the host, every residual from sr_calibration_residuals_batch — against the
+    oracle's literal point-by-point restatement of the same loops on the same correspondences."""
+    from oracle import oracle_api as O
+    from calib_util import calibration_problem
+    cams, pairs, pix, truth, start = calibration_problem(O.Scene)
+    V, n = len(cams), len(pairs)
+    h, w = 480, 640
+    blank = [np.zeros((h, w, 4), np.uint8)] * V
+    xml = write_project(str(tmp_path), cams, blank, [np.full((h, w), 255, np.uint8)] * V)
+    fixed = np.zeros(truth.size, np.uint8)
+    fixed[0] = fix_index  # the GUI always fixes the refractive index (stereowidget.cpp:577-578)
+
+    def run(flags, model):
+        prob = os.path.join(str(tmp_path), f"problem{flags}.bin")
+        with open(prob, "wb") as f:
+            f.write(np.array([n, flags], np.int32).tobytes())
+            f.write(np.ascontiguousarray(pairs, np.int32).tobytes())
+            f.write(np.ascontiguousarray(pix, np.float64).tobytes())
+            f.write(np.ascontiguousarray(model, np.float64).tobytes())
+            f.write(fixed.tobytes())
+        r = subprocess.run([HARNESS, "--calibrate", xml, prob, str(tmp_path)], capture_output=True, text=True)
+        assert r.returncode == 0, r.stdout + r.stderr
+        out = np.fromfile(os.path.join(str(tmp_path), "calib.bin"), dtype=np.float64)
+        return out[:truth.size], out[truth.size:]
+
+    # the cameras the harness loads from the XML carry the true interface: the model is what decides
+    gm, (it, c0, c1, total, avg, err0, ok, _restored) = run(0, start)
+    om, oit, oc0, oc1 = O.calibration_lm(cams, pairs, pix, start, fixed)
+    assert ok == 1.0
+    assert it == oit and it >= 5
+    # (finite differences with steps down to 1e-4 amplify the ~1e-12 residual differences between the GPU and the
+    # oracle, and the normal's pixel x is weakly determined: a 1e-13 relative change of the input pixels moves
+    # the oracle's own answer by 1e-6)
+    assert abs(c0 - oc0) <= 1e-9 * oc0 and abs(c1 - oc1) <= 1e-5 * oc1
+    assert c1 < 1e-2 * c0                      # it calibrates: chi^2 drops by orders of magnitude ...
+    assert np.allclose(gm, om, rtol=1e-5, atol=1e-3)
+    assert abs(total - c1) <= 1e-12 * c1 and abs(avg - total / n) <= 1e-12 * avg
+    res = O.calibration_residuals(_with_model(cams, om), pairs[:1], pix[:1])
+    assert abs(err0 - abs(res[0])) <= 1e-4 * max(1.0, abs(res[0]))
+    py_err = np.abs(gm - truth)[2::3]
+    assert (py_err < 2.0).all()                # ... and the well-determined parameters are recovered
+
+    # the reference's text as written: its gradient attribution leaves H singular, nothing is accepted
+    gm2, (it2, c0b, c1b, *_rest) = run(1, start)
+    om2, oit2, _, oc1b = O.calibration_lm(cams, pairs, pix, start, fixed, exact_attribution=False)
+    assert (gm2 == start).all() and (om2 == start).all() and it2 == oit2 and c1b == c0b
+    # ... and its solve test skips every successful solve
+    gm3, (it3, *_r3) = run(2, start)
+    om3, oit3, _, _ = O.calibration_lm(cams, pairs, pix, start, fixed, literal_check=True)
+    assert (gm3 == start).all() and (om3 == start).all() and it3 == oit3 == 5
+
+
+def _with_model(cams, model):
+    """Cameras re-configured as RefractiveCalibrationFunction::update does (:238-251)."""
+    import copy
+    out = []
+    for v, c in enumerate(cams):
+        c = copy.copy(c)
+        Kinv = np.array(c.Kinv[:]).reshape(3, 3)
+        nrm = Kinv @ np.array([model[3 * v + 1], model[3 * v + 2], 1.0])
+        nrm /= np.linalg.norm(nrm)
+        for i in range(3):
+            c.plane_n[i] = nrm[i]
+        c.plane_d = model[3 * v + 3]
+        c.n = model[0]
+        out.append(c)
+    return out

@@ -261,3 +261,26 @@ def test_costs_against_independent_numpy_restatement():
                 P = T.default_params(cost_kind == T.SR_COST_NCC_MVS, 1.0, 2.0, 4, radius=R, weight_kind=kind, cost_kind=cost_kind)
                 got = sc.cost(P, 0, 1, x1, y1, x2, y2)
                 assert abs(got - ref) <= 1e-9 * max(1.0, abs(ref)), (R, kind, cost_kind, x1, y1, x2, y2, got, ref)
+
+
+def test_calibration_lm_recovers_the_interface():
+    """util/lm.cpp + RefractiveCalibrationFunction restated (oracle.cpp, orc_calibration_lm): from a wrong
+    first guess the loop drives chi^2 down to the noise floor (the value at the true model) and recovers
+    the well-determined parameters; with the reference's text as written (gradient attribution by
+    paramIndex / 3, or the inverted solve test) no step is ever accepted."""
+    import sys
+    import os
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from calib_util import calibration_problem
+    cams, pairs, pix, truth, start = calibration_problem(O.Scene)
+    fixed = np.zeros(truth.size, np.uint8)
+    fixed[0] = 1
+    _, _, at_truth, _ = O.calibration_lm(cams, pairs, pix, truth, np.ones(truth.size, np.uint8))
+    m, it, c0, c1 = O.calibration_lm(cams, pairs, pix, start, fixed)
+    assert c0 > 100 * at_truth and c1 <= 1.05 * at_truth and 5 <= it < 100
+    assert m[0] == start[0]                                  # fixed parameters do not move
+    assert (np.abs(m - truth)[2::3] < 2.0).all()             # pixel y of every normal
+    # chi^2 reported == sum of squared residuals of the cameras configured with the model
+    for flags in (dict(exact_attribution=False), dict(literal_check=True)):
+        m2, it2, c0b, c1b = O.calibration_lm(cams, pairs, pix, start, fixed, **flags)
+        assert (m2 == start).all() and c1b == c0b == c0
