@@ -110,6 +110,9 @@ __device__ __noinline__ double verify_cost_mvs(const MatchArgs &a, const double 
                                 // other warp's slot
 #endif
 constexpr int SCREEN_BLOCK = SR_SCREEN_BLOCK;
+#ifndef SR_SCREEN_DISTRIBUTED
+#define SR_SCREEN_DISTRIBUTED 1  // 0: A/B against the slot-by-slot verification
+#endif
 
 // PITCH: compile-time row pitch of the FP32 gray planes (0: run-time a.pitch_f).
 template <int R, int G, bool STATS, int PITCH>
@@ -131,6 +134,11 @@ __global__ void __launch_bounds__(SCREEN_BLOCK, ((R <= 2) ? SR_SCREEN_MINBLOCKS 
     __shared__ int px_bestIdx[SCREEN_BLOCK];
     __shared__ double px_bestZ[SCREEN_BLOCK];  // curve mode: depth hypothesis of the verified winner
     __shared__ unsigned long long px_act[SCREEN_BLOCK];  // bit i: this lane's i-th tap is active (TPL <= 35)
+    // Distributed verification (thread-per-pixel variants): the warp's queued candidates as a compact
+    // list, (owner lane << 8) | queue slot, and what a lane verifying ANOTHER lane's candidate needs to
+    // know about that pixel (bit 0: all_slow, bit 1: has_inactive).
+    __shared__ unsigned short v_ent[SCREEN_QCAP * SCREEN_BLOCK];
+    __shared__ unsigned char px_flags[SCREEN_BLOCK];
 
     const int tid = threadIdx.x;
     const int lane = tid & 31;
@@ -211,6 +219,7 @@ __global__ void __launch_bounds__(SCREEN_BLOCK, ((R <= 2) ? SR_SCREEN_MINBLOCKS 
         px_bestC[tid] = 0.0;
         px_bestIdx[tid] = SR_INDEX_NONE;
         px_bestZ[tid] = -1.0;
+        px_flags[tid] = (unsigned char)((all_slow ? 1 : 0) | (has_inactive ? 2 : 0));
     }
     // keep the FP32 copies as values of their own (otherwise they are re-derived from the FP64
     // ones with an F2F / DSETP inside the label loop)
@@ -302,7 +311,72 @@ __global__ void __launch_bounds__(SCREEN_BLOCK, ((R <= 2) ? SR_SCREEN_MINBLOCKS 
     float max_err = 0.0f;  // STATS only
     int n_viol = 0;        // STATS only: verified labels outside their error bar (must stay 0)
 
-    auto flush = [&]() {
+    // Verification of the queued candidates, label mode, thread-per-pixel.  A flush is triggered by ONE
+    // full queue while most lanes hold a few entries, so walking the queues slot by slot runs the
+    // FP64 filter with a handful of active lanes (measured: ~100 warp-wide evaluations for ~105
+    // lane-evaluations per warp).  Instead the warp's entries are compacted into one list and dealt
+    // out one per lane: ceil(sum qn / 32) evaluations per flush.  The verified cost (a double)
+    // replaces the entry's tap and upper bound in the owner's queue, and every lane then applies the
+    // reference's selection rule to its own entries in their original order.
+    auto flush_distributed = [&]() {
+        constexpr unsigned FULL = 0xffffffffu;
+        const int wb = tid - lane;  // first thread of this warp within the block
+        unsigned short *ent = v_ent + wb * SCREEN_QCAP;
+        int incl = qn;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int v = __shfl_up_sync(FULL, incl, o);
+            if (lane >= o) incl += v;
+        }
+        const int total = __shfl_sync(FULL, incl, 31);
+        const int off = incl - qn;
+        for (int q = 0; q < qn; ++q) ent[off + q] = (unsigned short)((lane << 8) | q);
+        __syncwarp();
+#pragma unroll 1
+        for (int e = lane; e < total; e += 32) {
+            const int o = wb + (ent[e] >> 8), q = ent[e] & 0xff;  // o: the owner's thread index
+            const int lab = q_lab[q][o], tap = q_tap[q][o];
+            const int j = (lab >> 16) & 0xff;
+            const int tx = (int)(short)(tap & 0xffff), ty = (int)(short)((uint32_t)tap >> 16);
+            const int opid = min((int)(blockIdx.x * PIX_PER_BLOCK + o), a.rows * a.w - 1);
+            const int ox = opid % a.w, oy = a.row0 + opid / a.w;
+            const bool inside = tx >= R && ty >= R && tx < w - R && ty < h - R;
+            const double cost = (inside && px_flags[o] == 0)
+                                    ? verify_cost_mvs<R, G>(a, a.grayR[j], ox, oy, tx, ty, opid, 0, gmask, px_meanL[o], px_totW[o], px_s2[o])
+                                    : slow_cost<R, G, COST>(a, a.grayR[j], ox, oy, tx, ty, opid, 0, gmask);
+            if (STATS) ++n_verified;
+            if (STATS && q_c32[q][o] < 2.0f) {  // |ncc32 - ncc64| relative to its error bar
+                const float eb = (lab >> 30) ? SCREEN_EPS_TIGHT : SCREEN_EPS_LOOSE;
+                const float c32 = q_c32[q][o] - eb;
+                const float err = fabsf((float)(cost - (double)c32));
+                max_err = fmaxf(max_err, err);
+                if (err > eb) ++n_viol;
+            }
+            q_tap[q][o] = __double2loint(cost);
+            q_c32[q][o] = __int_as_float(__double2hiint(cost));
+        }
+        __syncwarp();
+        double bestC = px_bestC[tid];
+        int bestIdx = px_bestIdx[tid];
+        for (int q = 0; q < qn; ++q) {
+            const double cost = __hiloint2double(__float_as_int(q_c32[q][tid]), q_tap[q][tid]);
+            const int d = q_lab[q][tid] & 0xffff;
+            if (cost > a.ncc_threshold) {  // multiviewstereo.cpp:589-602,654-660
+                const bool deeper = depth_up ? (d > bestIdx) : (d < bestIdx);
+                if (bestIdx == SR_INDEX_NONE || cost > bestC || (cost == bestC && deeper)) {
+                    bestC = cost;
+                    bestIdx = d;
+                }
+            }
+        }
+        qn = 0;
+        px_bestC[tid] = bestC;
+        px_bestIdx[tid] = bestIdx;
+        if (bestIdx != SR_INDEX_NONE) lower32 = fmaxf(lower32, (float)bestC - 1e-6f);
+        __syncwarp();  // the list and the queues are rewritten by the label loop
+    };
+
+    auto flush_by_slot = [&]() {
         const int nmax = __reduce_max_sync(0xffffffffu, qn);
         // the pixel's coordinates are re-derived here (rare path) instead of living in registers
         // across the label loop
@@ -356,6 +430,10 @@ __global__ void __launch_bounds__(SCREEN_BLOCK, ((R <= 2) ? SR_SCREEN_MINBLOCKS 
         px_bestIdx[tid] = bestIdx;
         // the verified maximum is a valid (and tighter) floor for the screen
         if (bestIdx != SR_INDEX_NONE) lower32 = fmaxf(lower32, (float)bestC - 1e-6f);
+    };
+    auto flush = [&]() {
+        if (G == 1 && SR_SCREEN_DISTRIBUTED && !a.curve) flush_distributed();
+        else flush_by_slot();
     };
 
     // ---- label sweep -------------------------------------------------------------------------
