@@ -162,12 +162,15 @@ struct RefrProjector {
 #define SR_BUILD_STRIDE 4
 #endif
 constexpr int BUILD_STRIDE = SR_BUILD_STRIDE;
+#ifndef SR_BUILD_MINBLOCKS
+#define SR_BUILD_MINBLOCKS 1  // resident 128-thread blocks per SM the register allocation must allow
+#endif
 
 // MVS: the multi-view tap rule (tap inside the image and WHITE in the neighbour's mask);
 // HAS_MASK: the neighbour has a mask plane (a.nbr_mask != null).  Compile-time so that the other
 // variant's clamps, mask address arithmetic and loads do not occupy (predicated-off) issue slots.
 template <bool MVS, bool HAS_MASK>
-__global__ void __launch_bounds__(128) build_refr_kernel(const __grid_constant__ BuildRefrArgs a) {
+__global__ void __launch_bounds__(128, SR_BUILD_MINBLOCKS) build_refr_kernel(const __grid_constant__ BuildRefrArgs a) {
     const int pid = blockIdx.x * blockDim.x + threadIdx.x;
     if (pid >= a.rows * a.w) return;
     const int x = pid % a.w, y = a.row0 + pid / a.w;

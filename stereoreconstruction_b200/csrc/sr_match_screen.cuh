@@ -44,7 +44,10 @@ namespace sr {
 constexpr float SCREEN_EPS_TIGHT = 1e-5f;
 constexpr float SCREEN_EPS_LOOSE = 2e-4f;
 constexpr float SCREEN_FORCE = 3.0e38f;  // "must be verified in FP64" marker (|ncc| <= 1 otherwise)
-constexpr int SCREEN_QCAP = 8;
+#ifndef SR_SCREEN_QCAP
+#define SR_SCREEN_QCAP 8  // candidate queue entries per pixel
+#endif
+constexpr int SCREEN_QCAP = SR_SCREEN_QCAP;
 
 // Packed FP32 FMA of sm_100 (SASS FFMA2): two independent fused multiply-adds per issue slot.
 __device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c) {
@@ -110,6 +113,9 @@ __device__ __noinline__ double verify_cost_mvs(const MatchArgs &a, const double 
                                 // other warp's slot
 #endif
 constexpr int SCREEN_BLOCK = SR_SCREEN_BLOCK;
+#ifndef SR_SCREEN_RINGPTR
+#define SR_SCREEN_RINGPTR 1  // 0: A/B against the indexed tap ring
+#endif
 #ifndef SR_SCREEN_DISTRIBUTED
 #define SR_SCREEN_DISTRIBUTED 1  // 0: A/B against the slot-by-slot verification
 #endif
@@ -459,6 +465,16 @@ __global__ void __launch_bounds__(SCREEN_BLOCK, ((R <= 2) ? SR_SCREEN_MINBLOCKS 
     issue_next();
 
     int buf = 0;
+#if SR_SCREEN_RINGPTR
+    // The ring column of this thread as a shared-window address that the label loop increments (the
+    // compiler otherwise re-derives it from %tid and the loop counters for every label: 7 issue slots).
+    // Lanes without a pixel never request taps: their columns hold TAP_NONE from here on.
+    if (!alive) {
+        for (int l = 0; l < TAP_CHUNK; ++l) tap_ring[0][l][tid] = tap_ring[1][l][tid] = TAP_NONE;
+    }
+    const unsigned ring_base = (unsigned)__cvta_generic_to_shared(&tap_ring[0][0][tid]);
+    constexpr unsigned RING_STEP = SCREEN_BLOCK * 4, RING_BUF = TAP_CHUNK * SCREEN_BLOCK * 4;
+#endif
 #pragma unroll 1
     for (int j = 0; j < a.num_nbrs; ++j) {
       const float *__restrict__ gRf = a.grayRf[j];
@@ -467,18 +483,32 @@ __global__ void __launch_bounds__(SCREEN_BLOCK, ((R <= 2) ? SR_SCREEN_MINBLOCKS 
         issue_next();
         cp_async_wait<1>();
         const int nl = min(TAP_CHUNK, D - d0);
+#if SR_SCREEN_RINGPTR
+        unsigned ra = ring_base + buf * RING_BUF;
+#pragma unroll 1
+        for (int l = 0; l < nl; ++l, ra += RING_STEP) {
+            int32_t tap;
+            asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tap) : "r"(ra));
+            if (tap != TAP_NONE) {
+#else
         const int32_t *ring = &tap_ring[buf][0][tid];
 #pragma unroll 1
         for (int l = 0; l < nl; ++l) {
             const int32_t tap = alive ? ring[l * SCREEN_BLOCK] : TAP_NONE;
             if (tap != TAP_NONE) {
+#endif
                 // (Consecutive labels often share a tap; re-using the previous value only pays when all
                 // 32 lanes repeat at once, which is rare, and costs three live registers: not done.
                 // The queue below still keeps one entry per distinct tap.)
                 float c32 = SCREEN_FORCE, eps = 0.0f;
                 {
                     const int tx = (int)(short)(tap & 0xffff), ty = (int)(short)((uint32_t)tap >> 16);
+#if SR_SCREEN_RINGPTR
+                    // R <= t < dim - R as one unsigned comparison per coordinate
+                    if (!all_slow && (unsigned)(tx - R) < (unsigned)(w - 2 * R) && (unsigned)(ty - R) < (unsigned)(h - 2 * R)) {
+#else
                     if (!all_slow && tx >= R && ty >= R && tx < w - R && ty < h - R) {
+#endif
                         const float *base = gRf + ((size_t)ty * fp + tx);
                         c32 = has_inactive ? screen_one(base, eps, std::true_type{}) : screen_one(base, eps, std::false_type{});
                     }
