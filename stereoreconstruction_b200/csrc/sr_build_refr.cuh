@@ -162,15 +162,17 @@ struct RefrProjector {
 #define SR_BUILD_STRIDE 4
 #endif
 constexpr int BUILD_STRIDE = SR_BUILD_STRIDE;
-#ifndef SR_BUILD_MINBLOCKS
-#define SR_BUILD_MINBLOCKS 1  // resident 128-thread blocks per SM the register allocation must allow
+#ifdef SR_BUILD_MINBLOCKS  // A/B: resident 128-thread blocks per SM the register allocation must allow
+#define SR_BUILD_BOUNDS __launch_bounds__(128, SR_BUILD_MINBLOCKS)
+#else  // measured best: 128 registers, 4 blocks per SM (160 registers / 3 blocks: 8.6 vs 7.95 ms per cfg4 view)
+#define SR_BUILD_BOUNDS __launch_bounds__(128)
 #endif
 
 // MVS: the multi-view tap rule (tap inside the image and WHITE in the neighbour's mask);
 // HAS_MASK: the neighbour has a mask plane (a.nbr_mask != null).  Compile-time so that the other
 // variant's clamps, mask address arithmetic and loads do not occupy (predicated-off) issue slots.
 template <bool MVS, bool HAS_MASK>
-__global__ void __launch_bounds__(128, SR_BUILD_MINBLOCKS) build_refr_kernel(const __grid_constant__ BuildRefrArgs a) {
+__global__ void SR_BUILD_BOUNDS build_refr_kernel(const __grid_constant__ BuildRefrArgs a) {
     const int pid = blockIdx.x * blockDim.x + threadIdx.x;
     if (pid >= a.rows * a.w) return;
     const int x = pid % a.w, y = a.row0 + pid / a.w;

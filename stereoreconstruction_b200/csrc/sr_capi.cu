@@ -573,6 +573,8 @@ int sr_run_view(sr_ctx *ctx, int ref, const int32_t *nbrs, int nn) {
         ma.out_volume = (P.keep_cost_volume & 1) ? ctx->d_volume : nullptr;
         ma.out_peaks = (P.keep_cost_volume & 2) ? ctx->d_peaks : nullptr;
         ma.w = w;
+        ma.win_w = w - 2 * P.radius;
+        ma.win_h = h - 2 * P.radius;
         ma.h = h;
         ma.row0 = b0;
         ma.rows = rows;
@@ -821,6 +823,8 @@ int sr_run_view_curve(sr_ctx *ctx, int ref, const int32_t *nbrs, int nn) {
         ma.out_depth = A.depth;
         ma.out_best = A.best;
         ma.w = w;
+        ma.win_w = w - 2 * P.radius;
+        ma.win_h = h - 2 * P.radius;
         ma.h = h;
         ma.row0 = b0;
         ma.rows = rows;

@@ -337,6 +337,7 @@ struct MatchArgs {
     double *out_peaks;              // [9][2][h*w] or null: the K = 9 largest (ncc, depth) pairs per pixel,
                                     // ascending (CostFunction::peakPairs, multiviewstereo.cpp:479-482,600-602)
     int w, h, row0, rows, D, num_nbrs;
+    int win_w, win_h;               // w - 2*radius, h - 2*radius: tap positions whose whole window is inside
     int tap_planes;                 // planes per neighbour in `taps` when it is larger than D (curve mode), else 0
     int select_kind;
     int depth_up;                   // depth_table is increasing in the label (max_depth > min_depth)

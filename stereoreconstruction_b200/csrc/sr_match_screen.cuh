@@ -168,9 +168,10 @@ __global__ void __launch_bounds__(SCREEN_BLOCK, ((R <= 2) ? SR_SCREEN_MINBLOCKS 
     }
 
     // ---- reference-window invariants, FP64 (once per pixel) ----------------------------------
+    // dlf carries 1/sqrt(s2): ncc32 = (sum dlf_i t_i) * rsqrt(s3), one rounding per element as before
     float wtf[TPL], dlf[TPL];
     bool all_slow = false, has_inactive = false;
-    float s2f = 0.0f, inv_totWf = 0.0f, eps_pix = SCREEN_EPS_LOOSE;
+    float inv_totWf = 0.0f, eps_pix = SCREEN_EPS_LOOSE;
     {
         double wt[TPL], gl[TPL];
         double totW = 0.0, SL = 0.0;
@@ -207,15 +208,17 @@ __global__ void __launch_bounds__(SCREEN_BLOCK, ((R <= 2) ? SR_SCREEN_MINBLOCKS 
             const double dl = (wt[i] > 0.0) ? wt[i] * gl[i] - meanL : 0.0;
             s2 += dl * dl;
             wtf[i] = (float)wt[i];
-            dlf[i] = (float)dl;
+            gl[i] = dl;
         }
         s2 = group_sum<G>(s2, gmask);
+        const double rs2 = (s2 >= (double)WN && s2 < 1e30) ? 1.0 / sqrt(s2) : 0.0;  // otherwise all_slow: dlf unused
+#pragma unroll
+        for (int i = 0; i < TPL; ++i) dlf[i] = (float)(gl[i] * rs2);
         // An ill-conditioned reference side is evaluated only by the exact FP64 filter.  Inactive
         // taps (outside the image, weight <= 1e-10) carry w = dl = 0 through the screen and their
         // t_i is masked out of s3 (screen_one<true>, taken only by the warps that hold such a pixel).
         all_slow = !(totW >= 1e-10) || !(s2 >= (double)WN) || !(s2 < 1e30);
         has_inactive = ninact != 0;
-        s2f = (float)s2;
         eps_pix = (s2 >= 100.0 * WN) ? SCREEN_EPS_TIGHT : SCREEN_EPS_LOOSE;
         inv_totWf = (float)(1.0 / totW);
         px_meanL[tid] = meanL;
@@ -229,7 +232,7 @@ __global__ void __launch_bounds__(SCREEN_BLOCK, ((R <= 2) ? SR_SCREEN_MINBLOCKS 
     }
     // keep the FP32 copies as values of their own (otherwise they are re-derived from the FP64
     // ones with an F2F / DSETP inside the label loop)
-    asm volatile("" : "+f"(s2f), "+f"(eps_pix), "+f"(inv_totWf));
+    asm volatile("" : "+f"(eps_pix), "+f"(inv_totWf));
 
     // ---- FP32 screening of one label: returns ncc32 or SCREEN_FORCE ---------------------------
     // Taps are processed in pairs (2p, 2p+1) with the packed FFMA2 (fma.rn.f32x2): the pair of
@@ -301,9 +304,9 @@ __global__ void __launch_bounds__(SCREEN_BLOCK, ((R <= 2) ? SR_SCREEN_MINBLOCKS 
         // ill-conditioned or non-finite neighbour window: FP64 decides
         if (!(s3 >= (float)WN) || !(s3 < 1e30f)) return SCREEN_FORCE;
         eps = (s3 >= 100.0f * WN) ? eps_pix : SCREEN_EPS_LOOSE;
-        // s2f*s3 >= WN^2 here: the flush-to-zero rsqrt needs no denormal fix-up (3 issue slots less)
+        // s3 >= WN here: the flush-to-zero rsqrt needs no denormal fix-up (3 issue slots less)
         float rs;
-        asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(rs) : "f"(s2f * s3));
+        asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(rs) : "f"(s3));
         return s1 * rs;
     };
 
@@ -505,7 +508,7 @@ __global__ void __launch_bounds__(SCREEN_BLOCK, ((R <= 2) ? SR_SCREEN_MINBLOCKS 
                     const int tx = (int)(short)(tap & 0xffff), ty = (int)(short)((uint32_t)tap >> 16);
 #if SR_SCREEN_RINGPTR
                     // R <= t < dim - R as one unsigned comparison per coordinate
-                    if (!all_slow && (unsigned)(tx - R) < (unsigned)(w - 2 * R) && (unsigned)(ty - R) < (unsigned)(h - 2 * R)) {
+                    if (!all_slow && (unsigned)(tx - R) < (unsigned)a.win_w && (unsigned)(ty - R) < (unsigned)a.win_h) {
 #else
                     if (!all_slow && tx >= R && ty >= R && tx < w - R && ty < h - R) {
 #endif
