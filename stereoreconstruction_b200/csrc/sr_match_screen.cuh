@@ -10,7 +10,8 @@
 //   screen (FP32)  ncc32 of every (label, neighbour) by the reference's own two-pass form
 //                  t_i = w_i*g_i - meanR;  s3 = sum t_i^2;  s1 = sum dl_i*t_i;  ncc = s1/sqrt(s2*s3)
 //                  on FP32 copies of the gray planes — 25 LDG.32 + 100 FFMA per 5x5 window, the
-//                  weights, dl_i and the window taps all in registers.  Every screened value
+//                  weights, dl_i and the window taps all in registers (dl_i is stored divided by
+//                  sqrt(s2), rounded once from FP64, so ncc32 = s1 * rsqrt(s3)).  Every screened value
 //                  carries an error bar eps (SCREEN_EPS_*, by conditioning of the two windows);
 //                  ill-conditioned windows and windows touching the neighbour's border are FORCEd
 //                  into the verified set.
@@ -18,11 +19,13 @@
 //                  bound of the winning ncc64, so a label can only win if ncc32 + eps >= lower32.
 //                  Candidates live in a small per-pixel queue in shared memory; entries whose
 //                  upper bound falls below a risen lower32 are evicted.
-//   verify (FP64)  when a queue fills (and at the end) the whole warp evaluates its queued
-//                  candidates with slow_cost — the reference's exact two-pass tap filter in FP64,
-//                  operation for operation — and applies the reference's selection rule to them
-//                  in the original order.  The result is the reference's winner, its depth and its
-//                  FP64 cost; the screening precision never reaches the output.
+//   verify (FP64)  when a queue fills (and at the end) the warp evaluates its queued candidates
+//                  with the reference's exact two-pass tap filter in FP64, operation for operation
+//                  (verify_cost_mvs / slow_cost) — the warp's entries are compacted into one list
+//                  and dealt out one per lane, whoever owns them — and every lane applies the
+//                  reference's selection rule to its own entries in the original order.  The
+//                  result is the reference's winner, its depth and its FP64 cost; the screening
+//                  precision never reaches the output.
 //
 // Consecutive labels whose projections truncate to the same integer tap have the same cost by
 // construction; the queue keeps one entry per distinct tap (carrying the label the tie-break would
