@@ -2,12 +2,14 @@
 // with the reference's sources read from /root/reference (see Makefile target _ref/libref.so).
 // TEST INFRASTRUCTURE: lets tests/test_oracle_vs_ref.py pin oracle/oracle.cpp against the real
 // LineIterator/clipLine, Ray3d/intersect/refract/closestPoints, VectorImage::pixel/sample,
-// AdaptiveWeight and GeodesicWeight.  This file contains no reference code, only calls.
+// AdaptiveWeight, GeodesicWeight and Camera (project / projectRefraction / unproject / set).  This
+// file contains no reference code, only calls.
 #include "util/lineiter.hpp"
 #include "util/ray.hpp"
 #include "util/vectorimage.hpp"
 #include "stereo/adaptiveweight.hpp"
 #include "stereo/geodesicweight.hpp"
+#include "project/camera.hpp"
 #include <cstdint>
 
 typedef Eigen::Vector3d V3;
@@ -99,4 +101,85 @@ void ref_weights(const ref_image *r, int kind, int radius, int n, const int32_t 
                 out[((size_t)i * wn + (row + radius)) * wn + (col + radius)] = (kind == 0) ? aw(row, col) : gw(row, col);
     }
 }
+
+// ---- project/camera.cpp: the reference's own Camera, configured from the oracle's camera POD ----
+// POD layout (oracle.cpp: struct Camera == include/sr_b200.h: sr_camera): K[9] Kinv[9] R[9] Rinv[9]
+// t[3] C[3] dist[5] plane_n[3] plane_d n prin_dir[3] is_refractive is_distorted.
+struct ref_cam_pod {
+    double K[9], Kinv[9], R[9], Rinv[9], t[3], C[3], dist[5], plane_n[3], plane_d, n, prin_dir[3];
+    int32_t is_refractive, is_distorted;
+};
+static void ref_configure(Camera &cam, const ref_cam_pod *p) {
+    Eigen::Matrix3d K, R;
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) { K(i, j) = p->K[3 * i + j]; R(i, j) = p->R[3 * i + j]; }
+    cam.set(K, R, V3(p->t[0], p->t[1], p->t[2]));
+    LensDistortions d;
+    for (int i = 0; i < 5; ++i) d[i] = p->dist[i];
+    cam.setLensDistortion(d);
+    cam.setRefractiveIndex(p->n);
+    cam.setPlane(Plane3d(V3(p->plane_n[0], p->plane_n[1], p->plane_n[2]), p->plane_d));
 }
+// What Camera::set / setLensDistortion / setPlane / setRefractiveIndex derive: the same POD back.
+void ref_camera_derived(const ref_cam_pod *in, ref_cam_pod *out) {
+    Camera cam("ref");
+    ref_configure(cam, in);
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) {
+            out->K[3 * i + j] = cam.K()(i, j); out->Kinv[3 * i + j] = cam.Kinv()(i, j);
+            out->R[3 * i + j] = cam.R()(i, j); out->Rinv[3 * i + j] = cam.Rinv()(i, j);
+        }
+    for (int i = 0; i < 3; ++i) {
+        out->t[i] = cam.t()[i]; out->C[i] = cam.C()[i];
+        out->plane_n[i] = cam.plane().normal()[i];
+        out->prin_dir[i] = cam.principleRay().direction()[i];
+    }
+    for (int i = 0; i < 5; ++i) out->dist[i] = cam.lensDistortion()[i];
+    out->plane_d = cam.plane().distance();
+    out->n = cam.refractiveIndex();
+    out->is_refractive = cam.isRefractive();
+    out->is_distorted = cam.isDistorted();
+}
+// Camera::project (camera.cpp:380-419) of n global points
+void ref_camera_project(const ref_cam_pod *pod, int n, const double *xyz, double *out_xy, int32_t *out_ok) {
+    Camera cam("ref");
+    ref_configure(cam, pod);
+    for (int i = 0; i < n; ++i) {
+        V3 p(xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2]);
+        out_ok[i] = cam.project(p) ? 1 : 0;
+        out_xy[2 * i] = p[0];
+        out_xy[2 * i + 1] = p[1];
+    }
+}
+// Camera::unproject (camera.cpp:423-459) of n pixels: out = n * (source xyz, direction xyz)
+void ref_camera_unproject(const ref_cam_pod *pod, int n, const double *xy, double *out6) {
+    Camera cam("ref");
+    ref_configure(cam, pod);
+    for (int i = 0; i < n; ++i) {
+        Ray3d r = cam.unproject(xy[2 * i], xy[2 * i + 1]);
+        for (int k = 0; k < 3; ++k) { out6[6 * i + k] = r.source()[k]; out6[6 * i + 3 + k] = r.direction()[k]; }
+    }
+}
+// Camera::setP -> updateOthers (camera.cpp:251-288): K, R, t back out of a 3x4 matrix (row-major in)
+void ref_camera_from_P(const double *P12, ref_cam_pod *out) {
+    Camera cam("ref");
+    ProjMat P;
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 4; ++j) P(i, j) = P12[4 * i + j];
+    cam.setP(P);
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) {
+            out->K[3 * i + j] = cam.K()(i, j); out->Kinv[3 * i + j] = cam.Kinv()(i, j);
+            out->R[3 * i + j] = cam.R()(i, j); out->Rinv[3 * i + j] = cam.Rinv()(i, j);
+        }
+    for (int i = 0; i < 3; ++i) { out->t[i] = cam.t()[i]; out->C[i] = cam.C()[i]; out->prin_dir[i] = cam.principleRay().direction()[i]; }
+}
+}
+
+// What moc would generate for Camera's signals (project/camera.hpp:146-152): nobody is connected.
+void Camera::nameChanged(QString) {}
+void Camera::intrinsicParametersChanged(const Eigen::Matrix3d &) {}
+void Camera::extrinsicParametersChanged(const Eigen::Matrix3d &, const Eigen::Vector3d &) {}
+void Camera::lensDistortionChanged(const LensDistortions &) {}
+void Camera::responseChanged(const Responses &) {}
+void Camera::refractiveParametersChanged(const Plane3d &, double) {}

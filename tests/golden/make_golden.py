@@ -4,8 +4,8 @@
   python tests/golden/make_golden.py        (run in the build container, where /root/reference exists)
 
 ref_leaves.npz    outputs of the REFERENCE'S OWN sources (util/lineiter.cpp, util/ray.cpp,
-                  util/vectorimage.cpp, stereo/adaptiveweight.cpp, stereo/geodesicweight.cpp compiled
-                  where they lie into oracle/_ref/libref.so) on seeded inputs.  They pin the oracle
+                  util/vectorimage.cpp, stereo/adaptiveweight.cpp, stereo/geodesicweight.cpp,
+                  project/camera.cpp compiled where they lie into oracle/_ref/libref.so) on seeded inputs.  They pin the oracle
                   — and through it the CUDA path — on machines where /root/reference is absent.
 oracle_scenes.npz outputs of the CPU oracle (oracle/oracle.cpp) on two small seeded scenes (a
                   masked refractive 4-view arc and a rectified pair): depth-index maps, depths,
@@ -91,6 +91,16 @@ def ref_leaves():
             REF.ref_weights(r, kind, radius, cx.size, _ip(cx), _ip(cy), _dp(buf))
             out[f"weights_k{kind}_r{radius}"] = buf
     REF.ref_image_destroy(r)
+    # --- Camera::unproject / Camera::project (project/camera.cpp:95-138,380-459)
+    cams, pix, pts = G.camera_cases()
+    for i, c in enumerate(cams):
+        pod = O.as_cam_array([c])
+        rays = np.empty((len(pix), 6))
+        REF.ref_camera_unproject(pod, len(pix), _dp(pix), _dp(rays))
+        xy = np.empty((len(pts[i]), 2))
+        ok = np.empty(len(pts[i]), np.int32)
+        REF.ref_camera_project(pod, len(pts[i]), _dp(pts[i]), _dp(xy), _ip(ok))
+        out[f"cam{i}_rays"], out[f"cam{i}_xy"], out[f"cam{i}_ok"] = rays, xy, ok
     return out
 
 

@@ -80,3 +80,26 @@ def rectified_scene():
 
 def rectified_params():
     return T.default_params(False, 100.0, 500.0, 32, radius=16, weight_kind=T.SR_WEIGHT_ADAPTIVE)
+
+
+def camera_cases():
+    """Cameras covering every branch of project/camera.cpp (refractive x distorted), pixels to
+    unproject and global points to project for each."""
+    cams = []
+    for interface, dist in ((True, (-0.1, 0.05, 0.001, 0.001, 0.0)), (True, (0.0,) * 5),
+                            (False, (-0.1, 0.05, 0.001, 0.001, 0.0)), (False, (0.0,) * 5)):
+        cams += scenes.arc_cameras(4, 640, 480, arc_deg=40.0, interface=interface, distortion=dist)[1:3]
+    rng = np.random.RandomState(31)
+    pix = np.concatenate([rng.uniform(-20, 660, (300, 1)), rng.uniform(-20, 500, (300, 1))], axis=1)
+    pix = np.ascontiguousarray(np.concatenate([pix, [[319.5, 239.5], [0.5, 0.5], [639.5, 479.5]]]))
+    # points: pixel rays of an ideal pinhole at the camera, pushed to depths 200..900, plus a box of points anywhere
+    pts = []
+    for c in cams:
+        Kinv = np.array(c.Kinv[:]).reshape(3, 3)
+        Rinv = np.array(c.Rinv[:]).reshape(3, 3)
+        Cc = np.array(c.C[:])
+        uv = np.concatenate([rng.uniform(0, 640, (400, 1)), rng.uniform(0, 480, (400, 1)), np.ones((400, 1))], axis=1)
+        d = (Rinv @ (Kinv @ uv.T)).T
+        p = Cc + d * rng.uniform(200, 900, (400, 1))
+        pts.append(np.ascontiguousarray(np.concatenate([p, rng.uniform(-400, 400, (100, 3)) + [0, 0, 100]])))
+    return cams, pix, pts

@@ -136,6 +136,52 @@ def _check_maps(gi, gd, gb, oi, od, ob, best_tol):
     assert not cost_close(gb[lab], ob[lab], rel=best_tol, abs_floor=best_tol).any()
 
 
+def _camera_golden_check(leaves, i, rays, xy, ok, tol_ray=1e-12, tol_px=1e-8):
+    gr, gxy, gok = leaves[f"cam{i}_rays"], leaves[f"cam{i}_xy"], leaves[f"cam{i}_ok"]
+    assert np.abs(rays - gr).max() <= tol_ray * max(1.0, np.abs(gr).max())
+    same = (ok != 0) == (gok != 0)
+    assert same.mean() >= 0.995  # the +-1e-3 acceptance band of camera.cpp:121-134 is decided by roundings
+    both = (ok != 0) & (gok != 0)
+    assert both.mean() > 0.5
+    err = np.abs(xy[both] - gxy[both]).max(axis=1)
+    assert np.quantile(err, 0.995) <= tol_px and (err > 1e-6).mean() <= 0.005
+
+
+def test_oracle_camera_matches_reference_golden(leaves):
+    """Camera::unproject / Camera::project of the reference's own project/camera.cpp (golden) vs the oracle."""
+    cams, pix, pts = G.camera_cases()
+    L = O.lib()
+    for i, c in enumerate(cams):
+        sc = O.Scene([c], [np.zeros((480, 640, 4), np.uint8)])
+        rays = np.empty((len(pix), 6))
+        for k, (x, y) in enumerate(pix):
+            L.orc_unproject(O.as_cam_array([c]), C.c_double(x), C.c_double(y), _dp(rays[k]))
+        for root_mode in (0, 1):
+            xy, ok = sc.project_points(0, pts[i], root_mode=root_mode)
+            _camera_golden_check(leaves, i, rays, xy, ok)
+
+
+@pytest.mark.gpu
+def test_gpu_camera_matches_reference_golden(leaves, gpu_ctx):
+    """sr_project_points and the ray table of sr_unproject_grid against the reference's own Camera."""
+    cams, pix, pts = G.camera_cases()
+    for i, c in enumerate(cams):
+        gpu_ctx.set_views([c], [np.zeros((480, 640, 4), np.uint8)], None)
+        xy, ok = gpu_ctx.project_points(0, pts[i])
+        # the grid holds pixel centres: compare the golden rays of the centres that are in it
+        grid = gpu_ctx.unproject_grid(0)
+        centre = np.array([[319.5, 239.5], [0.5, 0.5], [639.5, 479.5]])
+        gr = leaves[f"cam{i}_rays"][-3:]
+        got = np.array([grid[int(y), int(x)] for x, y in centre])
+        assert np.abs(got - gr).max() <= 1e-11 * max(1.0, np.abs(gr).max())
+        gxy, gok = leaves[f"cam{i}_xy"], leaves[f"cam{i}_ok"]
+        same = (ok != 0) == (gok != 0)
+        assert same.mean() >= 0.995
+        both = (ok != 0) & (gok != 0)
+        err = np.abs(xy[both] - gxy[both]).max(axis=1)
+        assert np.quantile(err, 0.995) <= 1e-8 and (err > 1e-6).mean() <= 0.005
+
+
 @pytest.mark.gpu
 def test_gpu_weights_match_reference_golden(leaves, gpu_ctx):
     """AdaptiveWeight / GeodesicWeight on the GPU against the reference's own compiled sources."""

@@ -1,6 +1,8 @@
 """Pins oracle/oracle.cpp against the REFERENCE'S OWN leaf sources compiled from /root/reference
 (oracle/_ref/libref.so: util/lineiter.cpp, util/ray.cpp, util/vectorimage.cpp,
-stereo/adaptiveweight.cpp, stereo/geodesicweight.cpp — see oracle/Makefile).  Bit-exact."""
+stereo/adaptiveweight.cpp, stereo/geodesicweight.cpp, project/camera.cpp — see oracle/Makefile).
+Bit-exact for the leaves; to rounding (1e-12) for the camera model, whose matrix algebra goes
+through a stand-in for Eigen on the reference side."""
 import ctypes as C
 
 import numpy as np
@@ -123,3 +125,95 @@ def test_weights_match_reference(image, kind, radius):
     REF.ref_weights(r, kind, radius, cx.size, _ip(cx), _ip(cy), _dp(ref))
     assert (mine == ref).all()
     REF.ref_image_destroy(r)
+
+
+# ---- project/camera.cpp: the reference's own Camera class ------------------------------------------
+def _cams():
+    """Cameras covering every branch: refractive + distorted (cfg4's), refractive only, distorted
+    only, plain pinhole."""
+    from stereoreconstruction_b200 import scenes
+    out = []
+    for interface, dist in ((True, (-0.1, 0.05, 0.001, 0.001, 0.0)), (True, (0.0,) * 5),
+                            (False, (-0.1, 0.05, 0.001, 0.001, 0.0)), (False, (0.0,) * 5)):
+        out += scenes.arc_cameras(4, 640, 480, arc_deg=40.0, interface=interface, distortion=dist)[1:3]
+    return out
+
+
+def _pod(c):
+    arr = O.as_cam_array([c])
+    return arr
+
+
+def test_camera_derived_state_matches_reference():
+    """Camera::set / setLensDistortion / setRefractiveIndex / setPlane (camera.cpp:205-222,302-342):
+    Kinv, Rinv, C, the principal ray and the two flags, as the host code derives them."""
+    for c in _cams():
+        got = O.OrcCamera()
+        REF.ref_camera_derived(_pod(c), C.byref(got))
+        for f in ("K", "R", "t", "dist", "plane_n"):
+            assert np.allclose(np.array(getattr(got, f)[:]), np.array(getattr(c, f)[:]), rtol=0, atol=1e-15), f
+        for f in ("Kinv", "Rinv", "C", "prin_dir"):
+            assert np.allclose(np.array(getattr(got, f)[:]), np.array(getattr(c, f)[:]), rtol=1e-13, atol=1e-13), f
+        assert got.plane_d == c.plane_d and got.n == c.n
+        assert got.is_refractive == c.is_refractive and got.is_distorted == c.is_distorted
+
+
+def test_camera_unproject_matches_reference():
+    """Camera::unproject (camera.cpp:423-459): distortion removal (5 fixed-point rounds), K^-1, refract
+    at the interface, local -> global."""
+    rng = np.random.RandomState(3)
+    xy = np.concatenate([rng.uniform(-20, 660, (400, 1)), rng.uniform(-20, 500, (400, 1))], axis=1)
+    xy = np.concatenate([xy, [[319.5, 239.5], [0.5, 0.5], [639.5, 479.5]]])
+    for c in _cams():
+        ref = np.empty((len(xy), 6))
+        REF.ref_camera_unproject(_pod(c), len(xy), _dp(np.ascontiguousarray(xy)), _dp(ref))
+        got = np.empty((len(xy), 6))
+        L = O.lib()
+        for i, (x, y) in enumerate(xy):
+            L.orc_unproject(_pod(c), C.c_double(x), C.c_double(y), _dp(got[i]))
+        assert np.isfinite(ref).all()
+        assert np.abs(got - ref).max() <= 1e-12 * max(1.0, np.abs(ref).max())
+
+
+@pytest.mark.parametrize("root_mode", [0, 1])
+def test_camera_project_matches_reference(root_mode):
+    """Camera::project + projectRefraction (camera.cpp:95-138,380-419) — the quartic's coefficients, the
+    root acceptance test, the point on the interface, K, distortion with the reference's y-from-distorted-x
+    — against the oracle in both root modes (0: the same quartic + acceptance order; 1: the monotone
+    1-D solve the GPU uses).  The GSL call inside the reference is answered by the restated solver."""
+    rng = np.random.RandomState(4)
+    for c in _cams():
+        sc = O.Scene([c], [np.zeros((480, 640, 4), np.uint8)])
+        rays = sc.unproject_grid(0).reshape(-1, 6)
+        rays = rays[rng.randint(0, rays.shape[0], 600)]
+        pts = rays[:, :3] + rng.uniform(200, 900, (600, 1)) * rays[:, 3:]       # in front, in view
+        pts = np.concatenate([pts, rng.uniform(-400, 400, (200, 3)) + [0, 0, 100]])  # anywhere
+        ref_xy = np.empty((len(pts), 2))
+        ref_ok = np.empty(len(pts), np.int32)
+        REF.ref_camera_project(_pod(c), len(pts), _dp(np.ascontiguousarray(pts)), _dp(ref_xy), _ip(ref_ok))
+        xy, ok = sc.project_points(0, pts, root_mode=root_mode)
+        assert (ok != 0).mean() > 0.5
+        same = (ok != 0) == (ref_ok != 0)
+        assert same.mean() >= 0.995, same.mean()  # acceptance at the +-1e-3 band edges may differ by rounding
+        both = (ok != 0) & (ref_ok != 0)
+        err = np.abs(xy[both] - ref_xy[both]).max(axis=1)
+        assert np.quantile(err, 0.995) <= 1e-8, np.quantile(err, 0.995)
+        # a different accepted root is only possible inside the |y| < 1e-3 acceptance band (DESIGN.md section 2)
+        assert (err > 1e-6).mean() <= 0.005
+
+
+def test_camera_from_projection_matrix_matches_reference():
+    """Camera::setP -> updateOthers (camera.cpp:251-288): RQ factorisation as the host code does it."""
+    from stereoreconstruction_b200 import types as T
+    for c in _cams()[:2]:
+        K = np.array(c.K[:]).reshape(3, 3)
+        R = np.array(c.R[:]).reshape(3, 3)
+        P = K @ np.hstack([R, np.array(c.t[:])[:, None]])
+        got = O.OrcCamera()
+        REF.ref_camera_from_P(_dp(np.ascontiguousarray(P * 3.7)), C.byref(got))
+        mine = T.camera_from_P(P * 3.7)
+        for f in ("K", "R", "t", "C", "prin_dir"):
+            a, b = np.array(getattr(got, f)[:]), np.array(getattr(mine, f)[:])
+            assert np.allclose(a, b, rtol=1e-9, atol=1e-9), (f, a, b)
+        # (the reference divides P by the SQUARED norm of its third row, :252: a scaled P gives a scaled K)
+        assert np.allclose(np.array(got.K[:]) / got.K[8], np.array(c.K[:]), rtol=1e-9, atol=1e-7)
