@@ -178,8 +178,12 @@ def test_gpu_camera_matches_reference_golden(leaves, gpu_ctx):
         same = (ok != 0) == (gok != 0)
         assert same.mean() >= 0.995
         both = (ok != 0) & (gok != 0)
-        err = np.abs(xy[both] - gxy[both]).max(axis=1)
-        assert np.quantile(err, 0.995) <= 1e-8 and (err > 1e-6).mean() <= 0.005
+        err = np.abs(xy - gxy).max(axis=1)
+        mag = np.maximum(1.0, np.abs(gxy).max(axis=1))
+        # points in view (the first 400): 1e-9 px; points anywhere (distorted coordinates reach 1e7 px): relative
+        assert err[:400][both[:400]].max() <= 1e-9
+        rel = (err / mag)[both]
+        assert np.quantile(rel, 0.995) <= 1e-10 and (rel > 1e-8).mean() <= 0.005
 
 
 @pytest.mark.gpu
