@@ -12,9 +12,16 @@
 #include <cmath>
 #include <cstddef>
 #include <cstdlib>
+#include <deque>
+#include <fstream>
 #include <functional>
+#include <iostream>
+#include <map>
 #include <limits>
 #include <memory>
+#include <sstream>
+#include <cstdint>
+#include <cstring>
 #include <string>
 #include <type_traits>
 #include <utility>

@@ -7,6 +7,11 @@ ref_leaves.npz    outputs of the REFERENCE'S OWN sources (util/lineiter.cpp, uti
                   util/vectorimage.cpp, stereo/adaptiveweight.cpp, stereo/geodesicweight.cpp,
                   project/camera.cpp compiled where they lie into oracle/_ref/libref.so) on seeded inputs.  They pin the oracle
                   — and through it the CUDA path — on machines where /root/reference is absent.
+ref_mvs.npz       END-TO-END outputs of the reference's own MultiViewStereo class (stereo/multiviewstereo.cpp
+                  + project/camera.cpp + the leaves, compiled where they lie, driven initialize() ->
+                  runTask() by oracle/ref_glue_mvs.cpp): neighbour lists, depths before and after the
+                  cross-check, the K = 9 peak lists of one view — on the small refractive arc scene and
+                  on the bunny fixture with and without the injected interface (BASELINE configs[1]).
 oracle_scenes.npz outputs of the CPU oracle (oracle/oracle.cpp) on two small seeded scenes (a
                   masked refractive 4-view arc and a rectified pair): depth-index maps, depths,
                   winning costs, one cost volume, cross-check results.  The reference ships no
@@ -133,9 +138,33 @@ def oracle_scenes():
     return out
 
 
+def ref_mvs():
+    """The reference's own MultiViewStereo (stereo/multiviewstereo.cpp through oracle/ref_glue_mvs.cpp),
+    initialize() -> runTask(), on the small arc scene and on the bunny fixture (BASELINE configs[1])."""
+    out = {}
+    for name, (mind, maxd, D, cross) in G.REF_MVS_CASES.items():
+        cams, imgs, ms, scale = G.ref_mvs_inputs(name)
+        cams = G.settled_cameras(cams)
+        ref = O.RefMVS(cams, imgs, ms, mind, maxd, D, cross, image_scale=scale)
+        after, nb = ref.run()
+        out[f"{name}_cams"] = G.cams_to_bytes(cams)
+        out[f"{name}_neighbours"] = np.array([r + [-1] * (3 - len(r)) for r in nb], np.int32)
+        out[f"{name}_after"] = after
+        before = []
+        for v in range(len(cams)):
+            d, pk = ref.initial_estimate(v)
+            before.append(d)
+            if v == 1:
+                out[f"{name}_peaks_v1"] = pk
+        out[f"{name}_before"] = np.array(before)
+        ref.close()
+    return out
+
+
 if __name__ == "__main__":
     O.build()
+    np.savez_compressed(os.path.join(HERE, "ref_mvs.npz"), **ref_mvs())
     np.savez_compressed(os.path.join(HERE, "ref_leaves.npz"), **ref_leaves())
     np.savez_compressed(os.path.join(HERE, "oracle_scenes.npz"), **oracle_scenes())
-    for f in ("ref_leaves.npz", "oracle_scenes.npz"):
+    for f in ("ref_leaves.npz", "oracle_scenes.npz", "ref_mvs.npz"):
         print(f, os.path.getsize(os.path.join(HERE, f)), "bytes")

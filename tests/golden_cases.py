@@ -103,3 +103,60 @@ def camera_cases():
         p = Cc + d * rng.uniform(200, 900, (400, 1))
         pts.append(np.ascontiguousarray(np.concatenate([p, rng.uniform(-400, 400, (100, 3)) + [0, 0, 100]])))
     return cams, pix, pts
+
+
+def settled_cameras(cams):
+    """Cameras passed through the reference's own Camera::set (which re-orthonormalises R and re-derives
+    Kinv, Rinv, C) until the derived state reproduces itself, so that the reference and the code
+    under test start from bit-identical camera state.  Needs oracle/_ref (the build container)."""
+    import ctypes as C
+    from oracle import oracle_api as O
+    REF = O.ref_lib()
+    out = []
+    for c in cams:
+        cur = O.as_cam_array([c])
+        for _ in range(6):
+            nxt = O.OrcCamera()
+            REF.ref_camera_derived(cur, C.byref(nxt))
+            done = bytes(cur[0]) == bytes(nxt)
+            cur = O.as_cam_array([nxt])
+            if done:
+                break
+        s = T.SrCamera()
+        C.memmove(C.byref(s), C.byref(cur[0]), C.sizeof(s))
+        out.append(s)
+    return out
+
+
+def cams_to_bytes(cams):
+    import ctypes as C
+    return np.frombuffer(b"".join(bytes(c) for c in cams), dtype=np.uint8).copy()
+
+
+def cams_from_bytes(buf):
+    import ctypes as C
+    n = C.sizeof(T.SrCamera)
+    out = []
+    for i in range(len(buf) // n):
+        c = T.SrCamera()
+        C.memmove(C.byref(c), bytes(buf[i * n:(i + 1) * n]), n)
+        out.append(c)
+    return out
+
+
+REF_MVS_CASES = {
+    # name: (min depth, max depth, levels, cross-check threshold)
+    "arc": (420.0, 580.0, 40, 12.0),
+    "bunny": (300.0, 800.0, 100, 5.0),        # README.md:103-112 / SURVEY 8d cfg2
+    "bunny_refr": (300.0, 800.0, 100, 5.0),   # ... with the injected interface
+}
+
+
+def ref_mvs_inputs(name):
+    """(cams, images, masks, image_scale) of a reference end-to-end case (cameras NOT yet settled)."""
+    if name == "arc":
+        cams, imgs, ms = arc_scene()
+        return cams, imgs, ms, 1.0
+    from bunny_util import load
+    cams, imgs, ms, scale = load(refractive=(name == "bunny_refr"))
+    return cams, imgs, ms, scale

@@ -136,6 +136,72 @@ def _check_maps(gi, gd, gb, oi, od, ob, best_tol):
     assert not cost_close(gb[lab], ob[lab], rel=best_tol, abs_floor=best_tol).any()
 
 
+# ------------------------------------------------------------------ the reference's MultiViewStereo, end to end
+@pytest.fixture(scope="module")
+def ref_mvs_gold():
+    return np.load(os.path.join(GOLD, "ref_mvs.npz"))
+
+
+def _depth_close(a, b, rel):
+    """NaN == NaN, inf == inf, -1 == -1, otherwise |a - b| <= rel * |b|."""
+    with np.errstate(invalid="ignore"):
+        return (a == b) | (np.isnan(a) & np.isnan(b)) | (np.abs(a - b) <= rel * np.abs(b))
+
+
+@pytest.mark.parametrize("name", list(G.REF_MVS_CASES))
+def test_oracle_matches_reference_mvs_golden(ref_mvs_gold, name):
+    """The oracle against the committed END-TO-END outputs of the reference's own MultiViewStereo class
+    (tests/golden/make_golden.py: ref_mvs) — the arc scene bit for bit; the bunny cases to the last-ulp
+    differences of the two cameras whose Gram-Schmidt re-orthonormalisation (Camera::set) does not settle."""
+    g = ref_mvs_gold
+    mind, maxd, D, cross = G.REF_MVS_CASES[name]
+    _, imgs, ms, scale = G.ref_mvs_inputs(name)
+    cams = G.cams_from_bytes(g[f"{name}_cams"])
+    sc = O.Scene(cams, imgs, ms)
+    P = T.default_params(True, mind, maxd, D, image_scale=scale)
+    nb = [[int(v) for v in r if v >= 0] for r in g[f"{name}_neighbours"]]
+    assert nb == [[int(v) for v in r] for r in sc.select_neighbours(3)]
+    rel = 0.0 if name == "arc" else 1e-12
+    before = []
+    for v in range(len(cams)):
+        od, _, _, _, op = sc.mvs_view(P, v, nb[v], curve_mode=True, root_mode=0, want_peaks=(v == 1))
+        before.append(od)
+        ok = _depth_close(od, g[f"{name}_before"][v], rel)
+        assert ok.mean() >= 1 - 1e-4, (v, 1 - ok.mean())
+        if v == 1:
+            white = ms[v] == 255
+            assert _depth_close(op[white], g[f"{name}_peaks_v1"][white], rel).mean() >= 1 - 1e-4
+    # the cross-check of the reference's own depths: bit for bit in every case
+    want = sc.crosscheck_mvs(P, [g[f"{name}_before"][v].copy() for v in range(len(cams))], cross)
+    for v in range(len(cams)):
+        assert _same(want[v], g[f"{name}_after"][v])
+    assert sum((np.isfinite(b) & (b > 0)).sum() for b in before) > 1000
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", list(G.REF_MVS_CASES))
+def test_gpu_curve_mode_matches_reference_mvs_golden(ref_mvs_gold, gpu_ctx, name):
+    """The CUDA path (sr_run_view_curve for every view, then sr_cross_check) against the END-TO-END
+    outputs of the reference's own MultiViewStereo::runTask."""
+    g = ref_mvs_gold
+    mind, maxd, D, cross = G.REF_MVS_CASES[name]
+    _, imgs, ms, scale = G.ref_mvs_inputs(name)
+    cams = G.cams_from_bytes(g[f"{name}_cams"])
+    gpu_ctx.set_views(cams, imgs, ms)
+    P = T.default_params(True, mind, maxd, D, image_scale=scale)
+    gpu_ctx.set_params(P)
+    nb = gpu_ctx.select_neighbours(3)
+    assert nb == [[int(v) for v in r if v >= 0] for r in g[f"{name}_neighbours"]]
+    for v in range(len(cams)):
+        gpu_ctx.run_view_curve(v, nb[v])
+        ok = _depth_close(gpu_ctx.depth(v), g[f"{name}_before"][v], 1e-9)
+        assert ok.mean() >= 1 - 1e-4, (v, 1 - ok.mean())
+    gpu_ctx.cross_check(False, cross)
+    for v in range(len(cams)):
+        ok = _depth_close(gpu_ctx.depth(v), g[f"{name}_after"][v], 1e-9)
+        assert ok.mean() >= 1 - 2e-4, (v, 1 - ok.mean())
+
+
 def _camera_golden_check(leaves, i, rays, xy, ok, tol_ray=1e-12, tol_px=1e-8):
     gr, gxy, gok = leaves[f"cam{i}_rays"], leaves[f"cam{i}_xy"], leaves[f"cam{i}_ok"]
     assert np.abs(rays - gr).max() <= tol_ray * max(1.0, np.abs(gr).max())
@@ -167,6 +233,7 @@ def test_gpu_camera_matches_reference_golden(leaves, gpu_ctx):
     cams, pix, pts = G.camera_cases()
     for i, c in enumerate(cams):
         gpu_ctx.set_views([c], [np.zeros((480, 640, 4), np.uint8)], None)
+        gpu_ctx.set_params(T.default_params(True, 10.0, 100.0, 8))  # image_scale 1: the grid's pixel centres are (x + 0.5, y + 0.5)
         xy, ok = gpu_ctx.project_points(0, pts[i])
         # the grid holds pixel centres: compare the golden rays of the centres that are in it
         grid = gpu_ctx.unproject_grid(0)

@@ -217,3 +217,42 @@ def test_camera_from_projection_matrix_matches_reference():
             assert np.allclose(a, b, rtol=1e-9, atol=1e-9), (f, a, b)
         # (the reference divides P by the SQUARED norm of its third row, :252: a scaled P gives a scaled K)
         assert np.allclose(np.array(got.K[:]) / got.K[8], np.array(c.K[:]), rtol=1e-9, atol=1e-7)
+
+
+# ---- stereo/multiviewstereo.cpp: the reference's own MultiViewStereo, end to end ---------------------
+def test_mvs_end_to_end_matches_reference():
+    """initialize() -> runTask() of the reference's own class (neighbour rule, rasterised epipolar curves,
+    weighted NCC, K = 9 peak lists, selection, cross-check; multiviewstereo.cpp:193-247,325-475,524-810) on a
+    refractive, lens-distorted, masked 4-view scene: the oracle reproduces every output BIT FOR BIT."""
+    import golden_cases as G
+    from stereoreconstruction_b200 import types as T
+    cams, imgs, ms = G.arc_scene()
+    mind, maxd, D, cross = G.REF_MVS_CASES["arc"]
+    ref = O.RefMVS(cams, imgs, ms, mind, maxd, D, cross)
+    after, nb = ref.run()
+    sc = O.Scene(cams, imgs, ms)
+    P = T.default_params(True, mind, maxd, D)
+    assert nb == [[int(v) for v in r] for r in sc.select_neighbours(3)]
+    before = []
+    for v in range(len(cams)):
+        d, pk = ref.initial_estimate(v)
+        od, _, ob, _, op = sc.mvs_view(P, v, nb[v], curve_mode=True, root_mode=0, want_peaks=True)
+        before.append(od)
+        assert ((d == od) | (np.isnan(d) & np.isnan(od))).all()
+        white = ms[v] == 255
+        assert (pk[white] == op[white]).all()
+        assert (np.isfinite(od) & (od > 0)).mean() > 0.3
+    want = sc.crosscheck_mvs(P, before, cross)
+    for v in range(len(cams)):
+        assert ((after[v] == want[v]) | (np.isnan(after[v]) & np.isnan(want[v]))).all()
+        assert 0.2 < (np.isfinite(want[v]) & (want[v] > 0)).mean() < (np.isfinite(before[v]) & (before[v] > 0)).mean()
+    # the file-local cost function and the public curve of single pixels
+    rng = np.random.RandomState(8)
+    for _ in range(40):
+        x, y = int(rng.randint(4, 92)), int(rng.randint(4, 60))
+        curve = ref.curve(1, 2, x, y)
+        mine = sc.epipolar_curve(P, 1, 2, x, y, True, 0)
+        assert curve.shape == mine.shape and (curve == mine).all()
+        for (px, py) in curve[:: max(1, len(curve) // 5)]:
+            assert ref.cost_ncc(1, 2, x, y, px, py) == sc.cost(P, 1, 2, x, y, int(px), int(py))
+    ref.close()
