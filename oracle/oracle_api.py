@@ -323,6 +323,54 @@ class RefMVS:
         return out[:min(n, max_pts)].copy()
 
 
+class RefTwoView:
+    """The REFERENCE'S OWN TwoViewStereo (stereo/twoviewstereo.cpp compiled where it lies, ref_glue_two.cpp):
+    constructor -> computeCostVolumes / computeDepthMaps.  masks: uint8 (h,w) with 255 = WHITE, or None
+    (the null QImage the reference treats as all-WHITE)."""
+
+    def __init__(self, cam_l, cam_r, img_l, img_r, mask_l, mask_r, min_depth, max_depth, num_levels, image_scale=1.0):
+        self.R = ref_lib()
+        if self.R is None:
+            raise RuntimeError("oracle/_ref/libref.so is not available")
+        self.h, self.w = img_l.shape[:2]
+        self._keep = [np.ascontiguousarray(img_l, np.uint8), np.ascontiguousarray(img_r, np.uint8),
+                      None if mask_l is None else np.ascontiguousarray(mask_l, np.uint8),
+                      None if mask_r is None else np.ascontiguousarray(mask_r, np.uint8)]
+        vp = [C.c_void_p(a.ctypes.data) if a is not None else None for a in self._keep]
+        self.R.ref_two_create.restype = C.c_void_p
+        self._h = C.c_void_p(self.R.ref_two_create(as_cam_array([cam_l]), as_cam_array([cam_r]), vp[0], vp[1], vp[2], vp[3],
+                                                   self.w, self.h, C.c_double(min_depth), C.c_double(max_depth),
+                                                   int(num_levels), C.c_double(image_scale)))
+
+    def close(self):
+        if self._h:
+            self.R.ref_two_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _two(self, fn):
+        l, r = np.empty((self.h, self.w)), np.empty((self.h, self.w))
+        fn(self._h, _dp(l), _dp(r))
+        return l, r
+
+    def search(self):
+        """computeCostVolumes: (left, right) depths before the cross-check."""
+        return self._two(self.R.ref_two_search)
+
+    def run(self):
+        """computeDepthMaps: search + cross-check."""
+        return self._two(self.R.ref_two_run)
+
+    def cost(self, sad, direction, x1, y1, x2, y2):
+        self.R.ref_two_cost.restype = C.c_double
+        return self.R.ref_two_cost(self._h, int(sad), int(direction), int(x1), int(y1), int(x2), int(y2))
+
+
 def stats_reset():
     lib().orc_stats_reset()
 

@@ -30,6 +30,13 @@
 using std::fabs;
 using std::sqrt;
 
+// The reference was written on OS X (README.md), whose C++ library declares the floating-point
+// overloads of abs in the GLOBAL namespace; glibc + libstdc++ declare only `int abs(int)` there, and
+// the unqualified abs(sum1) of stereo/twoviewstereo.cpp:976 would silently truncate its double
+// argument.  Provide what the author's toolchain provided.
+inline double abs(double x) { return std::fabs(x); }
+inline float abs(float x) { return std::fabs(x); }
+
 // glibc's <math.h> declares a one-argument ::iszero template under _GNU_SOURCE (which g++ defines),
 // ambiguous with the two-argument template of project/camera.cpp:50-53.  All standard headers are
 // included above; from here on the identifier names the reference's own function.

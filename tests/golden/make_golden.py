@@ -12,6 +12,9 @@ ref_mvs.npz       END-TO-END outputs of the reference's own MultiViewStereo clas
                   runTask() by oracle/ref_glue_mvs.cpp): neighbour lists, depths before and after the
                   cross-check, the K = 9 peak lists of one view — on the small refractive arc scene and
                   on the bunny fixture with and without the injected interface (BASELINE configs[1]).
+ref_two.npz       the same for the reference's own TwoViewStereo class (stereo/twoviewstereo.cpp): both
+                  directions of the live curve search before and after the cross-check, on the arc scene and
+                  on the bunny pair 7310085 / 7310087 with and without the interface (BASELINE configs[0]).
 oracle_scenes.npz outputs of the CPU oracle (oracle/oracle.cpp) on two small seeded scenes (a
                   masked refractive 4-view arc and a rectified pair): depth-index maps, depths,
                   winning costs, one cost volume, cross-check results.  The reference ships no
@@ -161,10 +164,28 @@ def ref_mvs():
     return out
 
 
+def ref_two():
+    """The reference's own TwoViewStereo (stereo/twoviewstereo.cpp through oracle/ref_glue_two.cpp):
+    both directions of the live curve search, before and after the cross-check."""
+    out = {}
+    for name, (a, b, mind, maxd, D) in G.REF_TWO_CASES.items():
+        cams, imgs, ms, scale = G.ref_mvs_inputs(name)
+        cams = G.settled_cameras([cams[a], cams[b]])
+        ref = O.RefTwoView(cams[0], cams[1], imgs[a], imgs[b], ms[a], ms[b], mind, maxd, D, image_scale=scale)
+        bl, br = ref.search()
+        al, ar = ref.run()
+        ref.close()
+        out[f"{name}_cams"] = G.cams_to_bytes(cams)
+        out[f"{name}_before"] = np.array([bl, br])
+        out[f"{name}_after"] = np.array([al, ar])
+    return out
+
+
 if __name__ == "__main__":
     O.build()
+    np.savez_compressed(os.path.join(HERE, "ref_two.npz"), **ref_two())
     np.savez_compressed(os.path.join(HERE, "ref_mvs.npz"), **ref_mvs())
     np.savez_compressed(os.path.join(HERE, "ref_leaves.npz"), **ref_leaves())
     np.savez_compressed(os.path.join(HERE, "oracle_scenes.npz"), **oracle_scenes())
-    for f in ("ref_leaves.npz", "oracle_scenes.npz", "ref_mvs.npz"):
+    for f in ("ref_leaves.npz", "oracle_scenes.npz", "ref_mvs.npz", "ref_two.npz"):
         print(f, os.path.getsize(os.path.join(HERE, f)), "bytes")

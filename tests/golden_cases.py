@@ -160,3 +160,11 @@ def ref_mvs_inputs(name):
     from bunny_util import load
     cams, imgs, ms, scale = load(refractive=(name == "bunny_refr"))
     return cams, imgs, ms, scale
+
+
+REF_TWO_CASES = {
+    # name: (left view, right view, min depth, max depth, levels); r = 5 GeodesicWeight NCC, cross-check 1 (the class's constants)
+    "arc": (1, 2, 420.0, 580.0, 32),
+    "bunny": (0, 1, 300.0, 800.0, 100),       # cameras 7310085 + 7310087
+    "bunny_refr": (0, 1, 300.0, 800.0, 100),
+}

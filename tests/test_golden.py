@@ -202,6 +202,52 @@ def test_gpu_curve_mode_matches_reference_mvs_golden(ref_mvs_gold, gpu_ctx, name
         assert ok.mean() >= 1 - 2e-4, (v, 1 - ok.mean())
 
 
+@pytest.fixture(scope="module")
+def ref_two_gold():
+    return np.load(os.path.join(GOLD, "ref_two.npz"))
+
+
+@pytest.mark.parametrize("name", list(G.REF_TWO_CASES))
+def test_oracle_matches_reference_twoview_golden(ref_two_gold, name):
+    """The oracle against the committed END-TO-END outputs of the reference's own TwoViewStereo class
+    (both directions of the live curve search before and after the cross-check)."""
+    g = ref_two_gold
+    a, b, mind, maxd, D = G.REF_TWO_CASES[name]
+    _, imgs, ms, scale = G.ref_mvs_inputs(name)
+    cams = G.cams_from_bytes(g[f"{name}_cams"])
+    sc = O.Scene(cams, [imgs[a], imgs[b]], [ms[a], ms[b]])
+    P = T.default_params(False, mind, maxd, D, image_scale=scale)
+    rel = 0.0 if name == "arc" else 1e-12
+    ol, _, _ = sc.twoview_curve(P, 0, 1, root_mode=0)
+    orr, _, _ = sc.twoview_curve(P, 1, 0, root_mode=0)
+    assert _depth_close(ol, g[f"{name}_before"][0], rel).mean() >= 1 - 1e-4
+    assert _depth_close(orr, g[f"{name}_before"][1], rel).mean() >= 1 - 1e-4
+    wl, wr = sc.crosscheck_two(P, 0, 1, g[f"{name}_before"][0], g[f"{name}_before"][1], 1.0, root_mode=0)
+    assert _same(wl, g[f"{name}_after"][0]) and _same(wr, g[f"{name}_after"][1])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", list(G.REF_TWO_CASES))
+def test_gpu_twoview_curve_matches_reference_golden(ref_two_gold, gpu_ctx, name):
+    """The CUDA path (sr_run_view_curve in both directions with the two-view selection, then sr_cross_check)
+    against the END-TO-END outputs of the reference's own TwoViewStereo::computeDepthMaps."""
+    g = ref_two_gold
+    a, b, mind, maxd, D = G.REF_TWO_CASES[name]
+    _, imgs, ms, scale = G.ref_mvs_inputs(name)
+    cams = G.cams_from_bytes(g[f"{name}_cams"])
+    gpu_ctx.set_views(cams, [imgs[a], imgs[b]], [ms[a], ms[b]])
+    gpu_ctx.set_params(T.default_params(False, mind, maxd, D, image_scale=scale))
+    gpu_ctx.run_view_curve(0, [1])
+    gpu_ctx.run_view_curve(1, [0])
+    for v in (0, 1):
+        ok = _depth_close(gpu_ctx.depth(v), g[f"{name}_before"][v], 1e-9)
+        assert ok.mean() >= 1 - 1e-4, (v, 1 - ok.mean())
+    gpu_ctx.cross_check(True, 1.0)
+    for v in (0, 1):
+        ok = _depth_close(gpu_ctx.depth(v), g[f"{name}_after"][v], 1e-9)
+        assert ok.mean() >= 1 - 2e-4, (v, 1 - ok.mean())
+
+
 def _camera_golden_check(leaves, i, rays, xy, ok, tol_ray=1e-12, tol_px=1e-8):
     gr, gxy, gok = leaves[f"cam{i}_rays"], leaves[f"cam{i}_xy"], leaves[f"cam{i}_ok"]
     assert np.abs(rays - gr).max() <= tol_ray * max(1.0, np.abs(gr).max())

@@ -256,3 +256,39 @@ def test_mvs_end_to_end_matches_reference():
         for (px, py) in curve[:: max(1, len(curve) // 5)]:
             assert ref.cost_ncc(1, 2, x, y, px, py) == sc.cost(P, 1, 2, x, y, int(px), int(py))
     ref.close()
+
+
+# ---- stereo/twoviewstereo.cpp: the reference's own TwoViewStereo, end to end ----------------------------
+def test_twoview_end_to_end_matches_reference():
+    """constructor -> computeCostVolumes -> crossCheck of the reference's own class (live rasterised-curve
+    search with the second-best test in both directions, cross-check; twoviewstereo.cpp:89-124,233-500,
+    596-672) and its two cost functions (cost_ncc :909-977, cost_sad :864-905, windows over borders and
+    masked pixels included): the oracle reproduces every output BIT FOR BIT.  (The reference's unqualified
+    abs(sum1) is the floating overload of its author's toolchain: ref_shim/precompiled_shim.hpp.)"""
+    import golden_cases as G
+    from stereoreconstruction_b200 import types as T
+    cams, imgs, ms = G.arc_scene()
+    a, b, mind, maxd, D = G.REF_TWO_CASES["arc"]
+    ref = O.RefTwoView(cams[a], cams[b], imgs[a], imgs[b], ms[a], ms[b], mind, maxd, D)
+    bl, br = ref.search()
+    sc = O.Scene(cams, imgs, ms)
+    P = T.default_params(False, mind, maxd, D)
+    ol, _, cl = sc.twoview_curve(P, a, b, root_mode=0)
+    orr, _, _ = sc.twoview_curve(P, b, a, root_mode=0)
+
+    def same(x, y):
+        return ((x == y) | (np.isnan(x) & np.isnan(y))).all()
+    assert same(bl, ol) and same(br, orr)
+    assert np.isfinite(ol).mean() > 0.3 and np.isinf(ol).any() and cl.max() > 5
+    al, ar = ref.run()
+    wl, wr = sc.crosscheck_two(P, a, b, ol, orr, 1.0, root_mode=0)
+    assert same(al, wl) and same(ar, wr)
+    rng = np.random.RandomState(1)
+    for _ in range(150):
+        x1, y1 = int(rng.randint(0, 96)), int(rng.randint(0, 64))
+        x2, y2 = int(rng.randint(-3, 99)), int(rng.randint(-3, 67))
+        for sad, kind in ((0, T.SR_COST_NCC_TWOVIEW), (1, T.SR_COST_SAD_TWOVIEW)):
+            P2 = T.default_params(False, mind, maxd, D, cost_kind=kind)
+            r_, o_ = ref.cost(sad, 0, x1, y1, x2, y2), sc.cost(P2, a, b, x1, y1, x2, y2)
+            assert r_ == o_ or (np.isnan(r_) and np.isnan(o_)), (sad, x1, y1, x2, y2, r_, o_)
+    ref.close()
