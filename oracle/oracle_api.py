@@ -313,6 +313,17 @@ class RefMVS:
         self.R.ref_mvs_initial_estimate(self._h, int(view), _dp(d), _dp(pk))
         return d, pk
 
+    def set_neighbours(self, view, nbrs):
+        nb = np.ascontiguousarray(nbrs, dtype=np.int32)
+        self.R.ref_mvs_set_neighbours(self._h, int(view), _ip(nb), int(nb.size))
+
+    def mask_rows(self, view, row_begin, row_end):
+        """Reduce the view's mask to rows [row_begin, row_end): the class skips pixels outside its mask."""
+        self.R.ref_mvs_mask_rows(self._h, int(view), int(row_begin), int(row_end))
+
+    def num_threads(self):
+        return self.R.ref_mvs_num_threads()
+
     def cost_ncc(self, a, b, x1, y1, x2, y2):
         self.R.ref_mvs_cost_ncc.restype = C.c_double
         return self.R.ref_mvs_cost_ncc(self._h, a, b, int(x1), int(y1), int(x2), int(y2))

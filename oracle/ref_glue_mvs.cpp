@@ -5,7 +5,9 @@
 // result — neighbour selection, rasterised epipolar curves, weighted NCC, the K = 9 peak lists, the
 // selection rule and the cross-check — to pin oracle/oracle.cpp against.  This file contains no
 // reference code: the translation unit includes the reference's .cpp so that its file-local
-// functions (cost_ncc) and the class's protected members can be called from here.
+// functions (cost_ncc) and the class's protected members can be called from here.  Built with
+// -DUSE_TBB: the reference's own tbb::parallel_for over image rows (multiviewstereo.cpp:548,675) is what
+// parallelises it (ref_shim/tbb/tbb.h stands in for the library).
 #define private public
 #define protected public
 #include "stereo/multiviewstereo.cpp"
@@ -13,6 +15,9 @@
 #undef protected
 #include <cstdint>
 #include <cstring>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
 
 // What moc would generate for Task's signals (gui/task.hpp:87-97): nobody is connected.
 void Task::started(const Task *) {}
@@ -114,6 +119,27 @@ void ref_mvs_initial_estimate(ref_mvs *m, int view, double *depth, double *peaks
             }
     }
 }
+// bench.py --impl reference: time computeInitialEstimate on a bounded sample without running the
+// whole task.  The neighbour lists are handed over (runTask's rule, :335-360, is not separately
+// callable; the caller's lists are checked equal to it in tests/test_oracle_vs_ref.py), and the
+// reference view's mask is reduced to a row band — the class skips pixels outside its mask (:565).
+void ref_mvs_set_neighbours(ref_mvs *m, int view, const int32_t *nbrs, int n) {
+    m->task.neighbours[view].assign(nbrs, nbrs + n);
+}
+void ref_mvs_mask_rows(ref_mvs *m, int view, int row_begin, int row_end) {
+    VectorImage &mask = m->task.masks[view];
+    for (int y = 0; y < mask.height(); ++y)
+        if (y < row_begin || y >= row_end)
+            for (int x = 0; x < mask.width(); ++x) mask.setPixel(x, y, BLACK);
+}
+int ref_mvs_num_threads() {
+#ifdef _OPENMP
+    return omp_get_max_threads();
+#else
+    return 1;
+#endif
+}
+
 // cost_ncc (:113-189) of view a's pixel (x1,y1) against view b's pixel (x2,y2), GeodesicWeight r = 2
 double ref_mvs_cost_ncc(ref_mvs *m, int a, int b, int x1, int y1, int x2, int y2) {
     WeightFunc wf(WINDOW_RADIUS);
