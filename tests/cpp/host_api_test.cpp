@@ -4,6 +4,9 @@
 // results for tests/test_host_api.py to compare against the C ABI called directly and the oracle.
 //
 //   host_api_test <project.xml> <imageSetId> <outdir> <minDepth> <maxDepth> <levels> <crossCheck>
+//   host_api_test --cameras <project.xml> <outdir>
+//       no GPU needed: loads the project and dumps every camera's sr_camera POD (Camera::setP ->
+//       updateOthers, lens distortion, interface) to <outdir>/cams.bin, ordered by camera id
 //   host_api_test --calibrate <project.xml> <problem.bin> <outdir>
 //       RefractionCalibration over the project's cameras; problem.bin = int32 n, int32 flags
 //       (1: reference gradient attribution, 2: literal solve check), int32 pairs[2n],
@@ -78,6 +81,19 @@ static int calibrate_main(const char *xml, const char *problem, const std::strin
 }
 
 int main(int argc, char **argv) {
+    if (argc == 4 && std::string(argv[1]) == "--cameras") {
+        try {
+            ProjectPtr project(new Project(argv[2]));
+            std::vector<sr_camera> pods;
+            for (const auto &kv : project->cameras()) pods.push_back(kv.second->toPod());
+            dump(std::string(argv[3]) + "/cams.bin", pods.data(), pods.size());
+            std::printf("cameras: %zu\n", pods.size());
+            return 0;
+        } catch (const std::exception &e) {
+            std::fprintf(stderr, "host_api_test: %s\n", e.what());
+            return 1;
+        }
+    }
     if (argc == 5 && std::string(argv[1]) == "--calibrate") {
         try {
             return calibrate_main(argv[2], argv[3], argv[4]);
