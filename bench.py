@@ -423,6 +423,16 @@ def main():
                 "depth_equal_where_index_equal": bool(((gd == o["depth"]) | (np.isnan(gd) & np.isnan(o["depth"])))[~mism].all()),
                 "max_rel_cost_diff": float(rel.max()) if rel.size else None, "labelled_fraction": float(lab.mean()),
             }
+        # ... and the reference's own MultiViewStereo (oracle/_ref, when the prebuilt library is there) on a band
+        # of the same view: its live curve formulation, timed beside the port (optional: never fails the line)
+        try:
+            got = reference_sample(wl, imgs, 0, target_s=8.0)
+        except Exception as e:  # noqa: BLE001
+            got = None
+            cpu["reference_itself"] = {"unavailable": str(e)[:200]}
+        if got:
+            cpu["reference_itself"] = {"value": got[0], "unit": UNIT, "cores": got[2], "kind": "reference",
+                                       "sample": got[3], "seconds": got[1]}
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
