@@ -220,13 +220,16 @@ def test_camera_from_projection_matrix_matches_reference():
 
 
 # ---- stereo/multiviewstereo.cpp: the reference's own MultiViewStereo, end to end ---------------------
-def test_mvs_end_to_end_matches_reference():
+@pytest.mark.parametrize("interface,distortion", [(True, True), (False, True), (False, False)])
+def test_mvs_end_to_end_matches_reference(interface, distortion):
     """initialize() -> runTask() of the reference's own class (neighbour rule, rasterised epipolar curves,
     weighted NCC, K = 9 peak lists, selection, cross-check; multiviewstereo.cpp:193-247,325-475,524-810) on a
-    refractive, lens-distorted, masked 4-view scene: the oracle reproduces every output BIT FOR BIT."""
+    masked 4-view scene — refractive + lens-distorted, air + distorted, air + pinhole: the oracle reproduces
+    every output BIT FOR BIT."""
     import golden_cases as G
     from stereoreconstruction_b200 import types as T
-    cams, imgs, ms = G.arc_scene()
+    from scene_util import refractive_arc_scene
+    cams, imgs, ms, _ = refractive_arc_scene(V=4, w=96, h=64, masks=True, interface=interface, distortion=distortion)
     mind, maxd, D, cross = G.REF_MVS_CASES["arc"]
     ref = O.RefMVS(cams, imgs, ms, mind, maxd, D, cross)
     after, nb = ref.run()
@@ -259,7 +262,8 @@ def test_mvs_end_to_end_matches_reference():
 
 
 # ---- stereo/twoviewstereo.cpp: the reference's own TwoViewStereo, end to end ----------------------------
-def test_twoview_end_to_end_matches_reference():
+@pytest.mark.parametrize("interface,distortion", [(True, True), (False, False)])
+def test_twoview_end_to_end_matches_reference(interface, distortion):
     """constructor -> computeCostVolumes -> crossCheck of the reference's own class (live rasterised-curve
     search with the second-best test in both directions, cross-check; twoviewstereo.cpp:89-124,233-500,
     596-672) and its two cost functions (cost_ncc :909-977, cost_sad :864-905, windows over borders and
@@ -267,7 +271,8 @@ def test_twoview_end_to_end_matches_reference():
     abs(sum1) is the floating overload of its author's toolchain: ref_shim/precompiled_shim.hpp.)"""
     import golden_cases as G
     from stereoreconstruction_b200 import types as T
-    cams, imgs, ms = G.arc_scene()
+    from scene_util import refractive_arc_scene
+    cams, imgs, ms, _ = refractive_arc_scene(V=4, w=96, h=64, masks=True, interface=interface, distortion=distortion)
     a, b, mind, maxd, D = G.REF_TWO_CASES["arc"]
     ref = O.RefTwoView(cams[a], cams[b], imgs[a], imgs[b], ms[a], ms[b], mind, maxd, D)
     bl, br = ref.search()
