@@ -17,8 +17,9 @@
 // tests/golden/ref_*.npz hold the reference's outputs for machines without /root/reference.
 // Not the reference's own: Qt, Project/ImageSet, Eigen's fixed-size matrices and the one GSL call are
 // stand-ins (ref_shim/); the reference's label-mode branch is compiled out in the reference itself
-// (twoviewstereo.cpp:283,308-329), so label mode is pinned through the pieces it shares with the
-// live curve mode (projection, costs, weights, selection) and the oracle's own consistency tests.
+// (twoviewstereo.cpp:283,308-329), so label mode is pinned by composing it, in the tests, from the
+// reference's own compiled pieces (unproject, intersect, project, cost_ncc) for a pixel sample:
+// index, depth and winning cost equal this restatement's label mode exactly.
 //
 // Third-party arithmetic not in /root/reference: GSL 1.14 gsl_poly_complex_solve
 // (project/camera.cpp:77-80): eigenvalues of the balanced companion matrix by Hessenberg QR.

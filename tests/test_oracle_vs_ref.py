@@ -297,3 +297,118 @@ def test_twoview_end_to_end_matches_reference(interface, distortion):
             r_, o_ = ref.cost(sad, 0, x1, y1, x2, y2), sc.cost(P2, a, b, x1, y1, x2, y2)
             assert r_ == o_ or (np.isnan(r_) and np.isnan(o_)), (sad, x1, y1, x2, y2, r_, o_)
     ref.close()
+
+
+def test_label_mode_is_the_reference_pieces_composed():
+    """The depth-label sweep (north_star's cost volume + WTA) is compiled out of the reference
+    (twoviewstereo.cpp:283,308-329), so it cannot be run there.  Here it is COMPOSED from the reference's own
+    compiled pieces — Camera::unproject, intersect (pointFromDepth), Camera::project, the MultiViewStereo
+    cost_ncc — with only the loop and the selection rule (multiviewstereo.cpp:589-602,654-660) written in
+    this test, for 120 random pixels: index, depth and winning cost equal the oracle's label mode."""
+    import golden_cases as G
+    from stereoreconstruction_b200 import types as T
+    cams, imgs, ms = G.arc_scene()
+    mind, maxd, D, cross = G.REF_MVS_CASES["arc"]
+    P = T.default_params(True, mind, maxd, D)
+    sc = O.Scene(cams, imgs, ms)
+    ref_view = 1
+    nb = [int(v) for v in sc.select_neighbours(3)[ref_view]]
+    od, oi, ob, _, _ = sc.mvs_view(P, ref_view, nb, root_mode=0)
+    ref = O.RefMVS(cams, imgs, ms, mind, maxd, D, cross)
+    L = O.lib()
+    L.orc_depth_from_label.restype = C.c_double
+    pp = O.as_params(P)
+    depths = np.array([L.orc_depth_from_label(C.byref(pp), d) for d in range(D)])
+    cam = cams[ref_view]
+    n = np.array(cam.prin_dir[:])
+    n = n / np.sqrt(n.dot(n))
+    Cc = np.array(cam.C[:])
+    rng = np.random.RandomState(12)
+    ys, xs = np.nonzero(ms[ref_view] == 255)
+    pick = rng.choice(len(ys), 120, replace=False)
+    h, w = ms[0].shape
+    checked = labelled = 0
+    for y, x in zip(ys[pick], xs[pick]):
+        ray = np.empty(6)
+        REF.ref_camera_unproject(_pod(cam), 1, _dp(np.array([x + 0.5, y + 0.5])), _dp(ray))
+        best = None  # (cost, depth, label)
+        for j in nb:
+            pts, ok = np.empty((D, 3)), np.zeros(D, bool)
+            for d in range(D):
+                x0 = Cc + n * depths[d]
+                out3 = np.empty(3)
+                ok[d] = REF.ref_intersect(_dp(ray[:3].copy()), _dp(ray[3:].copy()), _dp(n.copy()), C.c_double(n.dot(x0)), _dp(out3)) != 0
+                pts[d] = out3
+            xy, pok = np.empty((D, 2)), np.empty(D, np.int32)
+            REF.ref_camera_project(_pod(cams[j]), D, _dp(np.ascontiguousarray(pts)), _dp(xy), _ip(pok))
+            for d in range(D):
+                if not ok[d] or not pok[d]:
+                    continue
+                tx, ty = int(xy[d, 0]), int(xy[d, 1])  # truncation, multiviewstereo.cpp:773-775
+                if not (0 <= tx < w and 0 <= ty < h) or ms[j][ty, tx] != 255:
+                    continue
+                cost = ref.cost_ncc(ref_view, j, int(x), int(y), tx, ty)
+                if cost > 0.95 and (best is None or (cost, depths[d]) > best[:2]):
+                    best = (cost, depths[d], d)
+        checked += 1
+        if best is None:
+            assert oi[y, x] == -1 and od[y, x] == -1
+        else:
+            labelled += 1
+            assert oi[y, x] == best[2] and od[y, x] == best[1] and ob[y, x] == best[0], (x, y, best, oi[y, x], ob[y, x])
+    assert checked == 120 and labelled > 30
+    ref.close()
+
+
+def test_twoview_label_mode_is_the_reference_pieces_composed():
+    """The same for the two-view label sweep (twoviewstereo.cpp:308-329 — the compiled-out branch — with the
+    live path's second-best test :304-305): Camera::unproject, intersect, Camera::project and
+    TwoViewStereo::cost_ncc are the reference's own compiled code; the loop, the tap rule
+    (x*scale - 0.5, truncated by the callee's int parameters) and the selection are written here."""
+    import golden_cases as G
+    from stereoreconstruction_b200 import types as T
+    cams, imgs, ms = G.arc_scene()
+    a, b, mind, maxd, D = G.REF_TWO_CASES["arc"]
+    P = T.default_params(False, mind, maxd, D)
+    sc = O.Scene(cams, imgs, ms)
+    od, oi, ob, _ = sc.twoview_label(P, a, b, root_mode=0)
+    ref = O.RefTwoView(cams[a], cams[b], imgs[a], imgs[b], ms[a], ms[b], mind, maxd, D)
+    L = O.lib()
+    L.orc_depth_from_label.restype = C.c_double
+    pp = O.as_params(P)
+    depths = np.array([L.orc_depth_from_label(C.byref(pp), d) for d in range(D)])
+    cam = cams[a]
+    n = np.array(cam.prin_dir[:])
+    n = n / np.sqrt(n.dot(n))
+    Cc = np.array(cam.C[:])
+    rng = np.random.RandomState(13)
+    ys, xs = np.nonzero(ms[a] == 255)
+    pick = rng.choice(len(ys), 60, replace=False)
+    finite = 0
+    for y, x in zip(ys[pick], xs[pick]):
+        ray = np.empty(6)
+        REF.ref_camera_unproject(_pod(cam), 1, _dp(np.array([x + 0.5, y + 0.5])), _dp(ray))
+        pts, ok = np.empty((D, 3)), np.zeros(D, bool)
+        for d in range(D):
+            out3 = np.empty(3)
+            ok[d] = REF.ref_intersect(_dp(ray[:3].copy()), _dp(ray[3:].copy()), _dp(n.copy()),
+                                      C.c_double(n.dot(Cc + n * depths[d])), _dp(out3)) != 0
+            pts[d] = out3
+        xy, pok = np.empty((D, 2)), np.empty(D, np.int32)
+        REF.ref_camera_project(_pod(cams[b]), D, _dp(np.ascontiguousarray(pts)), _dp(xy), _ip(pok))
+        min_cost, second, depth, index = np.inf, np.inf, np.nan, -1
+        for d in range(D):
+            if not ok[d] or not pok[d]:
+                continue
+            cost = ref.cost(0, 0, int(x), int(y), int(xy[d, 0] - 0.5), int(xy[d, 1] - 0.5))
+            if cost + 1e-10 < min_cost:
+                second, min_cost, depth, index = min_cost, cost, depths[d], d
+        if index >= 0 and min_cost > 0.95 * second:
+            depth, index = np.inf, -3
+        assert oi[y, x] == index, (x, y, index, oi[y, x])
+        assert (od[y, x] == depth) or (np.isnan(depth) and np.isnan(od[y, x]))
+        if index != -1:
+            assert ob[y, x] == min_cost
+        finite += np.isfinite(depth)
+    assert finite > 10
+    ref.close()
