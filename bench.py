@@ -400,7 +400,7 @@ def main():
         "achieved": achieved, "peak": peak_gbs, "unit": "GB/s", "frac": achieved / peak_gbs, "traffic": traffic,
         "peak_source": peak_src, "match_ms_per_view": match_ms, "build_ms_per_view": build_ms,
         "pipeline_achieved_gbs": pipe_gbs, "pipeline_frac": pipe_gbs / peak_gbs,
-        "binding_bound": ("instruction issue / latency, not HBM: ~170 warp-instructions per (pixel, label, neighbour) in the "
+        "binding_bound": ("instruction issue / latency, not HBM: ~165 warp-instructions per (pixel, label, neighbour) in the "
                           "match kernel and ~210 in the refractive build (profiles/, DESIGN.md section 5); HBM sees "
                           "only the 4-byte tap per (pixel, label, neighbour)"),
     }
