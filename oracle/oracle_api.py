@@ -269,10 +269,13 @@ class RefMVS:
     runTask().  images: RGBA8 (h,w,4); masks: uint8 (h,w), 255 = WHITE, written into the alpha byte
     the reference reads its mask from."""
 
-    def __init__(self, cams, images, masks, min_depth, max_depth, num_levels, cross_check, image_scale=1.0):
+    def __init__(self, cams, images, masks, min_depth, max_depth, num_levels, cross_check, image_scale=1.0, adaptive=False):
+        """adaptive=True: the build of the same reference file whose `WeightFunc` typedef names AdaptiveWeight
+        (ref_glue_mvs_ada.cpp) instead of GeodesicWeight."""
         self.R = ref_lib()
         if self.R is None:
             raise RuntimeError("oracle/_ref/libref.so is not available")
+        self._p = "ref_mvsa_" if adaptive else "ref_mvs_"
         self.V = len(cams)
         self.h, self.w = images[0].shape[:2]
         self._rgba = []
@@ -281,15 +284,18 @@ class RefMVS:
             a[..., 3] = 255 if m is None else m
             self._rgba.append(a)
         ptrs = (C.c_void_p * self.V)(*[a.ctypes.data for a in self._rgba])
-        self.R.ref_mvs_create.restype = C.c_void_p
-        self._h = C.c_void_p(self.R.ref_mvs_create(self.V, as_cam_array(cams), ptrs, self.w, self.h, C.c_double(min_depth),
+        self._f('create').restype = C.c_void_p
+        self._h = C.c_void_p(self._f('create')(self.V, as_cam_array(cams), ptrs, self.w, self.h, C.c_double(min_depth),
                                                    C.c_double(max_depth), int(num_levels), C.c_double(cross_check),
                                                    C.c_double(image_scale)))
-        assert self.R.ref_mvs_num_views(self._h) == self.V
+        assert self._f('num_views')(self._h) == self.V
+
+    def _f(self, name):
+        return getattr(self.R, self._p + name)
 
     def close(self):
         if self._h:
-            self.R.ref_mvs_destroy(self._h)
+            self._f('destroy')(self._h)
             self._h = None
 
     def __del__(self):
@@ -302,7 +308,7 @@ class RefMVS:
         """runTask(): (depths after the cross-check (V,h,w), neighbour lists)."""
         after = np.empty((self.V, self.h, self.w))
         nb = np.empty((self.V, 3), np.int32)
-        self.R.ref_mvs_run(self._h, _dp(after), _ip(nb))
+        self._f('run')(self._h, _dp(after), _ip(nb))
         return after, [[int(v) for v in row if v >= 0] for row in nb]
 
     def initial_estimate(self, view):
@@ -310,27 +316,27 @@ class RefMVS:
         the cross-check (h,w) and the K = 9 peak pairs (h,w,9,2)."""
         d = np.empty((self.h, self.w))
         pk = np.empty((self.h, self.w, 9, 2))
-        self.R.ref_mvs_initial_estimate(self._h, int(view), _dp(d), _dp(pk))
+        self._f('initial_estimate')(self._h, int(view), _dp(d), _dp(pk))
         return d, pk
 
     def set_neighbours(self, view, nbrs):
         nb = np.ascontiguousarray(nbrs, dtype=np.int32)
-        self.R.ref_mvs_set_neighbours(self._h, int(view), _ip(nb), int(nb.size))
+        self._f('set_neighbours')(self._h, int(view), _ip(nb), int(nb.size))
 
     def mask_rows(self, view, row_begin, row_end):
         """Reduce the view's mask to rows [row_begin, row_end): the class skips pixels outside its mask."""
-        self.R.ref_mvs_mask_rows(self._h, int(view), int(row_begin), int(row_end))
+        self._f('mask_rows')(self._h, int(view), int(row_begin), int(row_end))
 
     def num_threads(self):
-        return self.R.ref_mvs_num_threads()
+        return self._f('num_threads')()
 
     def cost_ncc(self, a, b, x1, y1, x2, y2):
-        self.R.ref_mvs_cost_ncc.restype = C.c_double
-        return self.R.ref_mvs_cost_ncc(self._h, a, b, int(x1), int(y1), int(x2), int(y2))
+        self._f('cost_ncc').restype = C.c_double
+        return self._f('cost_ncc')(self._h, a, b, int(x1), int(y1), int(x2), int(y2))
 
     def curve(self, a, b, x, y, max_pts=1 << 14):
         out = np.empty((max_pts, 2), np.int32)
-        n = self.R.ref_mvs_curve(self._h, a, b, int(x), int(y), _ip(out), max_pts)
+        n = self._f('curve')(self._h, a, b, int(x), int(y), _ip(out), max_pts)
         return out[:min(n, max_pts)].copy()
 
 

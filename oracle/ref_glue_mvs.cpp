@@ -19,11 +19,13 @@
 #include <omp.h>
 #endif
 
+#ifndef REF_MVS_ADAPTIVE_TU  // (ref_glue_mvs_ada.cpp compiles this file a second time, see there)
 // What moc would generate for Task's signals (gui/task.hpp:87-97): nobody is connected.
 void Task::started(const Task *) {}
 void Task::finished(const Task *) {}
 void Task::progressUpdate(int) {}
 void Task::stageUpdate(QString) {}
+#endif
 
 namespace {
 struct cam_pod {  // == oracle.cpp: struct Camera == include/sr_b200.h: sr_camera

@@ -148,7 +148,7 @@ def ref_mvs():
     for name, (mind, maxd, D, cross) in G.REF_MVS_CASES.items():
         cams, imgs, ms, scale = G.ref_mvs_inputs(name)
         cams = G.settled_cameras(cams)
-        ref = O.RefMVS(cams, imgs, ms, mind, maxd, D, cross, image_scale=scale)
+        ref = O.RefMVS(cams, imgs, ms, mind, maxd, D, cross, image_scale=scale, adaptive=G.ref_mvs_adaptive(name))
         after, nb = ref.run()
         out[f"{name}_cams"] = G.cams_to_bytes(cams)
         out[f"{name}_neighbours"] = np.array([r + [-1] * (3 - len(r)) for r in nb], np.int32)

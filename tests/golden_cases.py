@@ -149,11 +149,20 @@ REF_MVS_CASES = {
     "arc": (420.0, 580.0, 40, 12.0),
     "bunny": (300.0, 800.0, 100, 5.0),        # README.md:103-112 / SURVEY 8d cfg2
     "bunny_refr": (300.0, 800.0, 100, 5.0),   # ... with the injected interface
+    # the same reference file built with `typedef AdaptiveWeight WeightFunc` (BASELINE configs[1]: adaptive-weight aggregation)
+    "arc_ada": (420.0, 580.0, 40, 12.0),
+    "bunny_refr_ada": (300.0, 800.0, 100, 5.0),
 }
+
+
+def ref_mvs_adaptive(name):
+    return name.endswith("_ada")
 
 
 def ref_mvs_inputs(name):
     """(cams, images, masks, image_scale) of a reference end-to-end case (cameras NOT yet settled)."""
+    if name.endswith("_ada"):
+        name = name[:-4]
     if name == "arc":
         cams, imgs, ms = arc_scene()
         return cams, imgs, ms, 1.0

@@ -220,8 +220,9 @@ def test_camera_from_projection_matrix_matches_reference():
 
 
 # ---- stereo/multiviewstereo.cpp: the reference's own MultiViewStereo, end to end ---------------------
+@pytest.mark.parametrize("adaptive", [False, True])
 @pytest.mark.parametrize("interface,distortion", [(True, True), (False, True), (False, False)])
-def test_mvs_end_to_end_matches_reference(interface, distortion):
+def test_mvs_end_to_end_matches_reference(interface, distortion, adaptive):
     """initialize() -> runTask() of the reference's own class (neighbour rule, rasterised epipolar curves,
     weighted NCC, K = 9 peak lists, selection, cross-check; multiviewstereo.cpp:193-247,325-475,524-810) on a
     masked 4-view scene — refractive + lens-distorted, air + distorted, air + pinhole: the oracle reproduces
@@ -231,10 +232,11 @@ def test_mvs_end_to_end_matches_reference(interface, distortion):
     from scene_util import refractive_arc_scene
     cams, imgs, ms, _ = refractive_arc_scene(V=4, w=96, h=64, masks=True, interface=interface, distortion=distortion)
     mind, maxd, D, cross = G.REF_MVS_CASES["arc"]
-    ref = O.RefMVS(cams, imgs, ms, mind, maxd, D, cross)
+    # adaptive: the reference file built with `typedef AdaptiveWeight WeightFunc` (BASELINE configs[1])
+    ref = O.RefMVS(cams, imgs, ms, mind, maxd, D, cross, adaptive=adaptive)
     after, nb = ref.run()
     sc = O.Scene(cams, imgs, ms)
-    P = T.default_params(True, mind, maxd, D)
+    P = T.default_params(True, mind, maxd, D, weight_kind=T.SR_WEIGHT_ADAPTIVE if adaptive else T.SR_WEIGHT_GEODESIC)
     assert nb == [[int(v) for v in r] for r in sc.select_neighbours(3)]
     before = []
     for v in range(len(cams)):
