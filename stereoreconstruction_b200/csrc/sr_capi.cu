@@ -27,6 +27,7 @@ struct ViewDev {
     uint8_t *mask = nullptr;
     double *gray_pix = nullptr, *gray_two = nullptr, *gray_msk = nullptr, *edges = nullptr;
     float *gray_pix_f = nullptr;
+    float *gray_pix_f4 = nullptr;  // four shifted copies of gray_pix_f (sr_screen2.cuh)
     bool have_image = false; // sr_set_views received pixels for this view
     bool all_white = false;  // no mask was passed for this view: every pixel is WHITE
     double *rays = nullptr;  // [6][h][w] Camera::unproject of every pixel centre (curve mode), lazily
@@ -155,6 +156,7 @@ void free_views(sr_ctx *c) {
         dfree(v.mask);
         dfree(v.gray_pix);
         dfree(v.gray_pix_f);
+        dfree(v.gray_pix_f4);
         dfree(v.rays);
         dfree(v.gray_two);
         dfree(v.gray_msk);
@@ -310,6 +312,8 @@ int sr_set_views(sr_ctx *ctx, int V, const sr_camera *cams, const uint8_t *const
             CK(cudaMalloc(&v.mask, n));
             CK(cudaMalloc(&v.gray_pix, n * 8));
             CK(cudaMalloc(&v.gray_pix_f, (size_t)screen_pitch(w) * h * 4));
+            CK(cudaMalloc(&v.gray_pix_f4, (size_t)screen_plane4_stride(w, h) * 4 * 4));
+            CK(cudaMemsetAsync(v.gray_pix_f4, 0, (size_t)screen_plane4_stride(w, h) * 4 * 4, ctx->stream));  // the shift margins
             CK(cudaMalloc(&v.gray_two, n * 8));
             CK(cudaMalloc(&v.gray_msk, n * 8));
             CK(cudaMalloc(&v.edges, n * 8 * 4));
@@ -340,7 +344,8 @@ int sr_set_views(sr_ctx *ctx, int V, const sr_camera *cams, const uint8_t *const
         if (!v.all_white) CK(cudaMemcpyAsync(v.mask, mask8[i], n, cudaMemcpyHostToDevice, ctx->stream));
         else CK(cudaMemsetAsync(v.mask, 255, n, ctx->stream));
         prep_view_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(v.rgba, v.mask, w, h, v.gray_pix,
-                                                                             v.gray_two, v.gray_msk, v.edges, v.gray_pix_f, screen_pitch(w));
+                                                                             v.gray_two, v.gray_msk, v.edges, v.gray_pix_f, screen_pitch(w),
+                                                                             v.gray_pix_f4, screen_plane4_stride(w, h));
         CKL();
         // results start as "not computed": NaN depth (twoviewstereo.cpp:118-119), index NONE
         CK(cudaMemsetAsync(v.depth, 0xff, n * 8, ctx->stream));
@@ -563,8 +568,10 @@ int sr_run_view(sr_ctx *ctx, int ref, const int32_t *nbrs, int nn) {
             ma.grayR[j] = (P.cost_kind == SR_COST_NCC_MVS) ? B.gray_pix
                           : (P.cost_kind == SR_COST_NCC_TWOVIEW) ? B.gray_two : B.gray_msk;
             ma.grayRf[j] = B.gray_pix_f;
+            ma.grayRf4[j] = B.gray_pix_f4;
         }
         ma.pitch_f = screen_pitch(w);
+        ma.plane4_stride = screen_plane4_stride(w, h);
         ma.taps = ctx->d_taps;
         ma.depth_table = ctx->d_depth_table;
         ma.out_index = A.index;
@@ -573,8 +580,8 @@ int sr_run_view(sr_ctx *ctx, int ref, const int32_t *nbrs, int nn) {
         ma.out_volume = (P.keep_cost_volume & 1) ? ctx->d_volume : nullptr;
         ma.out_peaks = (P.keep_cost_volume & 2) ? ctx->d_peaks : nullptr;
         ma.w = w;
-        ma.win_w = w - 2 * P.radius;
-        ma.win_h = h - 2 * P.radius;
+        ma.win_w = std::max(0, w - 2 * P.radius);  // (compared as unsigned: an image smaller than the window has no interior)
+        ma.win_h = std::max(0, h - 2 * P.radius);
         ma.h = h;
         ma.row0 = b0;
         ma.rows = rows;
@@ -809,9 +816,11 @@ int sr_run_view_curve(sr_ctx *ctx, int ref, const int32_t *nbrs, int nn) {
             ma.grayR[j] = (P.cost_kind == SR_COST_NCC_MVS) ? B.gray_pix
                           : (P.cost_kind == SR_COST_NCC_TWOVIEW) ? B.gray_two : B.gray_msk;
             ma.grayRf[j] = B.gray_pix_f;
+            ma.grayRf4[j] = B.gray_pix_f4;
             ma.raysR[j] = B.rays;
         }
         ma.pitch_f = screen_pitch(w);
+        ma.plane4_stride = screen_plane4_stride(w, h);
         ma.raysL = A.rays;
         memcpy(ma.camR, ctx->cams[ref].R, sizeof(ma.camR));
         memcpy(ma.camT, ctx->cams[ref].t, sizeof(ma.camT));
@@ -823,8 +832,8 @@ int sr_run_view_curve(sr_ctx *ctx, int ref, const int32_t *nbrs, int nn) {
         ma.out_depth = A.depth;
         ma.out_best = A.best;
         ma.w = w;
-        ma.win_w = w - 2 * P.radius;
-        ma.win_h = h - 2 * P.radius;
+        ma.win_w = std::max(0, w - 2 * P.radius);  // (compared as unsigned: an image smaller than the window has no interior)
+        ma.win_h = std::max(0, h - 2 * P.radius);
         ma.h = h;
         ma.row0 = b0;
         ma.rows = rows;

@@ -4,8 +4,13 @@
 #pragma once
 #include "sr_kernels.cuh"
 #include "sr_match_screen.cuh"
+#include "sr_screen2.cuh"
 
 namespace sr {
+
+#ifndef SR_SCREEN2
+#define SR_SCREEN2 1  // 0: A/B against the round-1 screen kernel for r <= 2
+#endif
 
 template <int R> struct LanesFor { static constexpr int G = (R <= 2) ? 1 : (R == 3) ? 2 : (R <= 5) ? 4 : (R <= 7) ? 8 : (R <= 10) ? 16 : 32; };
 
@@ -36,6 +41,19 @@ cudaError_t launch_match_screen(const MatchArgs &a, cudaStream_t st) {
     constexpr int PPB = SCREEN_BLOCK / G;
     const size_t npix = (size_t)a.rows * a.w;
     const unsigned grid = (unsigned)((npix + PPB - 1) / PPB);
+#if SR_SCREEN2
+    if (G == 1) {  // thread-per-pixel radii: sr_screen2.cuh (one warp per block)
+        constexpr int R2 = (G == 1) ? R : 1;
+        if (a.stats) return launch_screen2<R2, true, 0>(a, st);
+        switch (a.pitch_f) {
+            case 1024: return launch_screen2<R2, false, 1024>(a, st);
+            case 2048: return launch_screen2<R2, false, 2048>(a, st);
+            case 4096: return launch_screen2<R2, false, 4096>(a, st);
+            default: return launch_screen2<R2, false, 0>(a, st);
+        }
+        return cudaGetLastError();
+    }
+#endif
     if (a.stats) {
         match_mvs_screen_kernel<R, G, true, 0><<<grid, SCREEN_BLOCK, 0, st>>>(a);
     } else if (G == 1) {  // thread-per-pixel radii: the row pitch is a compile-time constant
