@@ -88,30 +88,69 @@ struct RefrProjector {
         cxs = cxs_;
         fys = fys_;
         cys = cys_;
+        uc = nullptr;
+    }
+
+    // The label-independent constants that are the same for every pixel of a (reference, target) pair.
+    // A kernel whose target view is a launch constant reads them as constant-bank operands (the members
+    // above).  The pipeline kernel (sr_pipeline.cuh) picks its target view at run time: there they would
+    // have to live in ~35 registers across the label sweep, so the block keeps them in shared memory and
+    // project<true>() re-reads them at each use (volatile: the reads are not hoisted back into registers).
+    enum { UC_PD = 0, UC_DD, UC_N1, UC_N2, UC_FXS, UC_CXS, UC_FYS, UC_CYS, UC_KDN, UC_K = UC_KDN + 3, UC_DISTORTED = UC_K + 5, UC_COUNT };
+    const volatile double *uc;
+    __device__ static void fill_uniform(double *t, const sr_camera &nbr, const double *Kn, double fxs_, double cxs_, double fys_, double cys_) {
+        const d3 KdN_ = fmul3(Kn, nbr.plane_d * ld3(nbr.plane_n));
+        t[UC_PD] = nbr.plane_d;
+        t[UC_DD] = nbr.plane_d * nbr.plane_d;
+        t[UC_N1] = nbr.n;
+        t[UC_N2] = nbr.n * nbr.n;
+        t[UC_FXS] = fxs_;
+        t[UC_CXS] = cxs_;
+        t[UC_FYS] = fys_;
+        t[UC_CYS] = cys_;
+        t[UC_KDN] = KdN_.x;
+        t[UC_KDN + 1] = KdN_.y;
+        t[UC_KDN + 2] = KdN_.z;
+        for (int i = 0; i < 5; ++i) t[UC_K + i] = nbr.dist[i];
+        t[UC_DISTORTED] = nbr.is_distorted ? 1.0 : 0.0;
     }
 
     // Exact projection of label d.  rho_guess in [0,1] or < 0 (paraxial start).  Outputs the
     // coordinate that is truncated (U,V) and the root rho.
+    template <bool UC = false>
     __device__ __forceinline__ bool project(int d, double rho_guess, double &U, double &V, double &rho_out) const {
+        // (plain if/else, not ?: — mixing a volatile lvalue into a conditional makes BOTH arms volatile reads)
+        double pd_, dd_, n1_, n2_;
+        if (UC) {
+            pd_ = uc[UC_PD];
+            dd_ = uc[UC_DD];
+            n1_ = uc[UC_N1];
+            n2_ = uc[UC_N2];
+        } else {
+            pd_ = pd;
+            dd_ = dd;
+            n1_ = n1;
+            n2_ = n2;
+        }
         const double t = fma(depth_table[d], tA, tB);
         if (!ray_ok || t < 1e-10) return false;
         const d3 radv = faxpy(t, R1, R0);
         const double rr = fdot(radv, radv);
         if (!(rr > 0.0)) return false;  // on the axis dir = radv/r is NaN in the reference: no root is accepted
         const double av = fma(t, a1, a0);
-        const double h = fabs(av) - pd, hh = h * h;
-        double rho = (rho_guess >= 0.0) ? rho_guess : n1 * fabs(pd) / (fabs(h) + n1 * fabs(pd) + 1e-300);
+        const double h = fabs(av) - pd_, hh = h * h;
+        double rho = (rho_guess >= 0.0) ? rho_guess : n1_ * fabs(pd_) / (fabs(h) + n1_ * fabs(pd_) + 1e-300);
         rho = fmin(fmax(rho, 0.0), 1.0);
         bool conv = false;
 #pragma unroll 1
         for (int it = 0; it < 8; ++it) {
             const double s = 1.0 - rho;
             const double p2 = rho * rho, s2 = s * s;
-            const double A = fma(p2, rr, dd), B = fma(s2, rr, hh);
-            const double G = fma(p2, B, -((n2 * s2) * A));
-            const double u = fma(n2, s, rho);
+            const double A = fma(p2, rr, dd_), B = fma(s2, rr, hh);
+            const double G = fma(p2, B, -((n2_ * s2) * A));
+            const double u = fma(n2_, s, rho);
             // G'/2 = rho*B + n^2 s A - rho s rr (rho + n^2 s)
-            const double g2 = fma(n2 * s, A, fma(rho, B, -(((rho * s) * rr) * u)));
+            const double g2 = fma(n2_ * s, A, fma(rho, B, -(((rho * s) * rr) * u)));
             const double step = (0.5 * G) * rcp_approx(g2);
             rho -= step;
             if (fabs(step) <= 3e-8) {
@@ -122,25 +161,50 @@ struct RefrProjector {
         }
         if (!conv || !(rho >= 0.0 && rho <= 1.0)) {
             const double r = sqrt(rr);
-            rho = snell_root_robust(r, pd, h, n1, -1.0) / r;
+            rho = snell_root_robust(r, pd_, h, n1_, -1.0) / r;
         }
         if (!(rho == rho)) return false;
         rho_out = rho;
         // point on the interface = rho*radv + d*N (camera.cpp:127); K*point hoisted
         const d3 Kr = faxpy(t, KR1, KR0);
-        const d3 p = faxpy(rho, Kr, KdN);
+        d3 KdN_;
+        if (UC) KdN_ = d3{uc[UC_KDN], uc[UC_KDN + 1], uc[UC_KDN + 2]};
+        else KdN_ = KdN;
+        const d3 p = faxpy(rho, Kr, KdN_);
         const double iz = fast_rcp(p.z);
         double xn = p.x * iz, yn = p.y * iz;
-        if (distorted) {  // camera.cpp:395-416 on normalised coordinates
+        bool distorted_;
+        if (UC) distorted_ = uc[UC_DISTORTED] != 0.0;
+        else distorted_ = distorted;
+        if (distorted_) {  // camera.cpp:395-416 on normalised coordinates
+            double k0, k1, k2, k3, k4;
+            if (UC) {
+                k0 = uc[UC_K];
+                k1 = uc[UC_K + 1];
+                k2 = uc[UC_K + 2];
+                k3 = uc[UC_K + 3];
+                k4 = uc[UC_K + 4];
+            } else {
+                k0 = k[0];
+                k1 = k[1];
+                k2 = k[2];
+                k3 = k[3];
+                k4 = k[4];
+            }
             const double q2 = fma(xn, xn, yn * yn);
-            const double cdist = fma(fma(fma(k[4], q2, k[1]), q2, k[0]), q2, 1.0);
+            const double cdist = fma(fma(fma(k4, q2, k1), q2, k0), q2, 1.0);
             const double xo = xn, yo = yn;
-            xn = fma(xo, cdist, fma(2 * k[2] * xo, yo, k[3] * fma(2 * xo, xo, q2)));
+            xn = fma(xo, cdist, fma(2 * k2 * xo, yo, k3 * fma(2 * xo, xo, q2)));
             // camera.cpp:411-412: y's tangential term uses the already-distorted x
-            yn = fma(yo, cdist, fma(k[2], fma(2 * yo, yo, q2), 2 * k[3] * xn * yo));
+            yn = fma(yo, cdist, fma(k2, fma(2 * yo, yo, q2), 2 * k3 * xn * yo));
         }
-        U = fma(fxs, xn, cxs);
-        V = fma(fys, yn, cys);
+        if (UC) {
+            U = fma(uc[UC_FXS], xn, uc[UC_CXS]);
+            V = fma(uc[UC_FYS], yn, uc[UC_CYS]);
+        } else {
+            U = fma(fxs, xn, cxs);
+            V = fma(fys, yn, cys);
+        }
         return true;
     }
 };
@@ -168,27 +232,40 @@ constexpr int BUILD_STRIDE = SR_BUILD_STRIDE;
 #define SR_BUILD_BOUNDS __launch_bounds__(128)
 #endif
 
+// What one label sweep needs to know: the target view, the reference view's geometry and where the
+// tables are.  (Pointers may point into the kernel's parameter space.)
+struct BuildSweep {
+    const sr_camera *nbr;        // target view
+    const double *Kn;            // see BuildRefrArgs::Kn
+    double fxs, cxs, fys, cys;
+    const double *prin, *C;      // reference view principal direction and centre
+    const double *rays;          // [6][h][w] of the reference view
+    const double *depth_table;   // [D]
+    const uint8_t *nbr_mask;     // null: every neighbour pixel is WHITE
+    int w, h, D;
+    unsigned long long *check;   // see BuildRefrArgs::check
+    const double *uniform;       // RefrProjector::fill_uniform table in shared memory, or null (constant-bank operands)
+};
+
 // MVS: the multi-view tap rule (tap inside the image and WHITE in the neighbour's mask);
 // HAS_MASK: the neighbour has a mask plane (a.nbr_mask != null).  Compile-time so that the other
 // variant's clamps, mask address arithmetic and loads do not occupy (predicated-off) issue slots.
-template <bool MVS, bool HAS_MASK>
-__global__ void SR_BUILD_BOUNDS build_refr_kernel(const __grid_constant__ BuildRefrArgs a) {
-    const int pid = blockIdx.x * blockDim.x + threadIdx.x;
-    if (pid >= a.rows * a.w) return;
-    const int x = pid % a.w, y = a.row0 + pid / a.w;
+// Labels [d0, d1) of reference pixel (x, y), d0 a multiple of BUILD_STRIDE; sink(d, tap) receives them
+// in increasing d.
+template <bool MVS, bool HAS_MASK, bool UC, class Sink>
+__device__ __forceinline__ void build_refr_sweep(const BuildSweep &a, int x, int y, int d0, int d1, Sink sink) {
     const size_t pix = (size_t)y * a.w + x;
-    if (a.ref_mask[pix] != 255) return;  // the match kernels never read taps of masked-out pixels
     const size_t n = (size_t)a.w * a.h;
     const d3 src = {a.rays[pix], a.rays[n + pix], a.rays[2 * n + pix]};
     const d3 dir = {a.rays[3 * n + pix], a.rays[4 * n + pix], a.rays[5 * n + pix]};
     RefrProjector pj;
-    pj.init(a.nbr, a.Kn, a.prin, a.C, src, dir, a.depth_table, a.fxs, a.cxs, a.fys, a.cys);
+    pj.init(*a.nbr, a.Kn, a.prin, a.C, src, dir, a.depth_table, a.fxs, a.cxs, a.fys, a.cys);
+    if (UC) pj.uc = a.uniform;
     const int D = a.D;
     auto project_label = [&](int d, double rho_guess, double &U, double &V, double &rho_out) -> bool {
-        return pj.project(d, rho_guess, U, V, rho_out);
+        return pj.template project<UC>(d, rho_guess, U, V, rho_out);
     };
 
-    const size_t plane = (size_t)a.rows * a.w;
     // trunc toward zero of a coordinate without the conversion pipe (F2I.F64 issues at 16
     // lanes/clk/SM): r = rint(|c|) through the 1.5*2^52 constant, whose sum carries the integer in
     // its low word; diff = |c| - r is exact and tells floor from rint.  Also returns |diff|, the
@@ -203,8 +280,6 @@ __global__ void SR_BUILD_BOUNDS build_refr_kernel(const __grid_constant__ BuildR
     };
 
     constexpr int S = BUILD_STRIDE;
-    const int d0 = blockIdx.y * a.d_chunk;  // d_chunk is a multiple of S
-    const int d1 = min(d0 + a.d_chunk, D);
     // anchor window: labels (k-1)S, kS, (k+1)S, (k+2)S for the interval [kS, (k+1)S)
     double au[4], av_[4], ar[4];
     bool aok[4], asane[4];
@@ -335,7 +410,7 @@ __global__ void SR_BUILD_BOUNDS build_refr_kernel(const __grid_constant__ BuildR
                 }
                 tap = (int32_t)(((uint32_t)(cy & 0xffff) << 16) | (uint32_t)(cx & 0xffff));
             }
-            a.taps[(size_t)d * plane + pid] = tap;
+            sink(d, tap);
         }
 #pragma unroll
         for (int i = 0; i < 3; ++i) {
@@ -346,6 +421,42 @@ __global__ void SR_BUILD_BOUNDS build_refr_kernel(const __grid_constant__ BuildR
             asane[i] = asane[i + 1];
         }
     }
+}
+
+__device__ __forceinline__ BuildSweep build_sweep_of(const BuildRefrArgs &a) {
+    BuildSweep s;
+    s.nbr = &a.nbr;
+    s.Kn = a.Kn;
+    s.fxs = a.fxs;
+    s.cxs = a.cxs;
+    s.fys = a.fys;
+    s.cys = a.cys;
+    s.prin = a.prin;
+    s.C = a.C;
+    s.rays = a.rays;
+    s.depth_table = a.depth_table;
+    s.nbr_mask = a.nbr_mask;
+    s.w = a.w;
+    s.h = a.h;
+    s.D = a.D;
+    s.check = a.check;
+    s.uniform = nullptr;
+    return s;
+}
+
+// Stand-alone form: one thread per reference pixel of the band, blockIdx.y = chunk of labels; the taps
+// go to the [D][rows][w] volume of this neighbour.
+template <bool MVS, bool HAS_MASK>
+__global__ void SR_BUILD_BOUNDS build_refr_kernel(const __grid_constant__ BuildRefrArgs a) {
+    const int pid = blockIdx.x * blockDim.x + threadIdx.x;
+    if (pid >= a.rows * a.w) return;
+    const int x = pid % a.w, y = a.row0 + pid / a.w;
+    if (a.ref_mask[(size_t)y * a.w + x] != 255) return;  // the match kernels never read taps of masked-out pixels
+    const size_t plane = (size_t)a.rows * a.w;
+    const int d0 = blockIdx.y * a.d_chunk;  // d_chunk is a multiple of BUILD_STRIDE
+    const int d1 = min(d0 + a.d_chunk, a.D);
+    int32_t *__restrict__ out = a.taps + pid;
+    build_refr_sweep<MVS, HAS_MASK, false>(build_sweep_of(a), x, y, d0, d1, [&](int d, int32_t tap) { out[(size_t)d * plane] = tap; });
 }
 
 }  // namespace sr

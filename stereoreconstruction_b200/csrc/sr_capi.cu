@@ -15,6 +15,7 @@
 #include "sr_match_dispatch.cuh"
 #include "sr_build_refr.cuh"
 #include "sr_curve.cuh"
+#include "sr_pipeline.cuh"
 
 using namespace sr;
 
@@ -27,7 +28,6 @@ struct ViewDev {
     uint8_t *mask = nullptr;
     double *gray_pix = nullptr, *gray_two = nullptr, *gray_msk = nullptr, *edges = nullptr;
     float *gray_pix_f = nullptr;
-    float *gray_pix_f4 = nullptr;  // four shifted copies of gray_pix_f (sr_screen2.cuh)
     bool have_image = false; // sr_set_views received pixels for this view
     bool all_white = false;  // no mask was passed for this view: every pixel is WHITE
     double *rays = nullptr;  // [6][h][w] Camera::unproject of every pixel centre (curve mode), lazily
@@ -116,6 +116,13 @@ struct sr_ctx {
     bool use_refr_build = true;  // SR_BUILD_REFR=0: refractive views through the generic build_kernel (A/B aid)
     int refr_chunk = 256;        // labels per thread of build_refr_kernel (SR_BUILD_CHUNK)
     bool use_screen = true;  // SR_MATCH_SCREEN=0: MVS selection through the all-FP64 match_kernel (A/B aid)
+    bool use_pipeline = false;  // SR_PIPELINE=1: build and screen as roles of ONE launch (sr_pipeline.cuh; measured slower: DESIGN.md)
+    int pipe_lag = 128;        // tiles between a tile's build and its screen (SR_PIPE_LAG)
+    size_t pipe_ring_bytes = (size_t)1 << 30;  // tap ring of the pipeline kernel (SR_PIPE_RING_MB)
+    int32_t *d_ring = nullptr;
+    size_t ring_cap = 0;
+    int *d_pipe_flags = nullptr;  // built[ntiles], done[ntiles], ticket
+    size_t pipe_flags_cap = 0;
     ncclComm_t comm = nullptr;
     int rank = 0, nranks = 1;
     // per-stage CUDA-event timing (sr_set_profiling): [begin, after build, after match] per band
@@ -136,12 +143,16 @@ int fail(sr_ctx *c, int code, const std::string &msg) {
         if (e_ != cudaSuccess)                                                                         \
             return fail(ctx, SR_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_));         \
     } while (0)
+// SR_DEBUG_SYNC=1: synchronise after every launch, so that a faulting kernel is reported at its own line
+static const bool g_debug_sync = getenv("SR_DEBUG_SYNC") && atoi(getenv("SR_DEBUG_SYNC")) != 0;
 #define CKL()                                                                                          \
     do {                                                                                               \
         ++ctx->launches;                                                                               \
         cudaError_t e_ = cudaGetLastError();                                                           \
+        if (e_ == cudaSuccess && g_debug_sync) e_ = cudaStreamSynchronize(ctx->stream);                \
         if (e_ != cudaSuccess)                                                                         \
-            return fail(ctx, SR_ERR_CUDA, std::string("kernel launch: ") + cudaGetErrorString(e_));    \
+            return fail(ctx, SR_ERR_CUDA, std::string("kernel launch (" __FILE__ ":") +                \
+                                              std::to_string(__LINE__) + "): " + cudaGetErrorString(e_)); \
     } while (0)
 
 template <typename T>
@@ -156,7 +167,6 @@ void free_views(sr_ctx *c) {
         dfree(v.mask);
         dfree(v.gray_pix);
         dfree(v.gray_pix_f);
-        dfree(v.gray_pix_f4);
         dfree(v.rays);
         dfree(v.gray_two);
         dfree(v.gray_msk);
@@ -193,6 +203,27 @@ double depth_from_label(const sr_params &p, int label) {
     double t = label / (p.num_levels - 1.0);
     if (p.depth_kind == SR_DEPTH_INV5) t /= (5 - 4 * t);  // stereo/twoviewstereo.cpp:981-985
     return p.min_depth * (1 - t) + p.max_depth * t;        // stereo/multiviewstereo.cpp:733-736
+}
+
+// K (rows 0/1 normalised for a distorted view) and the map from normalised/pixel coordinates to the
+// coordinate that is truncated: scale and the tap rule's shift (MVS: 0, two-view: -0.5) folded in.
+void refr_pixel_map(const sr_camera &nb, bool mvs, double sc, double *Kn, double &fxs, double &cxs, double &fys, double &cys) {
+    const double shift = mvs ? 0.0 : -0.5;
+    memcpy(Kn, nb.K, 9 * sizeof(double));
+    if (nb.is_distorted) {
+        const double fx = nb.K[0], fy = nb.K[4], cx = nb.K[2], cy = nb.K[5];
+        for (int c = 0; c < 3; ++c) {
+            Kn[c] = (nb.K[c] - cx * nb.K[6 + c]) / fx;
+            Kn[3 + c] = (nb.K[3 + c] - cy * nb.K[6 + c]) / fy;
+        }
+        fxs = fx * sc;
+        cxs = cx * sc + shift;
+        fys = fy * sc;
+        cys = cy * sc + shift;
+    } else {
+        fxs = fys = sc;
+        cxs = cys = shift;
+    }
 }
 
 int check_view(sr_ctx *ctx, int v) {
@@ -234,6 +265,9 @@ int sr_ctx_create(int device, sr_ctx **out) {
     if (const char *mb = getenv("SR_TAP_BUDGET_MB")) c->tap_budget = (size_t)atoll(mb) << 20;
     if (const char *sc = getenv("SR_MATCH_SCREEN")) c->use_screen = atoi(sc) != 0;
     if (const char *sb = getenv("SR_BUILD_REFR")) c->use_refr_build = atoi(sb) != 0;
+    if (const char *sp = getenv("SR_PIPELINE")) c->use_pipeline = atoi(sp) != 0;
+    if (const char *sl = getenv("SR_PIPE_LAG")) c->pipe_lag = std::max(1, atoi(sl));
+    if (const char *sr_ = getenv("SR_PIPE_RING_MB")) c->pipe_ring_bytes = (size_t)std::max(1, atoi(sr_)) << 20;
     if (const char *sk = getenv("SR_BUILD_CHUNK")) c->refr_chunk = std::max(4, atoi(sk));
     if (const char *ss = getenv("SR_MATCH_STATS")) {
         if (atoi(ss) != 0 && cudaMalloc(&c->d_stats, 16 * sizeof(unsigned long long)) == cudaSuccess)
@@ -255,6 +289,8 @@ void sr_ctx_destroy(sr_ctx *c) {
     dfree(c->d_volume);
     dfree(c->d_peaks);
     dfree(c->d_stats);
+    dfree(c->d_ring);
+    dfree(c->d_pipe_flags);
     if (c->d_scratch) cudaFree(c->d_scratch);
     cudaStreamDestroy(c->own_stream);
     delete c;
@@ -312,8 +348,6 @@ int sr_set_views(sr_ctx *ctx, int V, const sr_camera *cams, const uint8_t *const
             CK(cudaMalloc(&v.mask, n));
             CK(cudaMalloc(&v.gray_pix, n * 8));
             CK(cudaMalloc(&v.gray_pix_f, (size_t)screen_pitch(w) * h * 4));
-            CK(cudaMalloc(&v.gray_pix_f4, (size_t)screen_plane4_stride(w, h) * 4 * 4));
-            CK(cudaMemsetAsync(v.gray_pix_f4, 0, (size_t)screen_plane4_stride(w, h) * 4 * 4, ctx->stream));  // the shift margins
             CK(cudaMalloc(&v.gray_two, n * 8));
             CK(cudaMalloc(&v.gray_msk, n * 8));
             CK(cudaMalloc(&v.edges, n * 8 * 4));
@@ -344,8 +378,7 @@ int sr_set_views(sr_ctx *ctx, int V, const sr_camera *cams, const uint8_t *const
         if (!v.all_white) CK(cudaMemcpyAsync(v.mask, mask8[i], n, cudaMemcpyHostToDevice, ctx->stream));
         else CK(cudaMemsetAsync(v.mask, 255, n, ctx->stream));
         prep_view_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(v.rgba, v.mask, w, h, v.gray_pix,
-                                                                             v.gray_two, v.gray_msk, v.edges, v.gray_pix_f, screen_pitch(w),
-                                                                             v.gray_pix_f4, screen_plane4_stride(w, h));
+                                                                             v.gray_two, v.gray_msk, v.edges, v.gray_pix_f, screen_pitch(w));
         CKL();
         // results start as "not computed": NaN depth (twoviewstereo.cpp:118-119), index NONE
         CK(cudaMemsetAsync(v.depth, 0xff, n * 8, ctx->stream));
@@ -400,6 +433,130 @@ static int init_peaks(sr_ctx *ctx, int ref) {
     return SR_OK;
 }
 
+// sr_pipeline.cuh: support weights, then tap build + screen + verify + WTA of rows [r0, r1) as one launch.
+static int run_view_pipeline(sr_ctx *ctx, int ref, const int32_t *nbrs, int nn, int r0, int r1) {
+    const sr_params &P = ctx->params;
+    cudaStream_t st = ctx->stream;
+    const int w = ctx->w, h = ctx->h, D = P.num_levels, rows = r1 - r0;
+    ViewDev &A = ctx->views[ref];
+    int rc = init_peaks(ctx, ref);
+    if (rc) return rc;
+    ctx->vol_elems = 0;
+    if (ctx->cancel.load()) return fail(ctx, SR_ERR_CANCELLED, "cancelled");
+    const size_t wn = (size_t)(2 * P.radius + 1) * (2 * P.radius + 1);
+    const size_t plane = (size_t)rows * w;
+    const size_t need_w = wn * plane * 8;
+    if (need_w > ctx->weights_cap) {
+        CK(cudaStreamSynchronize(st));
+        dfree(ctx->d_weights);
+        ctx->weights_cap = 0;
+        CK(cudaMalloc(&ctx->d_weights, need_w));
+        ctx->weights_cap = need_w;
+    }
+    const int tiles_x = (w + 31) / 32, tiles_y = (rows + SCREEN2_TILE_ROWS - 1) / SCREEN2_TILE_ROWS;
+    const int ntiles = tiles_x * tiles_y;
+    const size_t tile_bytes = (size_t)nn * SCREEN2_TILE_ROWS * D * 32 * 4;
+    const int lag = std::min(ctx->pipe_lag, std::max(1, ntiles));
+    // the ring must be longer than the lag (a build block may only wait for an older screen block)
+    const int ring_tiles = (int)std::min<size_t>((size_t)ntiles, std::max<size_t>((size_t)lag + 64, ctx->pipe_ring_bytes / tile_bytes));
+    const size_t need_ring = (size_t)ring_tiles * tile_bytes;
+    if (need_ring > ctx->ring_cap) {
+        CK(cudaStreamSynchronize(st));
+        dfree(ctx->d_ring);
+        ctx->ring_cap = 0;
+        CK(cudaMalloc(&ctx->d_ring, need_ring));
+        ctx->ring_cap = need_ring;
+    }
+    const size_t need_flags = ((size_t)2 * ntiles + 1) * sizeof(int);
+    if (need_flags > ctx->pipe_flags_cap) {
+        CK(cudaStreamSynchronize(st));
+        dfree(ctx->d_pipe_flags);
+        ctx->pipe_flags_cap = 0;
+        CK(cudaMalloc(&ctx->d_pipe_flags, need_flags));
+        ctx->pipe_flags_cap = need_flags;
+    }
+    cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
+    if (ctx->profiling) {
+        for (int k = 0; k < 3; ++k) CK(cudaEventCreate(&ev[k]));
+        CK(cudaEventRecord(ev[0], st));
+        CK(cudaEventRecord(ev[1], st));  // (no separate build stage)
+    }
+    CK(cudaMemsetAsync(ctx->d_pipe_flags, 0, need_flags, st));
+    {
+        WeightArgs wa;
+        memset(&wa, 0, sizeof(wa));
+        wa.rgba = A.rgba;
+        wa.mask = A.mask;
+        wa.edges = A.edges;
+        wa.W = ctx->d_weights;
+        wa.w = w;
+        wa.h = h;
+        wa.row0 = r0;
+        wa.rows = rows;
+        wa.radius = P.radius;
+        const unsigned gx = (unsigned)((plane + 127) / 128);
+        if (P.weight_kind == SR_WEIGHT_ADAPTIVE)
+            weights_adaptive_kernel<<<gx, 128, (P.radius + 1) * sizeof(double), st>>>(wa);
+        else
+            launch_geodesic(wa, gx, st);
+        CKL();
+    }
+    PipeArgs pa;
+    memset(&pa, 0, sizeof(pa));
+    MatchArgs &ma = pa.m;
+    ma.W = ctx->d_weights;
+    ma.maskL = A.mask;
+    ma.grayL = A.gray_pix;
+    for (int j = 0; j < nn; ++j) {
+        const ViewDev &B = ctx->views[nbrs[j]];
+        ma.grayR[j] = B.gray_pix;
+        ma.grayRf[j] = B.gray_pix_f;
+        PipeNbr &nb = pa.nb[j];
+        nb.cam = ctx->cams[nbrs[j]];
+        refr_pixel_map(nb.cam, true, P.image_scale, nb.Kn, nb.fxs, nb.cxs, nb.fys, nb.cys);
+        nb.mask = B.all_white ? nullptr : B.mask;
+    }
+    ma.pitch_f = screen_pitch(w);
+    ma.depth_table = ctx->d_depth_table;
+    ma.out_index = A.index;
+    ma.out_depth = A.depth;
+    ma.out_best = A.best;
+    ma.w = w;
+    ma.h = h;
+    ma.win_w = std::max(0, w - 2 * P.radius);
+    ma.win_h = std::max(0, h - 2 * P.radius);
+    ma.row0 = r0;
+    ma.rows = rows;
+    ma.D = D;
+    ma.num_nbrs = nn;
+    ma.select_kind = P.select_kind;
+    ma.depth_up = (P.max_depth >= P.min_depth) ? 1 : 0;
+    ma.use_screen = 1;
+    ma.stats = ctx->d_stats;
+    ma.second_best_factor = P.second_best_factor;
+    ma.ncc_threshold = P.ncc_threshold;
+    memcpy(pa.prin, ctx->cams[ref].prin_dir, sizeof(pa.prin));
+    memcpy(pa.C, ctx->cams[ref].C, sizeof(pa.C));
+    pa.rays = ctx->d_rays;
+    pa.ring = ctx->d_ring;
+    pa.built = ctx->d_pipe_flags;
+    pa.done = ctx->d_pipe_flags + ntiles;
+    pa.ticket = reinterpret_cast<unsigned *>(ctx->d_pipe_flags + 2 * (size_t)ntiles);
+    pa.tiles_x = tiles_x;
+    pa.ntiles = ntiles;
+    pa.ring_tiles = ring_tiles;
+    pa.lag = lag;
+    pa.check = ctx->d_stats ? ctx->d_stats + 8 : nullptr;
+    cudaError_t e = launch_pipeline(P.radius, pa, st);
+    ++ctx->launches;
+    if (e != cudaSuccess) return fail(ctx, SR_ERR_CUDA, std::string("pipeline kernel: ") + cudaGetErrorString(e));
+    if (ctx->profiling) {
+        CK(cudaEventRecord(ev[2], st));
+        for (int k = 0; k < 3; ++k) ctx->prof_events.push_back(ev[k]);
+    }
+    return SR_OK;
+}
+
 int sr_run_view(sr_ctx *ctx, int ref, const int32_t *nbrs, int nn) {
     int rc = check_view(ctx, ref);
     if (rc) return rc;
@@ -424,6 +581,13 @@ int sr_run_view(sr_ctx *ctx, int ref, const int32_t *nbrs, int nn) {
 
     rays_kernel<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(ctx->cams[ref], w, h, P.image_scale, ctx->d_rays);
     CKL();
+
+    {   // MultiViewStereo label path with refractive neighbours: build and screen as one launch
+        bool pipe = ctx->use_pipeline && ctx->use_screen && ctx->use_refr_build && P.select_kind == SR_SELECT_MVS &&
+                    P.cost_kind == SR_COST_NCC_MVS && !P.keep_cost_volume && pipeline_supported(P.radius);
+        for (int j = 0; j < nn; ++j) pipe = pipe && ctx->cams[nbrs[j]].is_refractive;
+        if (pipe) return run_view_pipeline(ctx, ref, nbrs, nn, r0, r1);
+    }
 
     // Row bands bound the scratch (tap volume nn*D*rows*w*4 bytes + support weights
     // WN*rows*w*8 bytes); a kept cost volume needs one band.
@@ -481,22 +645,7 @@ int sr_run_view(sr_ctx *ctx, int ref, const int32_t *nbrs, int nn) {
                 // refractive target view: hoisted-affine reprojection + Newton on the quartic in x/r
                 BuildRefrArgs ra;
                 ra.nbr = nb;
-                const double shift = mvs ? 0.0 : -0.5, sc = P.image_scale;
-                memcpy(ra.Kn, nb.K, sizeof(ra.Kn));
-                if (nb.is_distorted) {
-                    const double fx = nb.K[0], fy = nb.K[4], cx = nb.K[2], cy = nb.K[5];
-                    for (int c = 0; c < 3; ++c) {
-                        ra.Kn[c] = (nb.K[c] - cx * nb.K[6 + c]) / fx;
-                        ra.Kn[3 + c] = (nb.K[3 + c] - cy * nb.K[6 + c]) / fy;
-                    }
-                    ra.fxs = fx * sc;
-                    ra.cxs = cx * sc + shift;
-                    ra.fys = fy * sc;
-                    ra.cys = cy * sc + shift;
-                } else {
-                    ra.fxs = ra.fys = sc;
-                    ra.cxs = ra.cys = shift;
-                }
+                refr_pixel_map(nb, mvs, P.image_scale, ra.Kn, ra.fxs, ra.cxs, ra.fys, ra.cys);
                 memcpy(ra.prin, ctx->cams[ref].prin_dir, sizeof(ra.prin));
                 memcpy(ra.C, ctx->cams[ref].C, sizeof(ra.C));
                 ra.rays = ctx->d_rays;
@@ -568,10 +717,8 @@ int sr_run_view(sr_ctx *ctx, int ref, const int32_t *nbrs, int nn) {
             ma.grayR[j] = (P.cost_kind == SR_COST_NCC_MVS) ? B.gray_pix
                           : (P.cost_kind == SR_COST_NCC_TWOVIEW) ? B.gray_two : B.gray_msk;
             ma.grayRf[j] = B.gray_pix_f;
-            ma.grayRf4[j] = B.gray_pix_f4;
         }
         ma.pitch_f = screen_pitch(w);
-        ma.plane4_stride = screen_plane4_stride(w, h);
         ma.taps = ctx->d_taps;
         ma.depth_table = ctx->d_depth_table;
         ma.out_index = A.index;
@@ -816,11 +963,9 @@ int sr_run_view_curve(sr_ctx *ctx, int ref, const int32_t *nbrs, int nn) {
             ma.grayR[j] = (P.cost_kind == SR_COST_NCC_MVS) ? B.gray_pix
                           : (P.cost_kind == SR_COST_NCC_TWOVIEW) ? B.gray_two : B.gray_msk;
             ma.grayRf[j] = B.gray_pix_f;
-            ma.grayRf4[j] = B.gray_pix_f4;
             ma.raysR[j] = B.rays;
         }
         ma.pitch_f = screen_pitch(w);
-        ma.plane4_stride = screen_plane4_stride(w, h);
         ma.raysL = A.rays;
         memcpy(ma.camR, ctx->cams[ref].R, sizeof(ma.camR));
         memcpy(ma.camT, ctx->cams[ref].t, sizeof(ma.camT));

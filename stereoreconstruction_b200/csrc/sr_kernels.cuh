@@ -32,11 +32,7 @@ namespace sr {
 
 constexpr int SR_MAX_NBRS = 8;
 // Row pitch of the FP32 gray planes: the smallest of 1024/2048/4096/16384 that holds a row.
-// (w + 4: the shifted copies of sr_screen2.cuh hold pixel x at index x + s, s <= 3, and a window's fifth
-// column is read at index e + 4 <= w + 3.)
-inline int screen_pitch(int w) { return w + 4 <= 1024 ? 1024 : w + 4 <= 2048 ? 2048 : w + 4 <= 4096 ? 4096 : 16384 + 8; }
-// Rows of padding above and below each shifted copy: a window row index never leaves [0, h), none needed.
-inline int screen_plane4_stride(int w, int h) { return screen_pitch(w) * h; }
+inline int screen_pitch(int w) { return w <= 1024 ? 1024 : w <= 2048 ? 2048 : w <= 4096 ? 4096 : 16384; }
 constexpr int32_t TAP_NONE = INT32_MIN;
 constexpr int TAP_CLAMP = 20000;  // |coordinate| beyond this is outside any image for any window
 
@@ -64,8 +60,7 @@ __device__ __forceinline__ double color_dist(uchar4 a, uchar4 b) {
 __global__ void prep_view_kernel(const uchar4 *__restrict__ rgba, const uint8_t *__restrict__ mask, int w, int h,
                                  double *__restrict__ gray_pix, double *__restrict__ gray_two,
                                  double *__restrict__ gray_msk, double *__restrict__ edges,
-                                 float *__restrict__ gray_pix_f, int pitch_f, float *__restrict__ gray_pix_f4,
-                                 int plane4_stride) {
+                                 float *__restrict__ gray_pix_f, int pitch_f) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= w * h) return;
     const int x = i % w, y = i / w;
@@ -76,9 +71,6 @@ __global__ void prep_view_kernel(const uchar4 *__restrict__ rgba, const uint8_t 
     // FP32 copy read by the screening pass of match_mvs_screen_kernel; its row pitch is a power of
     // two (screen_pitch) so that the 25 window loads are one base register + immediate offsets
     gray_pix_f[(size_t)y * pitch_f + x] = (float)g;
-    // the four shifted copies read by sr_screen2.cuh: copy s holds pixel x at index x + s
-#pragma unroll
-    for (int s = 0; s < 4; ++s) gray_pix_f4[(size_t)plane4_stride * s + (size_t)y * pitch_f + x + s] = (float)g;
     gray_msk[i] = white ? g : qnan();
     gray_two[i] = (white && x + 1 < w && y + 1 < h) ? g : qnan();
     const size_t n = (size_t)w * h;
@@ -335,9 +327,6 @@ struct MatchArgs {
     const double *grayR[SR_MAX_NBRS];  // neighbour taps (gray_pix C1, gray_two C2, gray_msk C3)
     const float *grayRf[SR_MAX_NBRS];  // FP32 copies of gray_pix (screening pass, MVS selection only)
     int pitch_f;                       // row pitch of the FP32 planes, in floats (screen_pitch(w))
-    const float *grayRf4[SR_MAX_NBRS]; // four copies of that plane, copy s shifted right by s floats (sr_screen2.cuh:
-                                       // the window's left edge is 16-byte aligned in one of them)
-    int plane4_stride;                 // floats between two copies (4 copies stay below 2^31 floats)
     const double *W;                // [WN][rows*w] support weights of this band
     const int32_t *taps;            // [nbr][D][rows][w]
     const double *depth_table;      // [D]

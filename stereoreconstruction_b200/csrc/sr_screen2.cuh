@@ -1,61 +1,75 @@
 // sr_screen2.cuh — the thread-per-pixel (r <= 2) form of the FP32 screen / FP64 verify selection of
-// sr_match_screen.cuh, reorganised around a 16-label chunk so that the label loop is nothing but
-// the window arithmetic:
+// sr_match_screen.cuh, reorganised so that the label loop is nothing but loads and window arithmetic.
 //
-//   * ONE code path for every pixel.  A reference pixel with inactive taps (outside the image, support
-//     weight <= 1e-10: stereo/multiviewstereo.cpp:137-141) carries w = dl = 0 for them, so their
-//     t_i = w_i g_i - meanR = -meanR exactly and s3 = sum_all t_i^2 - n_inactive * meanR^2.  The
-//     correction is one FFMA for everybody (n_inactive = 0 mostly) instead of a masked variant of the
-//     whole window that mixed warps executed IN ADDITION to the plain one.  The cancellation is bounded:
-//     the label is FORCEd to FP64 when the correction exceeds 100 x the corrected s3, below that the
-//     relative error of s3 is <= 15u * 101 ~ 9e-5, i.e. <= 4.5e-5 of ncc, inside SCREEN_EPS_LOOSE (such
-//     pixels never use the tight bar).
-//   * The neighbour window is 5 aligned LDG.128 + 5 LDG.32 instead of 25 LDG.32: the screen reads FOUR
-//     copies of the FP32 gray plane, copy s shifted right by s floats, and each lane picks the copy in
-//     which its window's left edge tx - 2 is 16-byte aligned.
-//   * Candidate handling is deferred to the end of the chunk: the loop stores ncc32 to a shared column,
-//     raises the lower bound and sets a bit in a per-lane mask; one warp vote per CHUNK (not per label)
-//     decides whether anybody has to look at the queue at all.  Queue overflow is resolved there too
-//     (flush, then continue with the lane's remaining bits), eviction of entries a risen bound has
-//     made hopeless happens when a queue fills and before a flush.
+//   * ONE-PASS window sums.  With p_i = w_i g_i (support weight x neighbour gray; w_i = 0 for the taps the
+//     reference skips on the reference side, stereo/multiviewstereo.cpp:137-141), n_a active taps and
+//     totW = sum w_i, the reference's two passes (:143-185) are algebraically
+//         meanR = S1 / totW,                      S1 = sum p_i
+//         s3 = sum_active (p_i - meanR)^2 = Q - meanR^2 (2 totW - n_a),      Q = sum p_i^2
+//         s1 = sum dl_i (p_i - meanR)      = X - meanR * SDL,                 X = sum (dl_i w_i) g_i
+//     so S1, Q and X are three independent accumulations over the taps: every loaded value is consumed
+//     as it arrives (no second pass that has to wait for the mean), the window needs no registers of
+//     its own beyond the loads in flight, and pixels with inactive taps need no special path at all.
+//     What the mean-first form bought in conditioning is paid back by an error bar that follows the
+//     cancellation kappa = Q / s3 of each label (see eps below) instead of two fixed classes.
+//   * Candidate handling is deferred to the end of a 16-label chunk: the loop stores the label's upper
+//     bound to a shared column, raises the lower bound and sets a bit in a per-lane mask; one warp vote
+//     per CHUNK decides whether anybody has to look at the queue at all.  Queue overflow is resolved
+//     there too (flush, then continue with the lane's remaining bits); entries a risen bound has made
+//     hopeless are evicted when a queue fills and before a flush.
+//   * The warps of a block own the rows of a 32-pixel-wide tile of the reference image.
 //
 // The rule that makes this exact is unchanged (sr_match_screen.cuh): a label is dropped only if its
 // upper bound ncc32 + eps is below lower32, a proven lower bound of the winning FP64 cost; every label
 // that survives is evaluated by the reference's own two-pass filter in FP64 and the reference's
 // selection rule (stereo/multiviewstereo.cpp:589-602,654-660) picks the winner.
+//
+// Error bar of the one-pass value (u = 2^-24; all inputs rounded once from FP64: <= u each):
+//   S1, Q, X are sums of <= 13 terms in two chains + a 3-add tree: <= 9 roundings per term.
+//     |dS1| <= 11u S1 (all terms >= 0),   |dQ| <= 15u Q,   |dX| <= 11u sum|dl_i| p_i <= 11u sqrt(Q)  (|dl| = 1)
+//   meanR: 13u relative;  meanR^2 (2 totW - n_a) = Q - s3, at most Q in magnitude when 2 totW > n_a
+//     (otherwise nothing cancels):  |ds3| <= 46u Q
+//   |meanR SDL| <= sqrt(n_a Q) |SDL| / totW:  |ds1| <= u sqrt(Q) (12 + 15 sigma),  sigma = |SDL| sqrt(n_a) / totW
+//   ncc = s1 / sqrt(s3):  |dncc| <= |ds1| / sqrt(s3) + |ds3| / (2 s3) <= u [(12 + 15 sigma) sqrt(kappa) + 23 kappa]
+//   with sqrt(kappa) <= (1 + kappa) / 2, a safety factor 1.5 and 3e-7 for rsqrt.approx and the last product:
+//         eps = e0 + e1 * kappa,   e0 = 1.5u (6 + 7.5 sigma) + 3e-7,   e1 = 1.5u (29 + 7.5 sigma)
+//   (per-pixel constants).  The first-order step needs |ds3| << s3: labels with eps > SCREEN_EPS_MAX, and
+//   windows with s3 < WN (RMS deviation below one gray level), are FORCEd to FP64.
+//   SR_MATCH_STATS=1 checks every verified label against its bar (outside_error_bar must stay 0).
 #pragma once
 #include "sr_match_screen.cuh"
 
 namespace sr {
 
-#ifndef SR_SCREEN2_VEC4
-#define SR_SCREEN2_VEC4 1  // 0: A/B against 25 scalar loads from the single FP32 plane
+#ifndef SR_SCREEN2_ABL
+#define SR_SCREEN2_ABL 0  // 1-4: timing ablations of the label loop (wrong results; profiling only)
 #endif
-constexpr float SCREEN_CORR_MAX = 100.0f;  // n_inactive * meanR^2 <= this * s3, else FP64 decides
+#ifndef SR_SCREEN2_NL
+#define SR_SCREEN2_NL 1  // labels evaluated together per loop iteration (independent chains: ILP within the warp)
+#endif
+#ifndef SR_SCREEN2_ONEPASS
+#define SR_SCREEN2_ONEPASS 1  // 0: A/B against the two-pass (mean first) form of the screen
+#endif
+constexpr float SCREEN_CORR_MAX = 100.0f;  // two-pass form: n_inactive * meanR^2 <= this * s3, else FP64 decides
+constexpr float SCREEN_EPS_MAX = 5e-3f;    // one-pass form: a wider error bar means FP64 decides
 constexpr float SCREEN_SKIP = -2.0f;       // "no value": below every possible lower bound
 
 // Shared memory of one screening warp.
+template <bool STATS>
 struct Screen2Smem {
     int32_t tap_ring[2][TAP_CHUNK][32];
-    float c32_ring[TAP_CHUNK][32];   // ncc32 + eps of the chunk's labels (SCREEN_FORCE: FP64 decides)
-    int32_t q_lab[SCREEN_QCAP][32];  // (eps class << 30) | (neighbour << 16) | label
+    float ub_ring[TAP_CHUNK][32];    // ncc32 + eps of the chunk's labels (SCREEN_FORCE: FP64 decides)
+    int32_t q_lab[SCREEN_QCAP][32];  // (neighbour << 16) | label
     int32_t q_tap[SCREEN_QCAP][32];
-    float q_c32[SCREEN_QCAP][32];    // upper bound ncc32 + eps; after verification: high word of the FP64 cost
+    float q_ub[SCREEN_QCAP][32];     // upper bound; after verification: high word of the FP64 cost
     double px_meanL[32], px_totW[32], px_s2[32], px_bestC[32], px_bestZ[32];
     int px_bestIdx[32];
     unsigned short v_ent[SCREEN_QCAP * 32];
     unsigned char px_flags[32];  // bit 0: all_slow, bit 1: has_inactive
-    int st_verified[32], st_viol[32];  // SR_MATCH_STATS only
-    float st_maxerr[32];
+    // SR_MATCH_STATS only: the labels' error bars, and what the verifications found
+    float eps_ring[STATS ? TAP_CHUNK : 1][32], q_eps[STATS ? SCREEN_QCAP : 1][32], st_maxerr[STATS ? 32 : 1];
+    int st_verified[STATS ? 32 : 1], st_viol[STATS ? 32 : 1];
 };
-
-// Register slot i of the window arrays holds window tap k = slot_tap(i) (row-major k).  With the
-// vectorised loads a row's first four taps come from one LDG.128 and pair up as (0,1),(2,3); the
-// fifth taps of the five rows follow.
-template <int R>
-__host__ __device__ constexpr int screen2_slot_tap(int i) {
-    return (R == 2 && SR_SCREEN2_VEC4) ? (i < 20 ? (i / 4) * 5 + (i % 4) : (i - 20) * 5 + 4) : i;
-}
 
 __device__ __forceinline__ int32_t lds_b32(unsigned addr) {
     int32_t v;
@@ -75,8 +89,8 @@ struct Screen2Cold {
 __device__ __forceinline__ int screen2_pid(const MatchArgs &a, int first_pid, int o) { return min(first_pid + o, a.rows * a.w - 1); }
 
 // exact evaluation of one queued candidate of lane `o` (FP64, the reference's filter)
-template <int R>
-__device__ __forceinline__ double screen2_exact_cost(const MatchArgs &a, const Screen2Smem &sm, int first_pid, int o, int lab, int tap) {
+template <int R, bool STATS>
+__device__ __forceinline__ double screen2_exact_cost(const MatchArgs &a, const Screen2Smem<STATS> &sm, int first_pid, int o, int lab, int tap) {
     const int j = (lab >> 16) & 0xff;
     const int tx = tap & 0xffff, ty = (int)((uint32_t)tap >> 16);
     const int opid = screen2_pid(a, first_pid, o);
@@ -88,12 +102,12 @@ __device__ __forceinline__ double screen2_exact_cost(const MatchArgs &a, const S
 }
 
 template <bool STATS>
-__device__ __forceinline__ void screen2_stats_verified(Screen2Smem &sm, int lane, int o, int q, int lab, double cost) {
+__device__ __forceinline__ void screen2_stats_verified(Screen2Smem<STATS> &sm, int lane, int o, int q, double cost) {
     if (!STATS) return;
     ++sm.st_verified[lane];
-    if (sm.q_c32[q][o] < 2.0f) {  // |ncc32 - ncc64| relative to its error bar
-        const float eb = (lab >> 30) ? SCREEN_EPS_TIGHT : SCREEN_EPS_LOOSE;
-        const float c32 = sm.q_c32[q][o] - eb;
+    if (sm.q_ub[q][o] < 2.0f) {  // |ncc32 - ncc64| relative to its error bar
+        const float eb = sm.q_eps[q][o];
+        const float c32 = sm.q_ub[q][o] - eb;
         const float err = fabsf((float)(cost - (double)c32));
         sm.st_maxerr[lane] = fmaxf(sm.st_maxerr[lane], err);
         if (err > eb) ++sm.st_viol[lane];
@@ -101,15 +115,17 @@ __device__ __forceinline__ void screen2_stats_verified(Screen2Smem &sm, int lane
 }
 
 // Queued labels whose upper bound has fallen below the (risen) lower bound cannot win.
-__device__ __forceinline__ int screen2_evict(Screen2Smem &sm, int lane, int qn, float lower32) {
+template <bool STATS>
+__device__ __forceinline__ int screen2_evict(Screen2Smem<STATS> &sm, int lane, int qn, float lower32) {
     int kept = 0;
     for (int q = 0; q < qn; ++q) {
-        const float uq = sm.q_c32[q][lane];
+        const float uq = sm.q_ub[q][lane];
         if (uq >= lower32) {
             if (kept != q) {
-                sm.q_c32[kept][lane] = uq;
+                sm.q_ub[kept][lane] = uq;
                 sm.q_lab[kept][lane] = sm.q_lab[q][lane];
                 sm.q_tap[kept][lane] = sm.q_tap[q][lane];
+                if (STATS) sm.q_eps[kept][lane] = sm.q_eps[q][lane];
             }
             ++kept;
         }
@@ -123,9 +139,9 @@ __device__ __forceinline__ int screen2_evict(Screen2Smem &sm, int lane, int qn, 
 // own entries in order.  Curve mode: candidates are (ncc, z) pairs, z = closest approach of the two
 // viewing rays (:583-588); each lane walks its own queue.
 template <int R, bool STATS>
-__device__ __noinline__ float screen2_flush(const MatchArgs &a, Screen2Smem &sm, int lane, int first_pid, int qn, float lower32) {
+__device__ __noinline__ float screen2_flush(const MatchArgs &a, Screen2Smem<STATS> &sm, int lane, int first_pid, int qn, float lower32) {
     constexpr unsigned FULL = 0xffffffffu;
-    qn = screen2_evict(sm, lane, qn, lower32);
+    qn = screen2_evict<STATS>(sm, lane, qn, lower32);
     double bestC = sm.px_bestC[lane];
     int bestIdx = sm.px_bestIdx[lane];
     if (a.curve) {
@@ -136,8 +152,8 @@ __device__ __noinline__ float screen2_flush(const MatchArgs &a, Screen2Smem &sm,
         for (int q = 0; q < qn; ++q) {
             const int lab = sm.q_lab[q][lane], tap = sm.q_tap[q][lane];
             const int j = (lab >> 16) & 0xff, d = lab & 0xffff;
-            const double cost = screen2_exact_cost<R>(a, sm, first_pid, lane, lab, tap);
-            screen2_stats_verified<STATS>(sm, lane, lane, q, lab, cost);
+            const double cost = screen2_exact_cost<R, STATS>(a, sm, first_pid, lane, lab, tap);
+            screen2_stats_verified<STATS>(sm, lane, lane, q, cost);
             if (cost > a.ncc_threshold && (bestIdx == SR_INDEX_NONE || cost >= bestC)) {
                 const int tx = tap & 0xffff, ty = (int)((uint32_t)tap >> 16);
                 const double z = curve_depth(a.raysL, a.raysR[j], (size_t)w * h, pix, (size_t)ty * w + tx, a.camR, a.camT);
@@ -164,15 +180,15 @@ __device__ __noinline__ float screen2_flush(const MatchArgs &a, Screen2Smem &sm,
         for (int e = lane; e < total; e += 32) {
             const int o = ent[e] >> 8, q = ent[e] & 0xff;
             const int lab = sm.q_lab[q][o], tap = sm.q_tap[q][o];
-            const double cost = screen2_exact_cost<R>(a, sm, first_pid, o, lab, tap);
-            screen2_stats_verified<STATS>(sm, lane, o, q, lab, cost);
+            const double cost = screen2_exact_cost<R, STATS>(a, sm, first_pid, o, lab, tap);
+            screen2_stats_verified<STATS>(sm, lane, o, q, cost);
             sm.q_tap[q][o] = __double2loint(cost);
-            sm.q_c32[q][o] = __int_as_float(__double2hiint(cost));
+            sm.q_ub[q][o] = __int_as_float(__double2hiint(cost));
         }
         __syncwarp();
         const bool depth_up = a.depth_up != 0;
         for (int q = 0; q < qn; ++q) {
-            const double cost = __hiloint2double(__float_as_int(sm.q_c32[q][lane]), sm.q_tap[q][lane]);
+            const double cost = __hiloint2double(__float_as_int(sm.q_ub[q][lane]), sm.q_tap[q][lane]);
             const int d = sm.q_lab[q][lane] & 0xffff;
             if (cost > a.ncc_threshold) {
                 const bool deeper = depth_up ? (d > bestIdx) : (d < bestIdx);
@@ -191,10 +207,10 @@ __device__ __noinline__ float screen2_flush(const MatchArgs &a, Screen2Smem &sm,
     return lower32;
 }
 
-// End of a chunk: the lanes' marked labels (bits of `pend`, upper bounds in sm.c32_ring) go through the queue; a queue that is full even after eviction makes the warp flush.
+// End of a chunk: the lanes' marked labels (bits of `pend`, upper bounds in sm.ub_ring) go through the queue; a queue that is full even after eviction makes the warp flush.
 template <int R, bool STATS>
-__device__ __noinline__ Screen2Cold screen2_process_pending(const MatchArgs &a, Screen2Smem &sm, int lane, int first_pid, int j, int d0,
-                                                            int buf, int qn, unsigned pend, unsigned tight, float lower32) {
+__device__ __noinline__ Screen2Cold screen2_process_pending(const MatchArgs &a, Screen2Smem<STATS> &sm, int lane, int first_pid, int j, int d0,
+                                                            int buf, int qn, unsigned pend, float lower32) {
     constexpr unsigned FULL = 0xffffffffu;
     const bool depth_up = a.depth_up != 0;
 #pragma unroll 1
@@ -202,16 +218,15 @@ __device__ __noinline__ Screen2Cold screen2_process_pending(const MatchArgs &a, 
 #pragma unroll 1
         while (pend) {
             if (qn == SCREEN_QCAP) {
-                qn = screen2_evict(sm, lane, qn, lower32);
+                qn = screen2_evict<STATS>(sm, lane, qn, lower32);
                 if (qn == SCREEN_QCAP) break;  // still full: the warp flushes
             }
             const int l = __ffs(pend) - 1;
             pend &= pend - 1;
-            const float ub = sm.c32_ring[l][lane];  // ncc32 + eps, or SCREEN_FORCE
-            const bool is_tight = (tight >> l) & 1u;  // (statistics only)
-            if (!(ub >= lower32)) continue;  // the bound rose after this label was marked
+            const float ub = sm.ub_ring[l][lane];  // ncc32 + eps, or SCREEN_FORCE
+            if (!(ub >= lower32)) continue;        // the bound rose after this label was marked
             const int32_t tap = sm.tap_ring[buf][l][lane];
-            const int lab = (is_tight ? (1 << 30) : 0) | (j << 16) | (d0 + l);
+            const int lab = (j << 16) | (d0 + l);
             if (qn > 0 && sm.q_tap[qn - 1][lane] == tap && ((sm.q_lab[qn - 1][lane] >> 16) & 0xff) == j) {
                 // equal cost by construction: the tie-break picks the deeper label (curve mode: the same
                 // pixel is the same (ncc, z) pair, nothing to add)
@@ -219,7 +234,8 @@ __device__ __noinline__ Screen2Cold screen2_process_pending(const MatchArgs &a, 
             } else {
                 sm.q_lab[qn][lane] = lab;
                 sm.q_tap[qn][lane] = tap;
-                sm.q_c32[qn][lane] = ub;
+                sm.q_ub[qn][lane] = ub;
+                if (STATS) sm.q_eps[qn][lane] = sm.eps_ring[l][lane];
                 ++qn;
             }
         }
@@ -237,28 +253,30 @@ __device__ __noinline__ Screen2Cold screen2_process_pending(const MatchArgs &a, 
 template <int R, bool STATS, int PITCH>
 struct Screener {
     static constexpr int WS = 2 * R + 1, WN = WS * WS;
-    static constexpr bool VEC4 = (R == 2) && (SR_SCREEN2_VEC4 != 0);
     static constexpr unsigned FULL = 0xffffffffu;
+    static constexpr bool ONEPASS = SR_SCREEN2_ONEPASS != 0;
 
     const MatchArgs &a;
-    Screen2Smem &sm;
+    Screen2Smem<STATS> &sm;
     const int lane;
-    float wtf[WN], dlf[WN];
-    float inv_totWf, ninact_f, lower32;
+    // wtf: support weights; c1f: one-pass dl_i w_i / sqrt(s2), two-pass dl_i / sqrt(s2)
+    float wtf[WN], c1f[WN];
+    // one-pass: k0 = 2 totW - n_a, k1 = SDL / sqrt(s2), error bar e0 + e1 * kappa
+    // two-pass: k0 = n_inactive, e0 = the pixel's error-bar class
+    float inv_totWf, k0, k1, e0, e1, lower32;
     int qn, my_win_w, first_pid;
-    unsigned pend, tight;  // tight: SR_MATCH_STATS only
-    bool alive, pix_tight;
+    unsigned pend;
+    bool alive;
     int n_forced, n_screened;  // STATS only
 
-    __device__ __forceinline__ Screener(const MatchArgs &a_, Screen2Smem &sm_, int lane_) : a(a_), sm(sm_), lane(lane_) {}
+    __device__ __forceinline__ Screener(const MatchArgs &a_, Screen2Smem<STATS> &sm_, int lane_) : a(a_), sm(sm_), lane(lane_) {}
 
     // ---- per-pixel invariants in FP64, as sr_match_screen.cuh ---------------------------------
     // The warp's pixels are first_pid_ .. first_pid_ + nvalid - 1 of the band (lanes >= nvalid have none).
     __device__ __forceinline__ void init(int first_pid_, int nvalid) {
         first_pid = first_pid_;
         const int w = a.w, h = a.h;
-        const int npix_i = a.rows * w;
-        const size_t npix = (size_t)npix_i;
+        const size_t npix = (size_t)a.rows * w;
         const bool in_band = lane < nvalid;
         const int pid = screen2_pid(a, first_pid, lane);
         const int x = pid % w, y = a.row0 + pid / w;
@@ -272,7 +290,7 @@ struct Screener {
         double wt[WN], gl[WN];
         double totW = 0.0, SL = 0.0;
         int ninact = 0;
-        // the reference's summation order is row-major k: accumulate in that order, store by slot
+        // (the reference's summation order, row-major: these sums also feed the exact verification)
 #pragma unroll
         for (int k = 0; k < WN; ++k) {
             const int row = k / WS - R, col = k % WS - R;
@@ -293,25 +311,38 @@ struct Screener {
             }
         }
         const double meanL = SL / totW;
-        double s2 = 0.0;
+        double s2 = 0.0, SDL = 0.0;
 #pragma unroll
         for (int k = 0; k < WN; ++k) {
             const double dl = (wt[k] > 0.0) ? wt[k] * gl[k] - meanL : 0.0;
             s2 += dl * dl;
+            SDL += dl;
             gl[k] = dl;
         }
         const bool all_slow = !(totW >= 1e-10) || !(s2 >= (double)WN) || !(s2 < 1e30);
-        const double rs2 = all_slow ? 0.0 : 1.0 / sqrt(s2);  // dlf carries 1/sqrt(s2): ncc32 = s1 * rsqrt(s3)
+        const double rs2 = all_slow ? 0.0 : 1.0 / sqrt(s2);  // folded into c1f: ncc32 = s1 * rsqrt(s3)
 #pragma unroll
         for (int i = 0; i < WN; ++i) {
-            const int k = screen2_slot_tap<R>(i);
-            wtf[i] = (float)wt[k];
-            dlf[i] = (float)(gl[k] * rs2);
+            wtf[i] = (float)wt[i];
+            c1f[i] = ONEPASS ? (float)((gl[i] * rs2) * wt[i]) : (float)(gl[i] * rs2);
         }
         const bool has_inactive = ninact != 0;
-        pix_tight = (s2 >= 100.0 * WN) && !has_inactive;
         inv_totWf = (float)(1.0 / totW);
-        ninact_f = (float)ninact;
+        if (ONEPASS) {
+            const double na = (double)(WN - ninact);
+            const double sigma = fabs(SDL * rs2) * sqrt(na) / totW;
+            const double u = 5.9604644775390625e-8;  // 2^-24
+            k0 = (float)(2.0 * totW - na);
+            k1 = (float)(SDL * rs2);
+            e0 = (float)(1.5 * u * (6.0 + 7.5 * sigma) + 3e-7);
+            e1 = (float)(1.5 * u * (29.0 + 7.5 * sigma));
+            if (!(e1 < 1.0f)) e1 = 1.0f;  // (all_slow pixels: unused)
+        } else {
+            k0 = (float)ninact;
+            k1 = 0.0f;
+            e0 = (s2 >= 100.0 * WN && !has_inactive) ? SCREEN_EPS_TIGHT : SCREEN_EPS_LOOSE;
+            e1 = 0.0f;
+        }
         // lanes that screen nothing (no pixel, or an ill-conditioned reference window that only the exact
         // filter may judge) see an empty interior: every evaluable tap of theirs is FORCEd
         my_win_w = (alive && !all_slow) ? a.win_w : 0;
@@ -326,117 +357,192 @@ struct Screener {
             sm.st_verified[lane] = sm.st_viol[lane] = 0;
             sm.st_maxerr[lane] = 0.0f;
         }
-        asm volatile("" : "+f"(inv_totWf), "+f"(ninact_f));
+        // keep the FP32 constants as values of their own (not re-derived from FP64 inside the label loop)
+        asm volatile("" : "+f"(inv_totWf), "+f"(k0), "+f"(k1), "+f"(e0), "+f"(e1));
         qn = 0;
-        pend = tight = 0u;
+        pend = 0u;
         lower32 = (float)a.ncc_threshold - 1e-6f;
         n_forced = n_screened = 0;
         if (STATS && alive && all_slow && a.stats) atomicAdd(a.stats + 4, 1ull);
         __syncwarp();
     }
 
-    // ---- FP32 screen of one interior tap ---------------------------------------------------------
-    // gplane: the neighbour's FP32 gray plane (VEC4: the first of its four shifted copies).
-    // Returns the upper bound ncc32 + eps (SCREEN_FORCE when FP64 has to decide) and the lower bound
-    // ncc32 - eps (SCREEN_SKIP then); is_tight = the label's error bar is SCREEN_EPS_TIGHT.
-    __device__ __forceinline__ float screen_one(const float *__restrict__ gplane, int tx, int ty, float &lb_out, bool &is_tight) const {
+    // ---- FP32 screen of NL interior taps at once ---------------------------------------------------
+    // idx[n]: element index of the window centre in the neighbour's FP32 plane.  The NL windows are
+    // independent chains of one basic block: the scheduler overlaps one label's load latency and
+    // dependent FFMA2 chains with the other's (the loop is latency-bound per warp, not issue-bound).
+    // Outputs per label: ub = ncc32 + eps (SCREEN_FORCE when FP64 has to decide), lb = ncc32 - eps
+    // (SCREEN_SKIP then), eps (statistics).
+    template <int NL>
+    __device__ __forceinline__ void screen_n(const float *__restrict__ gplane, const int (&idx)[NL], float (&ub)[NL], float (&lb)[NL],
+                                             float (&eps_out)[NL]) const {
         const int fp = PITCH ? PITCH : a.pitch_f;
-        float g[WN];
-        if (VEC4) {
-            // copy s holds pixel x at index x + s; s = (2 - tx) & 3 aligns the window's left edge
-            // (e = tx - 2 + s is a multiple of 4); 32-bit index arithmetic: 4 copies < 2^31 floats
-            const int s = (2 - tx) & 3;
-            const int idx = s * a.plane4_stride + (ty * fp + tx) + s;
-            const float *__restrict__ p = gplane + idx;
+        constexpr int NP = WN / 2;  // WN is odd: NP pairs + one scalar tap
+        float g[NL][WN];
 #pragma unroll
-            for (int row = 0; row < WS; ++row) {
-                const float4 v = *reinterpret_cast<const float4 *>(p + ((row - R) * fp - 2));
-                g[4 * row + 0] = v.x;
-                g[4 * row + 1] = v.y;
-                g[4 * row + 2] = v.z;
-                g[4 * row + 3] = v.w;
-                g[20 + row] = p[(row - R) * fp + 2];
-            }
-        } else {
-            const float *__restrict__ base = gplane + (ty * fp + tx);
+        for (int n = 0; n < NL; ++n) {
+#if SR_SCREEN2_ABL == 3  // ablation: warp-aligned (broadcast) loads
+            const float *__restrict__ base = gplane + ((idx[n] & ~31) + 2);
+#else
+            const float *__restrict__ base = gplane + idx[n];
+#endif
+#if SR_SCREEN2_ABL == 1  // ablation: no window loads
+#pragma unroll
+            for (int i = 0; i < WN; ++i) g[n][i] = __int_as_float(idx[n] + i);
+#else
 #pragma unroll
             for (int row = 0; row < WS; ++row)
 #pragma unroll
-                for (int col = 0; col < WS; ++col) g[row * WS + col] = base[(row - R) * fp + (col - R)];
+                for (int col = 0; col < WS; ++col) g[n][row * WS + col] = base[(row - R) * fp + (col - R)];
+#endif
         }
-        constexpr int NP = WN / 2;  // WN is odd: NP pairs + one scalar tap
-        float2 S1p[2] = {make_float2(0.0f, 0.0f), make_float2(0.0f, 0.0f)};
 #pragma unroll
-        for (int p = 0; p < NP; ++p)
-            S1p[p & 1] = fma2(make_float2(wtf[2 * p], wtf[2 * p + 1]), make_float2(g[2 * p], g[2 * p + 1]), S1p[p & 1]);
-        float S1 = (S1p[0].x + S1p[1].x) + (S1p[0].y + S1p[1].y);
-        S1 = fmaf(wtf[WN - 1], g[WN - 1], S1);
-        const float mR = S1 * inv_totWf;
-        const float2 nm = make_float2(-mR, -mR);
-        float2 s3p[2] = {make_float2(0.0f, 0.0f), make_float2(0.0f, 0.0f)};
-        float2 s1p[2] = {make_float2(0.0f, 0.0f), make_float2(0.0f, 0.0f)};
+        for (int n = 0; n < NL; ++n) {
+            float c32, eps;
+            bool ok;
+            if (ONEPASS) {
+                float2 S1p[2] = {make_float2(0.0f, 0.0f), make_float2(0.0f, 0.0f)};
+                float2 Qp[2] = {make_float2(0.0f, 0.0f), make_float2(0.0f, 0.0f)};
+                float2 Xp[2] = {make_float2(0.0f, 0.0f), make_float2(0.0f, 0.0f)};
+                const float2 zero = make_float2(0.0f, 0.0f);
 #pragma unroll
-        for (int p = 0; p < NP; ++p) {
-            const float2 t = fma2(make_float2(wtf[2 * p], wtf[2 * p + 1]), make_float2(g[2 * p], g[2 * p + 1]), nm);
-            s3p[p & 1] = fma2(t, t, s3p[p & 1]);
-            s1p[p & 1] = fma2(make_float2(dlf[2 * p], dlf[2 * p + 1]), t, s1p[p & 1]);
+                for (int p = 0; p < NP; ++p) {
+                    const float2 wv = make_float2(wtf[2 * p], wtf[2 * p + 1]), gv = make_float2(g[n][2 * p], g[n][2 * p + 1]);
+                    S1p[p & 1] = fma2(wv, gv, S1p[p & 1]);
+#if SR_SCREEN2_ABL != 2  // ablation 2: loads + one accumulation only
+                    const float2 pv = fma2(wv, gv, zero);
+                    Qp[p & 1] = fma2(pv, pv, Qp[p & 1]);
+                    Xp[p & 1] = fma2(make_float2(c1f[2 * p], c1f[2 * p + 1]), gv, Xp[p & 1]);
+#endif
+                }
+                float S1 = (S1p[0].x + S1p[1].x) + (S1p[0].y + S1p[1].y);
+                float Q = (Qp[0].x + Qp[1].x) + (Qp[0].y + Qp[1].y);
+                float X = (Xp[0].x + Xp[1].x) + (Xp[0].y + Xp[1].y);
+                {
+                    const float pl = wtf[WN - 1] * g[n][WN - 1];
+                    S1 += pl;
+                    Q = fmaf(pl, pl, Q);
+                    X = fmaf(c1f[WN - 1], g[n][WN - 1], X);
+                }
+                const float mR = S1 * inv_totWf;
+                const float s3 = fmaf(-k0, mR * mR, Q);
+                const float s1 = fmaf(-mR, k1, X);
+                float rs;
+                asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(rs) : "f"(s3));
+                c32 = s1 * rs;
+                eps = fmaf(Q * (rs * rs), e1, e0);  // e0 + e1 * kappa
+                // ill-conditioned or non-finite neighbour window, or a bar too wide to be first order: FP64 decides
+                ok = (s3 >= (float)WN) && (eps <= SCREEN_EPS_MAX);
+            } else {
+                float2 S1p[2] = {make_float2(0.0f, 0.0f), make_float2(0.0f, 0.0f)};
+#pragma unroll
+                for (int p = 0; p < NP; ++p)
+                    S1p[p & 1] = fma2(make_float2(wtf[2 * p], wtf[2 * p + 1]), make_float2(g[n][2 * p], g[n][2 * p + 1]), S1p[p & 1]);
+                float S1 = (S1p[0].x + S1p[1].x) + (S1p[0].y + S1p[1].y);
+                S1 = fmaf(wtf[WN - 1], g[n][WN - 1], S1);
+                const float mR = S1 * inv_totWf;
+                const float2 nm = make_float2(-mR, -mR);
+                float2 s3p[2] = {make_float2(0.0f, 0.0f), make_float2(0.0f, 0.0f)};
+                float2 s1p[2] = {make_float2(0.0f, 0.0f), make_float2(0.0f, 0.0f)};
+#pragma unroll
+                for (int p = 0; p < NP; ++p) {
+                    const float2 t = fma2(make_float2(wtf[2 * p], wtf[2 * p + 1]), make_float2(g[n][2 * p], g[n][2 * p + 1]), nm);
+                    s3p[p & 1] = fma2(t, t, s3p[p & 1]);
+                    s1p[p & 1] = fma2(make_float2(c1f[2 * p], c1f[2 * p + 1]), t, s1p[p & 1]);
+                }
+                float s3a = (s3p[0].x + s3p[1].x) + (s3p[0].y + s3p[1].y);
+                float s1 = (s1p[0].x + s1p[1].x) + (s1p[0].y + s1p[1].y);
+                {
+                    const float t = fmaf(wtf[WN - 1], g[n][WN - 1], -mR);
+                    s3a = fmaf(t, t, s3a);
+                    s1 = fmaf(c1f[WN - 1], t, s1);
+                }
+                // inactive taps (w = dl = 0) contributed (-mR)^2 each to s3a and nothing to s1; the label is
+                // FORCEd when that correction exceeds SCREEN_CORR_MAX * s3 (relative error of s3 <= 15u * 101,
+                // inside SCREEN_EPS_LOOSE, which such pixels always use)
+                const float s3 = fmaf(-k0, mR * mR, s3a);
+                eps = (s3 >= 100.0f * WN) ? e0 : SCREEN_EPS_LOOSE;
+                float rs;
+                asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(rs) : "f"(s3));
+                c32 = s1 * rs;
+                ok = (s3 >= (float)WN) && (s3 < 1e30f) && (s3a <= (SCREEN_CORR_MAX + 1.0f) * s3);
+            }
+            eps_out[n] = eps;
+#if SR_SCREEN2_ABL  // ablations: the arithmetic stays alive, no label ever becomes a candidate
+            lb[n] = SCREEN_SKIP;
+            ub[n] = (ok && c32 > 1e30f) ? c32 + eps : SCREEN_SKIP;
+#else
+            lb[n] = ok ? c32 - eps : SCREEN_SKIP;
+            ub[n] = ok ? c32 + eps : SCREEN_FORCE;
+#endif
         }
-        float s3a = (s3p[0].x + s3p[1].x) + (s3p[0].y + s3p[1].y);
-        float s1 = (s1p[0].x + s1p[1].x) + (s1p[0].y + s1p[1].y);
-        {
-            const float t = fmaf(wtf[WN - 1], g[WN - 1], -mR);
-            s3a = fmaf(t, t, s3a);
-            s1 = fmaf(dlf[WN - 1], t, s1);
+    }
+
+    // NL consecutive labels of a chunk: ring entries at shared addresses ra, ra + 128, ...; `bit` = mask bit
+    // of the first.  Labels whose window is not interior to the neighbour image are FORCEd (or skipped when
+    // the tap is TAP_NONE); a lane with at least one interior label evaluates all NL (the others at a safe
+    // address, result discarded).
+    template <int NL>
+    __device__ __forceinline__ void labels(const float *__restrict__ gplane, unsigned ra, unsigned ca, unsigned bit, int l) {
+        const int fp = PITCH ? PITCH : a.pitch_f;
+        const unsigned win_h = (unsigned)a.win_h;
+        int32_t tap[NL];
+        int idx[NL];
+        bool interior[NL], any = false;
+#pragma unroll
+        for (int n = 0; n < NL; ++n) {
+            tap[n] = lds_b32(ra + 128u * n);
+            const int tx = tap[n] & 0xffff, ty = (int)((uint32_t)tap[n] >> 16);  // MVS taps lie inside the image; TAP_NONE -> ty = 32768
+            interior[n] = (unsigned)(tx - R) < (unsigned)my_win_w && (unsigned)(ty - R) < win_h;
+            idx[n] = interior[n] ? ty * fp + tx : R * fp + R;
+            any = any || interior[n];
         }
-        // inactive taps contributed (-mR)^2 each to s3a and nothing to s1
-        const float s3 = fmaf(-ninact_f, mR * mR, s3a);
-        is_tight = pix_tight && (s3 >= 100.0f * WN);
-        const float eps = is_tight ? SCREEN_EPS_TIGHT : SCREEN_EPS_LOOSE;
-        float rs;
-        asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(rs) : "f"(s3));
-        const float c32 = s1 * rs;
-        // ill-conditioned, non-finite or cancellation-dominated neighbour window (correction s3a - s3 above
-        // SCREEN_CORR_MAX * s3): FP64 decides
-        const bool ok = (s3 >= (float)WN) && (s3 < 1e30f) && (s3a <= (SCREEN_CORR_MAX + 1.0f) * s3);
-        lb_out = ok ? c32 - eps : SCREEN_SKIP;
-        return ok ? c32 + eps : SCREEN_FORCE;
+        if (any) {
+            float ub[NL], lb[NL], eps[NL];
+            screen_n<NL>(gplane, idx, ub, lb, eps);
+#pragma unroll
+            for (int n = 0; n < NL; ++n) {
+                if (NL == 1 || interior[n]) {
+                    sts_f32(ca + 128u * n, ub[n]);
+                    lower32 = fmaxf(lower32, lb[n]);
+                    pend |= (ub[n] >= lower32) ? (bit << n) : 0u;
+                    if (STATS) {
+                        sm.eps_ring[l + n][lane] = eps[n];
+                        if (ub[n] == SCREEN_FORCE) ++n_forced;
+                        else ++n_screened;
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int n = 0; n < NL; ++n) {
+            if (!interior[n] && tap[n] != TAP_NONE && alive) {  // window on the neighbour's border / FP64-only pixel
+                sts_f32(ca + 128u * n, SCREEN_FORCE);
+                pend |= bit << n;
+                if (STATS) ++n_forced;
+            }
+        }
     }
 
     // ---- one chunk of labels of neighbour j: taps in sm.tap_ring[buf][0..nl) -----------------------
     __device__ __forceinline__ void chunk(int j, int d0, int nl, int buf, const float *__restrict__ gplane) {
         unsigned ra = (unsigned)__cvta_generic_to_shared(&sm.tap_ring[buf][0][lane]);
-        unsigned ca = (unsigned)__cvta_generic_to_shared(&sm.c32_ring[0][lane]);
+        unsigned ca = (unsigned)__cvta_generic_to_shared(&sm.ub_ring[0][lane]);
         unsigned bit = 1u;
-        const unsigned win_h = (unsigned)a.win_h;
+        constexpr int NL = SR_SCREEN2_NL;
+        int l = 0;
 #pragma unroll 1
-        for (int l = 0; l < nl; ++l, ra += 128u, ca += 128u, bit <<= 1) {
-            const int32_t tap = lds_b32(ra);
-            const int tx = tap & 0xffff, ty = (int)((uint32_t)tap >> 16);  // MVS taps lie inside the image; TAP_NONE -> ty = 32768
-            if ((unsigned)(tx - R) < (unsigned)my_win_w && (unsigned)(ty - R) < win_h) {
-                float lb;
-                bool is_tight;
-                const float ub = screen_one(gplane, tx, ty, lb, is_tight);
-                sts_f32(ca, ub);
-                lower32 = fmaxf(lower32, lb);
-                pend |= (ub >= lower32) ? bit : 0u;
-                if (STATS) {
-                    tight |= is_tight ? bit : 0u;
-                    if (ub == SCREEN_FORCE) ++n_forced;
-                    else ++n_screened;
-                }
-            } else if (tap != TAP_NONE && alive) {  // window on the neighbour's border / FP64-only pixel
-                sts_f32(ca, SCREEN_FORCE);
-                pend |= bit;
-                if (STATS) ++n_forced;
-            }
+        for (; l + NL <= nl; l += NL, ra += 128u * NL, ca += 128u * NL, bit <<= NL) labels<NL>(gplane, ra, ca, bit, l);
+        if (NL > 1) {
+#pragma unroll 1
+            for (; l < nl; ++l, ra += 128u, ca += 128u, bit <<= 1) labels<1>(gplane, ra, ca, bit, l);
         }
         if (__any_sync(FULL, pend != 0u)) {
-            const Screen2Cold r = screen2_process_pending<R, STATS>(a, sm, lane, first_pid, j, d0, buf, qn, pend, tight, lower32);
+            const Screen2Cold r = screen2_process_pending<R, STATS>(a, sm, lane, first_pid, j, d0, buf, qn, pend, lower32);
             qn = r.qn;
             lower32 = r.lower32;
             pend = 0u;
         }
-        tight = 0u;
     }
 
     __device__ __forceinline__ void finish() {
@@ -446,10 +552,10 @@ struct Screener {
             atomicAdd(a.stats + 0, 1ull);
             atomicAdd(a.stats + 1, (unsigned long long)n_screened);
             atomicAdd(a.stats + 2, (unsigned long long)n_forced);
-            atomicAdd(a.stats + 6, (unsigned long long)sm.st_viol[lane]);
         }
         if (STATS && a.stats) {  // verifications are counted by the lane that ran them
             atomicAdd(a.stats + 3, (unsigned long long)sm.st_verified[lane]);
+            atomicAdd(a.stats + 6, (unsigned long long)sm.st_viol[lane]);
             atomicMax(a.stats + 5, (unsigned long long)__float_as_uint(sm.st_maxerr[lane]));  // positive floats order as integers
         }
         if (alive) {
@@ -466,19 +572,21 @@ struct Screener {
 #ifndef SR_SCREEN2_TILE_ROWS
 #define SR_SCREEN2_TILE_ROWS 8  // warps per block: a block owns a 32 x TILE_ROWS tile of reference pixels
 #endif
+#ifndef SR_SCREEN2_MINBLOCKS
+#define SR_SCREEN2_MINBLOCKS 2  // resident blocks per SM the register allocation must allow
+#endif
 constexpr int SCREEN2_TILE_ROWS = SR_SCREEN2_TILE_ROWS;
-constexpr int SCREEN2_WARPS_PER_SM = 16;
 
 // Stand-alone form: the tap volume comes from HBM (label mode: build kernels; curve mode: the curve
 // rasteriser) through the two-stage cp.async ring.  The warps of a block are independent (nothing is
 // block-wide); they own the rows of a 32-pixel-wide tile so that their neighbour-image footprints overlap
 // in L1 (adjacent reference rows project to adjacent neighbour rows).  grid = (ceil(w/32), ceil(rows/TR)).
 template <int R, bool STATS, int PITCH>
-__global__ void __launch_bounds__(32 * SCREEN2_TILE_ROWS, SCREEN2_WARPS_PER_SM / SCREEN2_TILE_ROWS)
+__global__ void __launch_bounds__(32 * SCREEN2_TILE_ROWS, SR_SCREEN2_MINBLOCKS)
     match_mvs_screen2_kernel(const __grid_constant__ MatchArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    Screen2Smem &sm = reinterpret_cast<Screen2Smem *>(smem_raw)[warp];
+    Screen2Smem<STATS> &sm = reinterpret_cast<Screen2Smem<STATS> *>(smem_raw)[warp];
     const int x0 = blockIdx.x * 32, row = blockIdx.y * SCREEN2_TILE_ROWS + warp;  // row within the band
     const int nvalid = (row < a.rows) ? min(32, a.w - x0) : 0;
     const int first_pid = min(row, a.rows - 1) * a.w + x0;
@@ -511,7 +619,7 @@ __global__ void __launch_bounds__(32 * SCREEN2_TILE_ROWS, SCREEN2_WARPS_PER_SM /
     int buf = 0;
 #pragma unroll 1
     for (int j = 0; j < a.num_nbrs; ++j) {
-        const float *__restrict__ gplane = Screener<R, STATS, PITCH>::VEC4 ? a.grayRf4[j] : a.grayRf[j];
+        const float *__restrict__ gplane = a.grayRf[j];
 #pragma unroll 1
         for (int d0 = 0; d0 < D; d0 += TAP_CHUNK, buf ^= 1) {
             issue_next();
@@ -526,7 +634,7 @@ __global__ void __launch_bounds__(32 * SCREEN2_TILE_ROWS, SCREEN2_WARPS_PER_SM /
 template <int R, bool STATS, int PITCH>
 cudaError_t launch_screen2(const MatchArgs &a, cudaStream_t st) {
     auto kern = match_mvs_screen2_kernel<R, STATS, PITCH>;
-    constexpr size_t smem = sizeof(Screen2Smem) * SCREEN2_TILE_ROWS;
+    constexpr size_t smem = sizeof(Screen2Smem<STATS>) * SCREEN2_TILE_ROWS;
     if (smem > 48 * 1024) {  // (per device: set on every launch, it is cheap)
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
