@@ -51,6 +51,8 @@ public:
         this->crossCheckThreshold = crossCheckThreshold;
         this->imageScale = imageScale;
         this->views.clear();
+        peakPairs_.clear();
+        inMemory_ = false;
         images.clear();
         masks.clear();
         results.clear();
@@ -93,9 +95,13 @@ public:
     // ---- extensions ------------------------------------------------------------------------
     sr_params &params() { return params_; }
     void setDevice(int device) { device_ = device; }
-    //! true: search along the rasterised epipolar curve, depth from the rays' closest approach —
-    //! the reference's live formulation (multiviewstereo.cpp:574-602); false (default): the
-    //! depth-label cost volume + WTA of the same rule (SURVEY §8a S4 applied to S2).
+    //! true (default): search along the rasterised epipolar curve, depth from the rays' closest approach —
+    //! the reference's live formulation (multiviewstereo.cpp:574-602), so a caller switched over unchanged
+    //! gets the reference's depth maps; false: the depth-label cost volume + WTA of the same rule
+    //! (SURVEY §8a S4 applied to S2: the reference's compiled-out branch, about twice as fast here).
+    //! NOTE imageScale != 1: addView() rescales with this repository's QImage stand-in (bilinear), not Qt's
+    //! scaledToWidth (multiviewstereo.cpp:221) — the scaled pixels, and with them the depth maps, can differ
+    //! from the reference's in the last gray levels.  Pass pre-scaled images to stay bit-comparable.
     void setCurveMode(bool on) { curveMode_ = on; }
     //! true: also keep, per pixel, the K = 9 largest (ncc, depth) candidates of the search — the
     //! reference's CostFunction::peakPairs (multiviewstereo.cpp:479-482,589-602), the input of its
@@ -168,6 +174,14 @@ protected:
                     peakPairs_[v].resize((size_t)w * h * 18);
                     s.check(sr_get_peaks(s.get(), v, peakPairs_[v].data()), "sr_get_peaks");
                 }
+            } else {
+                // no neighbour was selected: the reference's loops find no candidate, which leaves -1 on the
+                // in-mask pixels and +INF on the others (multiviewstereo.cpp:559-565,604)
+                std::vector<double> fill((size_t)w * h);
+                for (int y = 0; y < h; ++y)
+                    for (int x = 0; x < w; ++x)
+                        fill[(size_t)y * w + x] = (masks[v].pixel(x, y) == WHITE) ? -1.0 : std::numeric_limits<double>::infinity();
+                s.check(sr_set_depth(s.get(), v, fill.data()), "sr_set_depth");
             }
         }
         stageUpdate("Constructing depth maps");
@@ -247,6 +261,6 @@ private:
     sr_params params_;
     int device_ = 0;
     bool inMemory_ = false;
-    bool curveMode_ = false;
+    bool curveMode_ = true;   // the reference's live formulation; setCurveMode(false) = depth-label cost volume
 };
 #endif

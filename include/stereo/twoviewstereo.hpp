@@ -119,8 +119,8 @@ public:
     // ---- extensions ------------------------------------------------------------------------
     sr_params &params() { return params_; }
     void setDevice(int device) { device_ = device; }
-    //! true: the reference's live search along the rasterised epipolar curve (twoviewstereo.cpp:285-305);
-    //! false (default): the depth-label cost volume + WTA (the compiled-out branch, :308-329).
+    //! true (default): the reference's live search along the rasterised epipolar curve (twoviewstereo.cpp:285-305);
+    //! false: the depth-label cost volume + WTA (the compiled-out branch, :308-329).
     void setCurveMode(bool on) { curveMode_ = on; }
     void setCrossCheckThreshold(double t) { crossCheckThreshold_ = t; }
     const DepthMap &leftDepths() const { return computedDepthLeft; }
@@ -201,6 +201,6 @@ private:
     double crossCheckThreshold_;
     sr_params params_;
     int device_ = 0;
-    bool curveMode_ = false;
+    bool curveMode_ = true;   // the reference's live formulation; setCurveMode(false) = disparity/depth-label cost volume
 };
 #endif

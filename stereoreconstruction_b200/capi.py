@@ -144,7 +144,7 @@ class Context:
         return dict(pixels=int(out[0]), screened=int(out[1]), forced=int(out[2]), verified=int(out[3]),
                     fp64_only_pixels=int(out[4]),
                     max_screen_err=float(np.array([out[5]], np.uint64).view(np.uint32)[0:1].view(np.float32)[0]),
-                    outside_error_bar=int(out[6]))
+                    outside_error_bar=int(out[6]), prescreen_false_drops=int(out[7]))
 
     # -- setup -------------------------------------------------------------------------
     def set_stream(self, cuda_stream_ptr):
@@ -209,8 +209,8 @@ class Context:
         self._ck(self._L.sr_get_depth_index(self._h, view, _p(out)))
         return out
 
-    def depth(self, view):
-        out = np.empty((self.h, self.w), dtype=np.float64)
+    def depth(self, view, out=None):
+        out = np.empty((self.h, self.w), dtype=np.float64) if out is None else out
         self._ck(self._L.sr_get_depth(self._h, view, _p(out)))
         return out
 

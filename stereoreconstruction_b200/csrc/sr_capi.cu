@@ -55,20 +55,25 @@ NcclApi g_nccl;
 const int NCCL_CHAR = 0;
 
 bool load_nccl(std::string &err) {
-    if (g_nccl.handle) return true;
+    static bool loaded = false;  // set only once every symbol has resolved
+    if (loaded) return true;
     const char *names[] = {"libnccl.so.2", "libnccl.so"};
+    void *handle = nullptr;
     for (const char *n : names) {
-        g_nccl.handle = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
-        if (g_nccl.handle) break;
+        handle = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+        if (handle) break;
     }
-    if (!g_nccl.handle) {
+    if (!handle) {
         err = std::string("cannot dlopen libnccl.so.2: ") + dlerror();
         return false;
     }
+    NcclApi api;
+    api.handle = handle;
 #define LD(field, sym)                                                    \
-    *(void **)(&g_nccl.field) = dlsym(g_nccl.handle, sym);                \
-    if (!g_nccl.field) {                                                  \
+    *(void **)(&api.field) = dlsym(handle, sym);                          \
+    if (!api.field) {                                                     \
         err = std::string("NCCL symbol missing: ") + sym;                 \
+        dlclose(handle);                                                  \
         return false;                                                     \
     }
     LD(GetUniqueId, "ncclGetUniqueId");
@@ -79,6 +84,8 @@ bool load_nccl(std::string &err) {
     LD(GroupEnd, "ncclGroupEnd");
     LD(GetErrorString, "ncclGetErrorString");
 #undef LD
+    g_nccl = api;
+    loaded = true;
     return true;
 }
 
@@ -107,6 +114,7 @@ struct sr_ctx {
     float *d_volume = nullptr;
     size_t vol_cap = 0, vol_elems = 0;
     double *d_peaks = nullptr;  // [9][2][h*w] of the last view run with keep_cost_volume & 2
+    size_t peaks_cap = 0;       // bytes
     int peaks_view = -1;
     void *d_scratch = nullptr;
     size_t scratch_cap = 0;
@@ -176,6 +184,7 @@ void free_views(sr_ctx *c) {
         dfree(v.best);
     }
     c->views.clear();
+    c->peaks_view = -1;  // peak lists belong to the image size they were computed at
     dfree(c->d_cams);
     dfree(c->d_depth_ptrs);
     dfree(c->d_rays);
@@ -342,29 +351,45 @@ int sr_set_views(sr_ctx *ctx, int V, const sr_camera *cams, const uint8_t *const
     if (V != ctx->V || w != ctx->w || h != ctx->h) {
         CK(cudaStreamSynchronize(ctx->stream));
         free_views(ctx);
+        ctx->V = ctx->w = ctx->h = 0;  // nothing is usable until every allocation below has succeeded
         ctx->views.resize(V);
-        for (ViewDev &v : ctx->views) {
-            CK(cudaMalloc(&v.rgba, n * 4));
-            CK(cudaMalloc(&v.mask, n));
-            CK(cudaMalloc(&v.gray_pix, n * 8));
-            CK(cudaMalloc(&v.gray_pix_f, (size_t)screen_pitch(w) * h * 4));
-            CK(cudaMalloc(&v.gray_two, n * 8));
-            CK(cudaMalloc(&v.gray_msk, n * 8));
-            CK(cudaMalloc(&v.edges, n * 8 * 4));
-            CK(cudaMalloc(&v.index, n * 4));
-            CK(cudaMalloc(&v.depth, n * 8));
-            CK(cudaMalloc(&v.best, n * 8));
+        int rc_alloc = [&]() -> int {
+            for (ViewDev &v : ctx->views) {
+                CK(cudaMalloc(&v.rgba, n * 4));
+                CK(cudaMalloc(&v.mask, n));
+                CK(cudaMalloc(&v.gray_pix, n * 8));
+                CK(cudaMalloc(&v.gray_pix_f, (size_t)screen_pitch(w) * h * 4));
+                CK(cudaMalloc(&v.gray_two, n * 8));
+                CK(cudaMalloc(&v.gray_msk, n * 8));
+                CK(cudaMalloc(&v.edges, n * 8 * 4));
+                CK(cudaMalloc(&v.index, n * 4));
+                CK(cudaMalloc(&v.depth, n * 8));
+                CK(cudaMalloc(&v.best, n * 8));
+            }
+            CK(cudaMalloc(&ctx->d_cams, sizeof(sr_camera) * V));
+            CK(cudaMalloc(&ctx->d_depth_ptrs, sizeof(double *) * V));
+            CK(cudaMalloc(&ctx->d_rays, n * 6 * 8));
+            std::vector<double *> ptrs(V);
+            for (int i = 0; i < V; ++i) ptrs[i] = ctx->views[i].depth;
+            CK(cudaMemcpyAsync(ctx->d_depth_ptrs, ptrs.data(), sizeof(double *) * V, cudaMemcpyHostToDevice, ctx->stream));
+            CK(cudaStreamSynchronize(ctx->stream));
+            return SR_OK;
+        }();
+        if (rc_alloc != SR_OK) {
+            free_views(ctx);  // (the error message of the failing call is kept)
+            return rc_alloc;
         }
-        CK(cudaMalloc(&ctx->d_cams, sizeof(sr_camera) * V));
-        CK(cudaMalloc(&ctx->d_depth_ptrs, sizeof(double *) * V));
-        CK(cudaMalloc(&ctx->d_rays, n * 6 * 8));
-        std::vector<double *> ptrs(V);
-        for (int i = 0; i < V; ++i) ptrs[i] = ctx->views[i].depth;
-        CK(cudaMemcpyAsync(ctx->d_depth_ptrs, ptrs.data(), sizeof(double *) * V, cudaMemcpyHostToDevice, ctx->stream));
-        CK(cudaStreamSynchronize(ctx->stream));
         ctx->V = V;
         ctx->w = w;
         ctx->h = h;
+        // A view this context is only told the camera of (another rank computes it) still has defined
+        // results: "not computed" (NaN depth, index NONE) under an all-WHITE mask, until a gather fills them.
+        for (ViewDev &v : ctx->views) {
+            CK(cudaMemsetAsync(v.mask, 255, n, ctx->stream));
+            CK(cudaMemsetAsync(v.depth, 0xff, n * 8, ctx->stream));
+            CK(cudaMemsetAsync(v.best, 0xff, n * 8, ctx->stream));
+            CK(cudaMemsetAsync(v.index, 0xff, n * 4, ctx->stream));
+        }
     }
     ctx->cams.assign(cams, cams + V);
     CK(cudaMemcpyAsync(ctx->d_cams, ctx->cams.data(), sizeof(sr_camera) * V, cudaMemcpyHostToDevice, ctx->stream));
@@ -421,7 +446,13 @@ static int init_peaks(sr_ctx *ctx, int ref) {
     if (!(P.keep_cost_volume & 2)) return SR_OK;
     if (P.select_kind != SR_SELECT_MVS) return fail(ctx, SR_ERR_INVALID, "peak lists belong to the multi-view selection");
     const size_t n = (size_t)ctx->w * ctx->h;
-    if (!ctx->d_peaks) CK(cudaMalloc(&ctx->d_peaks, n * 18 * 8));
+    if (n * 18 * 8 > ctx->peaks_cap) {  // (a context may be given larger images later)
+        CK(cudaStreamSynchronize(ctx->stream));
+        dfree(ctx->d_peaks);
+        ctx->peaks_cap = 0;
+        CK(cudaMalloc(&ctx->d_peaks, n * 18 * 8));
+        ctx->peaks_cap = n * 18 * 8;
+    }
     std::vector<double> init(n * 18);
     for (int k = 0; k < 9; ++k) {
         std::fill(init.begin() + (size_t)(2 * k) * n, init.begin() + (size_t)(2 * k + 1) * n, 0.0);
@@ -579,7 +610,7 @@ int sr_run_view(sr_ctx *ctx, int ref, const int32_t *nbrs, int nn) {
     const size_t n = (size_t)w * h;
     ViewDev &A = ctx->views[ref];
 
-    rays_kernel<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(ctx->cams[ref], w, h, P.image_scale, ctx->d_rays);
+    rays_kernel<<<(unsigned)(((size_t)(r1 - r0) * w + 127) / 128), 128, 0, st>>>(ctx->cams[ref], w, h, r0, r1 - r0, P.image_scale, ctx->d_rays);
     CKL();
 
     {   // MultiViewStereo label path with refractive neighbours: build and screen as one launch
@@ -805,7 +836,7 @@ static int ensure_rays(sr_ctx *ctx, int v) {
     const double scale = ctx->params.image_scale;
     if (!d.rays) CK(cudaMalloc(&d.rays, n * 6 * 8));
     if (d.rays_scale != scale) {
-        rays_kernel<<<(unsigned)((n + 127) / 128), 128, 0, ctx->stream>>>(ctx->cams[v], ctx->w, ctx->h, scale, d.rays);
+        rays_kernel<<<(unsigned)((n + 127) / 128), 128, 0, ctx->stream>>>(ctx->cams[v], ctx->w, ctx->h, 0, ctx->h, scale, d.rays);
         CKL();
         d.rays_scale = scale;
     }
@@ -930,6 +961,8 @@ int sr_run_view_curve(sr_ctx *ctx, int ref, const int32_t *nbrs, int nn) {
             L = std::max(1, (int)hmax);
             if (L <= cap) break;
             if (attempt >= 1) return fail(ctx, SR_ERR_STATE, "curve volume: inconsistent curve lengths");
+            // the match kernels carry a candidate's position in 16 bits (queue entries, index maps)
+            if (L > 65536) return fail(ctx, SR_ERR_INVALID, "an epipolar curve has more than 65536 candidates: narrow the depth range");
             cap = L;  // a longer curve than the volume holds: size the volume to it and fill again
             rows = (int)std::min<size_t>((size_t)rows, std::max<size_t>(1, ctx->tap_budget / ((size_t)nn * cap * w * 4 + per_row_w)));
         }
@@ -1130,7 +1163,7 @@ int sr_unproject_grid(sr_ctx *ctx, int view, double *out) {
     CK(cudaSetDevice(ctx->device));
     const size_t n = (size_t)ctx->w * ctx->h;
     const double scale = ctx->have_params ? ctx->params.image_scale : 1.0;
-    rays_kernel<<<(unsigned)((n + 127) / 128), 128, 0, ctx->stream>>>(ctx->cams[view], ctx->w, ctx->h, scale, ctx->d_rays);
+    rays_kernel<<<(unsigned)((n + 127) / 128), 128, 0, ctx->stream>>>(ctx->cams[view], ctx->w, ctx->h, 0, ctx->h, scale, ctx->d_rays);
     CKL();
     std::vector<double> soa(n * 6);
     rc = d2h(ctx, soa.data(), ctx->d_rays, n * 6 * 8);
@@ -1261,6 +1294,8 @@ int sr_comm_init(sr_ctx *ctx, const void *uid128, int rank, int nranks) {
 int sr_comm_allgather_views(sr_ctx *ctx, const int32_t *owner) {
     if (!ctx || !owner) return SR_ERR_INVALID;
     if (!ctx->comm) return fail(ctx, SR_ERR_STATE, "sr_comm_init has not been called");
+    for (int v = 0; v < ctx->V; ++v)
+        if (owner[v] < 0 || owner[v] >= ctx->nranks) return fail(ctx, SR_ERR_INVALID, "sr_comm_allgather_views: owner rank out of range");
     CK(cudaSetDevice(ctx->device));
     const size_t n = (size_t)ctx->w * ctx->h;
     int r = g_nccl.GroupStart();
@@ -1280,6 +1315,10 @@ int sr_comm_allgather_rows(sr_ctx *ctx, int view, const int32_t *row_begin, cons
     int rc = check_view(ctx, view);
     if (rc) return rc;
     if (!ctx->comm) return fail(ctx, SR_ERR_STATE, "sr_comm_init has not been called");
+    if (!row_begin || !row_end) return fail(ctx, SR_ERR_INVALID, "sr_comm_allgather_rows: null row ranges");
+    for (int k = 0; k < ctx->nranks; ++k)
+        if (row_begin[k] < 0 || row_begin[k] > row_end[k] || row_end[k] > ctx->h)
+            return fail(ctx, SR_ERR_INVALID, "sr_comm_allgather_rows: need 0 <= row_begin <= row_end <= height for every rank");
     CK(cudaSetDevice(ctx->device));
     ViewDev &d = ctx->views[view];
     int r = g_nccl.GroupStart();

@@ -80,10 +80,12 @@ __global__ void prep_view_kernel(const uchar4 *__restrict__ rgba, const uint8_t 
     edges[3 * n + i] = (x >= 1 && y + 1 < h) ? color_dist(c, rgba[i + w - 1]) : dinf();
 }
 
-__global__ void rays_kernel(sr_camera cam, int w, int h, double scale, double *__restrict__ rays) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= w * h) return;
-    const int x = i % w, y = i / w;
+// Rows [y0, y0 + ny) of the [6][h][w] ray table (a rank that owns a row band computes only its rows).
+__global__ void rays_kernel(sr_camera cam, int w, int h, int y0, int ny, double scale, double *__restrict__ rays) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= w * ny) return;
+    const int x = k % w, y = y0 + k / w;
+    const size_t i = (size_t)y * w + x;
     d3 s, d;
     cam_unproject(cam, (x + 0.5) / scale, (y + 0.5) / scale, s, d);
     const size_t n = (size_t)w * h;

@@ -44,8 +44,17 @@ namespace sr {
 #ifndef SR_SCREEN2_ABL
 #define SR_SCREEN2_ABL 0  // 1-4: timing ablations of the label loop (wrong results; profiling only)
 #endif
+#ifndef SR_SCREEN2_PRE
+#define SR_SCREEN2_PRE 0  // 1: two-level sweep (subset bound first, full window for the survivors)
+#endif
+#ifndef SR_SCREEN2_SWP
+#define SR_SCREEN2_SWP 0  // 1: software-pipelined label loop (next label's window loads ride with this label's FFMA2s)
+#endif
+#ifndef SR_SCREEN2_NACC
+#define SR_SCREEN2_NACC 1  // accumulator pairs per window sum (one-pass form)
+#endif
 #ifndef SR_SCREEN2_NL
-#define SR_SCREEN2_NL 1  // labels evaluated together per loop iteration (independent chains: ILP within the warp)
+#define SR_SCREEN2_NL 2  // labels evaluated together per loop iteration (independent chains: ILP within the warp)
 #endif
 #ifndef SR_SCREEN2_ONEPASS
 #define SR_SCREEN2_ONEPASS 1  // 0: A/B against the two-pass (mean first) form of the screen
@@ -70,6 +79,18 @@ struct Screen2Smem {
     float eps_ring[STATS ? TAP_CHUNK : 1][32], q_eps[STATS ? SCREEN_QCAP : 1][32], st_maxerr[STATS ? 32 : 1];
     int st_verified[STATS ? 32 : 1], st_viol[STATS ? 32 : 1];
 };
+
+// Register slot i of the window arrays holds window tap k = screen2_slot_tap<R>(i) (row-major k).  For the
+// 5x5 window the first PRE_TAPS slots are the taps of the pre-screen (the centre 3x3 block and the tap left
+// of it), so that they form whole FFMA2 pairs.
+constexpr int SCREEN2_PRE_TAPS = 10;
+template <int R>
+__host__ __device__ constexpr int screen2_slot_tap(int i) {
+    if (R != 2) return i;
+    constexpr int pre[SCREEN2_PRE_TAPS] = {6, 7, 8, 11, 12, 13, 16, 17, 18, 10};
+    constexpr int rest[15] = {0, 1, 2, 3, 4, 5, 9, 14, 15, 19, 20, 21, 22, 23, 24};
+    return i < SCREEN2_PRE_TAPS ? pre[i] : rest[i - SCREEN2_PRE_TAPS];
+}
 
 __device__ __forceinline__ int32_t lds_b32(unsigned addr) {
     int32_t v;
@@ -264,6 +285,8 @@ struct Screener {
     // one-pass: k0 = 2 totW - n_a, k1 = SDL / sqrt(s2), error bar e0 + e1 * kappa
     // two-pass: k0 = n_inactive, e0 = the pixel's error-bar class
     float inv_totWf, k0, k1, e0, e1, lower32;
+    float pre_sdl_n, pre_inv_n, pre_E;  // pre-screen: sum_A dl / n_A, 1 / n_A, centred energy of dl on A
+    int n_prerej, n_prebad;              // STATS only
     int qn, my_win_w, first_pid;
     unsigned pend;
     bool alive;
@@ -323,10 +346,29 @@ struct Screener {
         const double rs2 = all_slow ? 0.0 : 1.0 / sqrt(s2);  // folded into c1f: ncc32 = s1 * rsqrt(s3)
 #pragma unroll
         for (int i = 0; i < WN; ++i) {
-            wtf[i] = (float)wt[i];
-            c1f[i] = ONEPASS ? (float)((gl[i] * rs2) * wt[i]) : (float)(gl[i] * rs2);
+            const int k = screen2_slot_tap<R>(i);
+            wtf[i] = (float)wt[k];
+            c1f[i] = ONEPASS ? (float)((gl[k] * rs2) * wt[k]) : (float)(gl[k] * rs2);
         }
         const bool has_inactive = ninact != 0;
+        {   // pre-screen subset A = slots [0, SCREEN2_PRE_TAPS): active taps only (dl = 0 on the others)
+            double nA = 0.0, sA = 0.0, qA = 0.0;
+#pragma unroll
+            for (int i = 0; i < (R == 2 ? SCREEN2_PRE_TAPS : 0); ++i) {
+                const int k = screen2_slot_tap<R>(i);
+                if (wt[k] > 0.0) {
+                    const double d = gl[k] * rs2;
+                    nA += 1.0;
+                    sA += d;
+                    qA += d * d;
+                }
+            }
+            const double EA = (nA >= 2.0) ? qA - sA * sA / nA : 0.0;
+            pre_sdl_n = (nA > 0.0) ? (float)(sA / nA) : 0.0f;
+            pre_inv_n = (nA > 0.0) ? (float)(1.0 / nA) : 0.0f;
+            pre_E = (float)(EA * (1.0 - 1e-6));  // (rounded down: a smaller energy only weakens the bound)
+            if (!(pre_E > 0.0f) || all_slow) pre_E = 0.0f;
+        }
         inv_totWf = (float)(1.0 / totW);
         if (ONEPASS) {
             const double na = (double)(WN - ninact);
@@ -362,180 +404,308 @@ struct Screener {
         qn = 0;
         pend = 0u;
         lower32 = (float)a.ncc_threshold - 1e-6f;
-        n_forced = n_screened = 0;
+        n_forced = n_screened = n_prerej = n_prebad = 0;
         if (STATS && alive && all_slow && a.stats) atomicAdd(a.stats + 4, 1ull);
         __syncwarp();
     }
 
-    // ---- FP32 screen of NL interior taps at once ---------------------------------------------------
-    // idx[n]: element index of the window centre in the neighbour's FP32 plane.  The NL windows are
-    // independent chains of one basic block: the scheduler overlaps one label's load latency and
-    // dependent FFMA2 chains with the other's (the loop is latency-bound per warp, not issue-bound).
-    // Outputs per label: ub = ncc32 + eps (SCREEN_FORCE when FP64 has to decide), lb = ncc32 - eps
-    // (SCREEN_SKIP then), eps (statistics).
-    template <int NL>
-    __device__ __forceinline__ void screen_n(const float *__restrict__ gplane, const int (&idx)[NL], float (&ub)[NL], float (&lb)[NL],
-                                             float (&eps_out)[NL]) const {
+    // ---- FP32 screen -----------------------------------------------------------------------------------
+    // The (2R+1)^2 taps around element `idx` of the neighbour's FP32 plane (slots [FIRST, LAST)).
+    template <int FIRST = 0, int LAST = WN>
+    __device__ __forceinline__ void load_window(const float *__restrict__ gplane, int idx, float (&g)[WN]) const {
         const int fp = PITCH ? PITCH : a.pitch_f;
-        constexpr int NP = WN / 2;  // WN is odd: NP pairs + one scalar tap
-        float g[NL][WN];
-#pragma unroll
-        for (int n = 0; n < NL; ++n) {
 #if SR_SCREEN2_ABL == 3  // ablation: warp-aligned (broadcast) loads
-            const float *__restrict__ base = gplane + ((idx[n] & ~31) + 2);
+        const float *__restrict__ base = gplane + ((idx & ~31) + 2);
 #else
-            const float *__restrict__ base = gplane + idx[n];
+        const float *__restrict__ base = gplane + idx;
 #endif
 #if SR_SCREEN2_ABL == 1  // ablation: no window loads
 #pragma unroll
-            for (int i = 0; i < WN; ++i) g[n][i] = __int_as_float(idx[n] + i);
+        for (int i = FIRST; i < LAST; ++i) g[i] = __int_as_float(idx + i);
 #else
 #pragma unroll
-            for (int row = 0; row < WS; ++row)
-#pragma unroll
-                for (int col = 0; col < WS; ++col) g[n][row * WS + col] = base[(row - R) * fp + (col - R)];
-#endif
+        for (int i = FIRST; i < LAST; ++i) {
+            const int k = screen2_slot_tap<R>(i);
+            g[i] = base[(k / WS - R) * fp + (k % WS - R)];
         }
+#endif
+    }
+
+    // One window: ub = ncc32 + eps (SCREEN_FORCE when FP64 has to decide), lb = ncc32 - eps (SCREEN_SKIP
+    // then), eps (statistics).
+    __device__ __forceinline__ void eval_window(const float (&g)[WN], float &ub, float &lb, float &eps_out) const {
+        constexpr int NP = WN / 2;  // WN is odd: NP pairs + one scalar tap
+        float c32, eps;
+        bool ok;
+        if (ONEPASS) {
+            // NACC accumulator pairs per sum; the three sums interleave, so even one pair per sum keeps
+            // dependent FFMA2s three issue slots apart
+            constexpr int NACC = SR_SCREEN2_NACC;
+            float2 S1p[NACC], Qp[NACC], Xp[NACC];
 #pragma unroll
-        for (int n = 0; n < NL; ++n) {
-            float c32, eps;
-            bool ok;
-            if (ONEPASS) {
-                float2 S1p[2] = {make_float2(0.0f, 0.0f), make_float2(0.0f, 0.0f)};
-                float2 Qp[2] = {make_float2(0.0f, 0.0f), make_float2(0.0f, 0.0f)};
-                float2 Xp[2] = {make_float2(0.0f, 0.0f), make_float2(0.0f, 0.0f)};
+            for (int i = 0; i < NACC; ++i) S1p[i] = Qp[i] = Xp[i] = make_float2(0.0f, 0.0f);
+            const float2 zero = make_float2(0.0f, 0.0f);
+#pragma unroll
+            for (int p = 0; p < NP; ++p) {
+                const float2 wv = make_float2(wtf[2 * p], wtf[2 * p + 1]), gv = make_float2(g[2 * p], g[2 * p + 1]);
+                S1p[p % NACC] = fma2(wv, gv, S1p[p % NACC]);
+#if SR_SCREEN2_ABL != 2  // ablation 2: loads + one accumulation only
+                const float2 pv = fma2(wv, gv, zero);
+                Qp[p % NACC] = fma2(pv, pv, Qp[p % NACC]);
+                Xp[p % NACC] = fma2(make_float2(c1f[2 * p], c1f[2 * p + 1]), gv, Xp[p % NACC]);
+#endif
+            }
+            float S1, Q, X;
+            if (NACC == 1) {
+                S1 = S1p[0].x + S1p[0].y;
+                Q = Qp[0].x + Qp[0].y;
+                X = Xp[0].x + Xp[0].y;
+            } else {
+                S1 = (S1p[0].x + S1p[1].x) + (S1p[0].y + S1p[1].y);
+                Q = (Qp[0].x + Qp[1].x) + (Qp[0].y + Qp[1].y);
+                X = (Xp[0].x + Xp[1].x) + (Xp[0].y + Xp[1].y);
+            }
+            {
+                const float pl = wtf[WN - 1] * g[WN - 1];
+                S1 += pl;
+                Q = fmaf(pl, pl, Q);
+                X = fmaf(c1f[WN - 1], g[WN - 1], X);
+            }
+            const float mR = S1 * inv_totWf;
+            const float s3 = fmaf(-k0, mR * mR, Q);
+            const float s1 = fmaf(-mR, k1, X);
+            float rs;
+            asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(rs) : "f"(s3));
+            c32 = s1 * rs;
+            eps = fmaf(Q * (rs * rs), e1, e0);  // e0 + e1 * kappa
+            // ill-conditioned or non-finite neighbour window, or a bar too wide to be first order: FP64 decides
+            ok = (s3 >= (float)WN) && (eps <= SCREEN_EPS_MAX);
+        } else {
+            float2 S1p[2] = {make_float2(0.0f, 0.0f), make_float2(0.0f, 0.0f)};
+#pragma unroll
+            for (int p = 0; p < NP; ++p)
+                S1p[p & 1] = fma2(make_float2(wtf[2 * p], wtf[2 * p + 1]), make_float2(g[2 * p], g[2 * p + 1]), S1p[p & 1]);
+            float S1 = (S1p[0].x + S1p[1].x) + (S1p[0].y + S1p[1].y);
+            S1 = fmaf(wtf[WN - 1], g[WN - 1], S1);
+            const float mR = S1 * inv_totWf;
+            const float2 nm = make_float2(-mR, -mR);
+            float2 s3p[2] = {make_float2(0.0f, 0.0f), make_float2(0.0f, 0.0f)};
+            float2 s1p[2] = {make_float2(0.0f, 0.0f), make_float2(0.0f, 0.0f)};
+#pragma unroll
+            for (int p = 0; p < NP; ++p) {
+                const float2 t = fma2(make_float2(wtf[2 * p], wtf[2 * p + 1]), make_float2(g[2 * p], g[2 * p + 1]), nm);
+                s3p[p & 1] = fma2(t, t, s3p[p & 1]);
+                s1p[p & 1] = fma2(make_float2(c1f[2 * p], c1f[2 * p + 1]), t, s1p[p & 1]);
+            }
+            float s3a = (s3p[0].x + s3p[1].x) + (s3p[0].y + s3p[1].y);
+            float s1 = (s1p[0].x + s1p[1].x) + (s1p[0].y + s1p[1].y);
+            {
+                const float t = fmaf(wtf[WN - 1], g[WN - 1], -mR);
+                s3a = fmaf(t, t, s3a);
+                s1 = fmaf(c1f[WN - 1], t, s1);
+            }
+            // inactive taps (w = dl = 0) contributed (-mR)^2 each to s3a and nothing to s1; the label is
+            // FORCEd when that correction exceeds SCREEN_CORR_MAX * s3 (relative error of s3 <= 15u * 101,
+            // inside SCREEN_EPS_LOOSE, which such pixels always use)
+            const float s3 = fmaf(-k0, mR * mR, s3a);
+            eps = (s3 >= 100.0f * WN) ? e0 : SCREEN_EPS_LOOSE;
+            float rs;
+            asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(rs) : "f"(s3));
+            c32 = s1 * rs;
+            ok = (s3 >= (float)WN) && (s3 < 1e30f) && (s3a <= (SCREEN_CORR_MAX + 1.0f) * s3);
+        }
+        eps_out = eps;
+#if SR_SCREEN2_ABL  // ablations: the arithmetic stays alive, no label ever becomes a candidate
+        lb = SCREEN_SKIP;
+        ub = (ok && c32 > 1e30f) ? c32 + eps : SCREEN_SKIP;
+#else
+        lb = ok ? c32 - eps : SCREEN_SKIP;
+        ub = ok ? c32 + eps : SCREEN_FORCE;
+#endif
+    }
+
+    // NL windows at once: independent chains of one basic block.
+    template <int NL>
+    __device__ __forceinline__ void screen_n(const float *__restrict__ gplane, const int (&idx)[NL], float (&ub)[NL], float (&lb)[NL],
+                                             float (&eps_out)[NL]) const {
+        float g[NL][WN];
+#pragma unroll
+        for (int n = 0; n < NL; ++n) load_window(gplane, idx[n], g[n]);
+#pragma unroll
+        for (int n = 0; n < NL; ++n) eval_window(g[n], ub[n], lb[n], eps_out[n]);
+    }
+
+    // A ring entry -> is its window interior to the neighbour image (then idx = its element index, else a
+    // safe interior element).  MVS taps lie inside the image; TAP_NONE decodes to ty = 32768 (never interior).
+    __device__ __forceinline__ bool decode_tap(int32_t tap, int &idx) const {
+        const int fp = PITCH ? PITCH : a.pitch_f;
+        const int tx = tap & 0xffff, ty = (int)((uint32_t)tap >> 16);
+        const bool interior = (unsigned)(tx - R) < (unsigned)my_win_w && (unsigned)(ty - R) < (unsigned)a.win_h;
+        idx = interior ? ty * fp + tx : R * fp + R;
+        return interior;
+    }
+    // What a label's screen result does to the lane's state (ca: its slot of the upper-bound ring).
+    __device__ __forceinline__ void commit_label(bool interior, int32_t tap, float ub, float lb, float eps, unsigned ca, unsigned bit, int l) {
+        if (interior) {
+            sts_f32(ca, ub);
+            lower32 = fmaxf(lower32, lb);
+            pend |= (ub >= lower32) ? bit : 0u;
+            if (STATS) {
+                sm.eps_ring[l][lane] = eps;
+                if (ub == SCREEN_FORCE) ++n_forced;
+                else ++n_screened;
+            }
+        } else if (tap != TAP_NONE && alive) {  // window on the neighbour's border / FP64-only pixel
+            sts_f32(ca, SCREEN_FORCE);
+            pend |= bit;
+            if (STATS) ++n_forced;
+        }
+    }
+
+    // Software-pipelined sweep of a chunk: while label l is evaluated from one register set, the window of
+    // label l + 1 is loaded into the other.  The loads of a label no longer sit in front of its own
+    // arithmetic (a load phase on the LSU followed by an FMA phase, which the warps of a scheduler run in
+    // step with each other), they ride along with the previous label's FFMA2s.
+    __device__ __forceinline__ void chunk_pipelined(const float *__restrict__ gplane, unsigned ra, unsigned ca, int nl) {
+        float gA[WN], gB[WN];
+        int idxA, idxB;
+        int32_t tapA = lds_b32(ra), tapB;
+        bool inA = decode_tap(tapA, idxA), inB;
+        load_window(gplane, idxA, gA);
+        unsigned bit = 1u;
+#pragma unroll 1
+        for (int l = 0; l < nl; l += 2, ra += 256u, ca += 256u, bit <<= 2) {
+            float ub, lb, eps;
+            tapB = (l + 1 < nl) ? lds_b32(ra + 128u) : TAP_NONE;
+            inB = decode_tap(tapB, idxB);
+            load_window(gplane, idxB, gB);
+            eval_window(gA, ub, lb, eps);
+            commit_label(inA, tapA, ub, lb, eps, ca, bit, l);
+            tapA = (l + 2 < nl) ? lds_b32(ra + 256u) : TAP_NONE;
+            inA = decode_tap(tapA, idxA);
+            load_window(gplane, idxA, gA);
+            eval_window(gB, ub, lb, eps);
+            commit_label(inB, tapB, ub, lb, eps, ca + 128u, bit << 1, l + 1);
+        }
+    }
+
+    // Two-level sweep of a chunk (5x5 windows).
+    //
+    // Level 1 looks at the SCREEN2_PRE_TAPS taps of subset A only and proves most labels hopeless.  With
+    // dl the (unit-norm) reference deviations and t = p - meanR the neighbour's, over the active taps:
+    //     ncc = (<dl_A, t_A> + <dl_B, t_B>) / sqrt(|t_A|^2 + |t_B|^2)      (B = the taps not looked at)
+    // Maximising over the unknown t_B and over the unknown mean meanR (t_A = p_A - meanR 1_A ranges over a
+    // line in the plane spanned by p_A and 1_A) leaves
+    //     ncc^2 <= 1 - dist^2(dl_A, span{p_A, 1_A}) = 1 - E_A (1 - rho_A^2),
+    // E_A = the energy of dl_A about its own mean (a per-pixel constant), rho_A = the plain correlation of
+    // dl_A and p_A.  A label cannot reach the current lower bound L of the winning cost, and is dropped, if
+    //     rho_A^2 < 1 - (1 - L^2) / E_A     <=>     num^2 < (E_A - (1 - L^2)) * den,
+    // num = sum_A dl p - (sum_A dl)(sum_A p) / n_A,  den = sum_A p^2 - (sum_A p)^2 / n_A.  The FP32 sums carry
+    // |dnum| <= 32u sqrt(q), |dden| <= 32u q (q = sum_A p^2; 10 terms, <= 6 roundings each plus the inputs'):
+    // the test is made with (1 + 1/64) num^2 + 65 (32u)^2 q >= (|num| + |dnum|)^2 on the left and
+    // den - 2e-6 q <= den - |dden| on the right.  SR_MATCH_STATS=1 evaluates every dropped label in full as
+    // well and counts the ones that would have been candidates (must be 0).
+    //
+    // Level 2: the labels that survive (a 16-bit mask per lane) are evaluated in full, each lane taking
+    // ITS next surviving label per round, so the number of full evaluations a warp runs per chunk is the
+    // largest survivor count of a lane, not the number of labels with a survivor somewhere in the warp.
+    __device__ __forceinline__ void chunk_prescreened(const float *__restrict__ gplane, const unsigned ra0, const unsigned ca0, int nl) {
+        constexpr int PRE = SCREEN2_PRE_TAPS;
+        const float KB = pre_E - (1.0f - lower32 * lower32) * 1.000001f;  // (lower32 only rises: a stale value is conservative)
+        unsigned pass = 0u, bit = 1u;
+        unsigned ra = ra0, ca = ca0;
+#pragma unroll 1
+        for (int l = 0; l < nl; ++l, ra += 128u, ca += 128u, bit <<= 1) {
+            const int32_t tap = lds_b32(ra);
+            int idx;
+            if (decode_tap(tap, idx)) {
+                float g[WN];
+                load_window<0, PRE>(gplane, idx, g);
+                float2 Ap = make_float2(0.0f, 0.0f), Qp = make_float2(0.0f, 0.0f), Xp = make_float2(0.0f, 0.0f);
                 const float2 zero = make_float2(0.0f, 0.0f);
 #pragma unroll
-                for (int p = 0; p < NP; ++p) {
-                    const float2 wv = make_float2(wtf[2 * p], wtf[2 * p + 1]), gv = make_float2(g[n][2 * p], g[n][2 * p + 1]);
-                    S1p[p & 1] = fma2(wv, gv, S1p[p & 1]);
-#if SR_SCREEN2_ABL != 2  // ablation 2: loads + one accumulation only
+                for (int p = 0; p < PRE / 2; ++p) {
+                    const float2 wv = make_float2(wtf[2 * p], wtf[2 * p + 1]), gv = make_float2(g[2 * p], g[2 * p + 1]);
                     const float2 pv = fma2(wv, gv, zero);
-                    Qp[p & 1] = fma2(pv, pv, Qp[p & 1]);
-                    Xp[p & 1] = fma2(make_float2(c1f[2 * p], c1f[2 * p + 1]), gv, Xp[p & 1]);
-#endif
+                    Ap = fma2(wv, gv, Ap);
+                    Qp = fma2(pv, pv, Qp);
+                    Xp = fma2(make_float2(c1f[2 * p], c1f[2 * p + 1]), gv, Xp);
                 }
-                float S1 = (S1p[0].x + S1p[1].x) + (S1p[0].y + S1p[1].y);
-                float Q = (Qp[0].x + Qp[1].x) + (Qp[0].y + Qp[1].y);
-                float X = (Xp[0].x + Xp[1].x) + (Xp[0].y + Xp[1].y);
-                {
-                    const float pl = wtf[WN - 1] * g[n][WN - 1];
-                    S1 += pl;
-                    Q = fmaf(pl, pl, Q);
-                    X = fmaf(c1f[WN - 1], g[n][WN - 1], X);
+                const float av = Ap.x + Ap.y, q = Qp.x + Qp.y, x = Xp.x + Xp.y;
+                const float num = fmaf(-pre_sdl_n, av, x);
+                const float den = fmaf(-av * pre_inv_n, av, q);
+                const float lhs = fmaf(num * num, 1.0157f, 2.4e-10f * q);
+                const float rhs = KB * fmaf(-2e-6f, q, den);
+                const bool reject = (KB > 0.0f) && (lhs < rhs);
+                if (!reject) pass |= bit;
+                if (STATS && reject) {  // self-check: the full evaluation of a dropped label
+                    ++n_prerej;
+                    float ub, lb, eps;
+                    load_window<PRE, WN>(gplane, idx, g);
+                    eval_window(g, ub, lb, eps);
+                    if (ub >= lower32) ++n_prebad;
                 }
-                const float mR = S1 * inv_totWf;
-                const float s3 = fmaf(-k0, mR * mR, Q);
-                const float s1 = fmaf(-mR, k1, X);
-                float rs;
-                asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(rs) : "f"(s3));
-                c32 = s1 * rs;
-                eps = fmaf(Q * (rs * rs), e1, e0);  // e0 + e1 * kappa
-                // ill-conditioned or non-finite neighbour window, or a bar too wide to be first order: FP64 decides
-                ok = (s3 >= (float)WN) && (eps <= SCREEN_EPS_MAX);
-            } else {
-                float2 S1p[2] = {make_float2(0.0f, 0.0f), make_float2(0.0f, 0.0f)};
-#pragma unroll
-                for (int p = 0; p < NP; ++p)
-                    S1p[p & 1] = fma2(make_float2(wtf[2 * p], wtf[2 * p + 1]), make_float2(g[n][2 * p], g[n][2 * p + 1]), S1p[p & 1]);
-                float S1 = (S1p[0].x + S1p[1].x) + (S1p[0].y + S1p[1].y);
-                S1 = fmaf(wtf[WN - 1], g[n][WN - 1], S1);
-                const float mR = S1 * inv_totWf;
-                const float2 nm = make_float2(-mR, -mR);
-                float2 s3p[2] = {make_float2(0.0f, 0.0f), make_float2(0.0f, 0.0f)};
-                float2 s1p[2] = {make_float2(0.0f, 0.0f), make_float2(0.0f, 0.0f)};
-#pragma unroll
-                for (int p = 0; p < NP; ++p) {
-                    const float2 t = fma2(make_float2(wtf[2 * p], wtf[2 * p + 1]), make_float2(g[n][2 * p], g[n][2 * p + 1]), nm);
-                    s3p[p & 1] = fma2(t, t, s3p[p & 1]);
-                    s1p[p & 1] = fma2(make_float2(c1f[2 * p], c1f[2 * p + 1]), t, s1p[p & 1]);
-                }
-                float s3a = (s3p[0].x + s3p[1].x) + (s3p[0].y + s3p[1].y);
-                float s1 = (s1p[0].x + s1p[1].x) + (s1p[0].y + s1p[1].y);
-                {
-                    const float t = fmaf(wtf[WN - 1], g[n][WN - 1], -mR);
-                    s3a = fmaf(t, t, s3a);
-                    s1 = fmaf(c1f[WN - 1], t, s1);
-                }
-                // inactive taps (w = dl = 0) contributed (-mR)^2 each to s3a and nothing to s1; the label is
-                // FORCEd when that correction exceeds SCREEN_CORR_MAX * s3 (relative error of s3 <= 15u * 101,
-                // inside SCREEN_EPS_LOOSE, which such pixels always use)
-                const float s3 = fmaf(-k0, mR * mR, s3a);
-                eps = (s3 >= 100.0f * WN) ? e0 : SCREEN_EPS_LOOSE;
-                float rs;
-                asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(rs) : "f"(s3));
-                c32 = s1 * rs;
-                ok = (s3 >= (float)WN) && (s3 < 1e30f) && (s3a <= (SCREEN_CORR_MAX + 1.0f) * s3);
+            } else if (tap != TAP_NONE && alive) {  // window on the neighbour's border / FP64-only pixel
+                sts_f32(ca, SCREEN_FORCE);
+                pend |= bit;
+                if (STATS) ++n_forced;
             }
-            eps_out[n] = eps;
-#if SR_SCREEN2_ABL  // ablations: the arithmetic stays alive, no label ever becomes a candidate
-            lb[n] = SCREEN_SKIP;
-            ub[n] = (ok && c32 > 1e30f) ? c32 + eps : SCREEN_SKIP;
-#else
-            lb[n] = ok ? c32 - eps : SCREEN_SKIP;
-            ub[n] = ok ? c32 + eps : SCREEN_FORCE;
-#endif
+        }
+#pragma unroll 1
+        while (__any_sync(FULL, pass != 0u)) {
+            const bool has = pass != 0u;
+            const int l = has ? __ffs(pass) - 1 : 0;
+            pass &= pass - 1u;
+            const int32_t tap = lds_b32(ra0 + 128u * l);
+            int idx;
+            const bool interior = decode_tap(tap, idx) && has;
+            float g[WN], ub, lb, eps;
+            load_window(gplane, interior ? idx : R * (PITCH ? PITCH : a.pitch_f) + R, g);
+            eval_window(g, ub, lb, eps);
+            if (interior) commit_label(true, tap, ub, lb, eps, ca0 + 128u * l, 1u << l, l);
         }
     }
 
     // NL consecutive labels of a chunk: ring entries at shared addresses ra, ra + 128, ...; `bit` = mask bit
-    // of the first.  Labels whose window is not interior to the neighbour image are FORCEd (or skipped when
-    // the tap is TAP_NONE); a lane with at least one interior label evaluates all NL (the others at a safe
-    // address, result discarded).
+    // of the first.  A lane with at least one interior label evaluates all NL (the others at a safe address,
+    // result discarded).
     template <int NL>
     __device__ __forceinline__ void labels(const float *__restrict__ gplane, unsigned ra, unsigned ca, unsigned bit, int l) {
-        const int fp = PITCH ? PITCH : a.pitch_f;
-        const unsigned win_h = (unsigned)a.win_h;
         int32_t tap[NL];
         int idx[NL];
         bool interior[NL], any = false;
 #pragma unroll
         for (int n = 0; n < NL; ++n) {
             tap[n] = lds_b32(ra + 128u * n);
-            const int tx = tap[n] & 0xffff, ty = (int)((uint32_t)tap[n] >> 16);  // MVS taps lie inside the image; TAP_NONE -> ty = 32768
-            interior[n] = (unsigned)(tx - R) < (unsigned)my_win_w && (unsigned)(ty - R) < win_h;
-            idx[n] = interior[n] ? ty * fp + tx : R * fp + R;
+            interior[n] = decode_tap(tap[n], idx[n]);
             any = any || interior[n];
         }
-        if (any) {
-            float ub[NL], lb[NL], eps[NL];
-            screen_n<NL>(gplane, idx, ub, lb, eps);
+        float ub[NL], lb[NL], eps[NL];
 #pragma unroll
-            for (int n = 0; n < NL; ++n) {
-                if (NL == 1 || interior[n]) {
-                    sts_f32(ca + 128u * n, ub[n]);
-                    lower32 = fmaxf(lower32, lb[n]);
-                    pend |= (ub[n] >= lower32) ? (bit << n) : 0u;
-                    if (STATS) {
-                        sm.eps_ring[l + n][lane] = eps[n];
-                        if (ub[n] == SCREEN_FORCE) ++n_forced;
-                        else ++n_screened;
-                    }
-                }
-            }
-        }
+        for (int n = 0; n < NL; ++n) ub[n] = lb[n] = eps[n] = 0.0f;
+        if (any) screen_n<NL>(gplane, idx, ub, lb, eps);
 #pragma unroll
-        for (int n = 0; n < NL; ++n) {
-            if (!interior[n] && tap[n] != TAP_NONE && alive) {  // window on the neighbour's border / FP64-only pixel
-                sts_f32(ca + 128u * n, SCREEN_FORCE);
-                pend |= bit << n;
-                if (STATS) ++n_forced;
-            }
-        }
+        for (int n = 0; n < NL; ++n) commit_label(interior[n], tap[n], ub[n], lb[n], eps[n], ca + 128u * n, bit << n, l + n);
     }
 
     // ---- one chunk of labels of neighbour j: taps in sm.tap_ring[buf][0..nl) -----------------------
     __device__ __forceinline__ void chunk(int j, int d0, int nl, int buf, const float *__restrict__ gplane) {
         unsigned ra = (unsigned)__cvta_generic_to_shared(&sm.tap_ring[buf][0][lane]);
         unsigned ca = (unsigned)__cvta_generic_to_shared(&sm.ub_ring[0][lane]);
-        unsigned bit = 1u;
-        constexpr int NL = SR_SCREEN2_NL;
-        int l = 0;
+        if (SR_SCREEN2_PRE && ONEPASS && R == 2) {
+            chunk_prescreened(gplane, ra, ca, nl);
+        } else if (SR_SCREEN2_SWP && ONEPASS) {
+            chunk_pipelined(gplane, ra, ca, nl);
+        } else {
+            unsigned bit = 1u;
+            constexpr int NL = SR_SCREEN2_NL;
+            int l = 0;
 #pragma unroll 1
-        for (; l + NL <= nl; l += NL, ra += 128u * NL, ca += 128u * NL, bit <<= NL) labels<NL>(gplane, ra, ca, bit, l);
-        if (NL > 1) {
+            for (; l + NL <= nl; l += NL, ra += 128u * NL, ca += 128u * NL, bit <<= NL) labels<NL>(gplane, ra, ca, bit, l);
+            if (NL > 1) {
 #pragma unroll 1
-            for (; l < nl; ++l, ra += 128u, ca += 128u, bit <<= 1) labels<1>(gplane, ra, ca, bit, l);
+                for (; l < nl; ++l, ra += 128u, ca += 128u, bit <<= 1) labels<1>(gplane, ra, ca, bit, l);
+            }
         }
         if (__any_sync(FULL, pend != 0u)) {
             const Screen2Cold r = screen2_process_pending<R, STATS>(a, sm, lane, first_pid, j, d0, buf, qn, pend, lower32);
@@ -552,6 +722,7 @@ struct Screener {
             atomicAdd(a.stats + 0, 1ull);
             atomicAdd(a.stats + 1, (unsigned long long)n_screened);
             atomicAdd(a.stats + 2, (unsigned long long)n_forced);
+            atomicAdd(a.stats + 7, (unsigned long long)n_prebad);  // labels the subset bound dropped although they were candidates
         }
         if (STATS && a.stats) {  // verifications are counted by the lane that ran them
             atomicAdd(a.stats + 3, (unsigned long long)sm.st_verified[lane]);

@@ -124,6 +124,7 @@ int main(int argc, char **argv) {
         mvs.onProgressUpdate = [&](int v) { lastProgress = v; };
         mvs.onStageUpdate = [&](const std::string &s) { lastStage = s; };
         mvs.initialize(project, set, views, minDepth, maxDepth, levels, crossCheck, 1.0);
+        mvs.setCurveMode(false);  // first the depth-label volume (the class default is the reference's curve search)
         std::printf("mvs: %zu views loaded, numSteps=%d, title=%s\n", mvs.numViews(), mvs.numSteps(), mvs.title().c_str());
         mvs.run();
         std::vector<sr_camera> pods;
@@ -166,6 +167,7 @@ int main(int argc, char **argv) {
             TwoViewStereo two(views[0], l, QImage(), views[1], r, QImage(), minDepth, maxDepth, levels, 1.0);
             two.params().radius = 2;               // keep the harness quick; the reference constant is 5
             two.setCrossCheckThreshold(30.0);
+            two.setCurveMode(false);  // the label volume (compared with the oracle's label mode)
             two.run();
             dump(out + "/two_left_depth.bin", two.leftDepths().data(), two.leftDepths().size());
             dump(out + "/two_right_depth.bin", two.rightDepths().data(), two.rightDepths().size());
