@@ -391,6 +391,7 @@ def main():
         for _ in range(steps):
             for v in views:
                 ctx.run_view(v, nbrs[v])
+        ctx.flush()  # the views run on the library's internal lanes: order them before the event
         ev1.record(stream)
         barrier()
         return max_over_ranks(ev0.elapsed_time(ev1)) / steps, t_begin, time.time()
@@ -442,15 +443,19 @@ def main():
             ctx.run_view(v, nbrs[v])
     barrier()
     launches0 = ctx.launch_count()
-    ctx.set_profiling(True)
     ms_per_step, t_begin, t_end = timed_steps(my_views, args.steps, 0)
     clocks = sampler.finish(t_begin, t_end)
+    launches = ctx.launch_count() - launches0
+    # per-stage device times: one more step with the library's per-stage events on (which serialises the
+    # views on the context stream: a kernel's duration is then its own, not stretched by the overlap)
+    ctx.set_profiling(True)
+    for v in my_views:
+        ctx.run_view(v, nbrs[v])
     stages = ctx.stage_ms()
     if os.environ.get("SR_MATCH_STATS"):
         print("match stats:", ctx.match_stats(), file=sys.stderr)
         print("build stats:", ctx.build_stats(), file=sys.stderr)
     ctx.set_profiling(False)
-    launches = ctx.launch_count() - launches0
     value = units_total / (ms_per_step * 1e-3) / 1e6
     parity_n = None if args.no_extras else parity_vs_solo(args.partition, my_views, my_band)
     set_rows(*my_band)
@@ -499,6 +504,7 @@ def main():
             set_rows(*my_band)
             for v in my_views:
                 ctx.run_view(v, nbrs[v])
+            ctx.synchronize()  # (only to attribute the gather and the cross-check their own times)
             g0 = time.perf_counter()
             if world > 1:
                 if args.partition == "rows":
@@ -642,6 +648,7 @@ def main():
             # GPU curve mode (the reference's live formulation) on the sample view: throughput and parity
             ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             ctx.run_view_curve(v0, nbrs[v0])
+            ctx.flush()
             ev0.record(stream)
             ctx.run_view_curve(v0, nbrs[v0])
             ev1.record(stream)

@@ -174,6 +174,14 @@ int sr_select_neighbours(sr_ctx *ctx, int max_nbrs, int32_t *out_nbrs, int32_t *
  * failing pixels -> +INF) or stereo/multiviewstereo.cpp:666-729 (any other view may
  * confirm; failing pixels -> NaN).  Operates on the device-resident depth maps. */
 int sr_cross_check(sr_ctx *ctx, int two_view, double threshold);
+/* Consecutive sr_run_view calls alternate between two internal streams (so that one view's last,
+ * partially filled wave of blocks overlaps the next view's launches; SR_LANES=1 turns this off).
+ * Every other entry point first orders that work before the context stream; a caller that times
+ * or synchronises with ITS OWN events on the stream of sr_set_stream calls sr_flush() first: it makes
+ * the context stream wait for all views enqueued so far, without blocking the host.  sr_synchronize
+ * blocks the host until everything is done.  (Replaces the tbb::parallel_for join of
+ * stereo/multiviewstereo.cpp:548-556.) */
+int sr_flush(sr_ctx *ctx);
 int sr_synchronize(sr_ctx *ctx);
 
 /* ---- results (device -> host) ----------------------------------------------*/

@@ -24,7 +24,7 @@ HEADERS = ["csrc/sr_geometry.cuh", "csrc/sr_kernels.cuh", "csrc/sr_match_dispatc
 EXPORTS = [
     "sr_ctx_create", "sr_ctx_destroy", "sr_last_error", "sr_request_cancel", "sr_clear_cancel",
     "sr_set_stream", "sr_params_default", "sr_launch_count", "sr_set_profiling", "sr_get_stage_ms", "sr_get_match_stats", "sr_get_build_stats", "sr_set_views", "sr_set_params",
-    "sr_run_view", "sr_run_view_curve", "sr_select_neighbours", "sr_cross_check", "sr_synchronize",
+    "sr_run_view", "sr_run_view_curve", "sr_select_neighbours", "sr_cross_check", "sr_flush", "sr_synchronize",
     "sr_get_depth_index", "sr_get_depth", "sr_get_best_cost", "sr_get_cost_volume", "sr_get_peaks", "sr_set_depth",
     "sr_get_depth_image", "sr_unproject_grid", "sr_project_points", "sr_compute_weights", "sr_calibration_residuals",
     "sr_calibration_residuals_batch",
@@ -188,6 +188,10 @@ class Context:
 
     def cross_check(self, two_view, threshold):
         self._ck(self._L.sr_cross_check(self._h, int(two_view), C.c_double(threshold)))
+
+    def flush(self):
+        """Orders every view enqueued so far before the context stream (no host synchronisation)."""
+        self._ck(self._L.sr_flush(self._h))
 
     def synchronize(self):
         self._ck(self._L.sr_synchronize(self._h))

@@ -124,6 +124,25 @@ struct sr_ctx {
     bool use_refr_build = true;  // SR_BUILD_REFR=0: refractive views through the generic build_kernel (A/B aid)
     int refr_chunk = 256;        // labels per thread of build_refr_kernel (SR_BUILD_CHUNK)
     bool use_screen = true;  // SR_MATCH_SCREEN=0: MVS selection through the all-FP64 match_kernel (A/B aid)
+    // "Lanes" (stream + private scratch; two by default) that consecutive sr_run_view calls alternate between: the
+    // ramp-down of one view's kernels (the last, partially filled wave of 0.5 ms blocks) overlaps the
+    // next view's launches.  Everything else runs on `stream`, after join_lanes().  SR_LANES=1 turns it off.
+    struct Lane {
+        cudaStream_t stream = nullptr;
+        cudaEvent_t done = nullptr;
+        bool pending = false;
+        double *d_rays = nullptr;
+        size_t rays_cap = 0;
+        int32_t *d_taps = nullptr;
+        size_t taps_cap = 0;
+        double *d_weights = nullptr;
+        size_t weights_cap = 0;
+    };
+    static constexpr int MAX_LANES = 4;
+    Lane lanes[MAX_LANES];
+    int num_lanes = 2, next_lane = 0;
+    cudaEvent_t ev_fork = nullptr;
+    std::vector<int> view_lane;  // lane that last ran each reference view (-1: none pending)
     bool use_pipeline = false;  // SR_PIPELINE=1: build and screen as roles of ONE launch (sr_pipeline.cuh; measured slower: DESIGN.md)
     int pipe_lag = 128;        // tiles between a tile's build and its screen (SR_PIPE_LAG)
     size_t pipe_ring_bytes = (size_t)1 << 30;  // tap ring of the pipeline kernel (SR_PIPE_RING_MB)
@@ -235,6 +254,22 @@ void refr_pixel_map(const sr_camera &nb, bool mvs, double sc, double *Kn, double
     }
 }
 
+// Make the context stream wait for the lanes' pending views (no host synchronisation).
+int join_lanes(sr_ctx *ctx) {
+    for (sr_ctx::Lane &L : ctx->lanes)
+        if (L.pending) {
+            CK(cudaStreamWaitEvent(ctx->stream, L.done, 0));
+            L.pending = false;
+        }
+    std::fill(ctx->view_lane.begin(), ctx->view_lane.end(), -1);
+    return SR_OK;
+}
+#define JOIN()                          \
+    do {                                \
+        int rcj_ = join_lanes(ctx);     \
+        if (rcj_) return rcj_;          \
+    } while (0)
+
 int check_view(sr_ctx *ctx, int v) {
     if (!ctx) return SR_ERR_INVALID;
     if (ctx->V == 0) return fail(ctx, SR_ERR_STATE, "sr_set_views has not been called");
@@ -275,6 +310,14 @@ int sr_ctx_create(int device, sr_ctx **out) {
     if (const char *sc = getenv("SR_MATCH_SCREEN")) c->use_screen = atoi(sc) != 0;
     if (const char *sb = getenv("SR_BUILD_REFR")) c->use_refr_build = atoi(sb) != 0;
     if (const char *sp = getenv("SR_PIPELINE")) c->use_pipeline = atoi(sp) != 0;
+    if (const char *sn = getenv("SR_LANES")) c->num_lanes = std::min((int)sr_ctx::MAX_LANES, std::max(1, atoi(sn)));
+    if (c->num_lanes > 1) {
+        bool ok = cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming) == cudaSuccess;
+        for (int i = 0; i < c->num_lanes && ok; ++i)
+            ok = cudaStreamCreateWithFlags(&c->lanes[i].stream, cudaStreamNonBlocking) == cudaSuccess &&
+                 cudaEventCreateWithFlags(&c->lanes[i].done, cudaEventDisableTiming) == cudaSuccess;
+        if (!ok) c->num_lanes = 1;
+    }
     if (const char *sl = getenv("SR_PIPE_LAG")) c->pipe_lag = std::max(1, atoi(sl));
     if (const char *sr_ = getenv("SR_PIPE_RING_MB")) c->pipe_ring_bytes = (size_t)std::max(1, atoi(sr_)) << 20;
     if (const char *sk = getenv("SR_BUILD_CHUNK")) c->refr_chunk = std::max(4, atoi(sk));
@@ -289,6 +332,8 @@ int sr_ctx_create(int device, sr_ctx **out) {
 void sr_ctx_destroy(sr_ctx *c) {
     if (!c) return;
     cudaSetDevice(c->device);
+    for (sr_ctx::Lane &L : c->lanes)
+        if (L.stream) cudaStreamSynchronize(L.stream);
     cudaStreamSynchronize(c->stream);
     if (c->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
     free_views(c);
@@ -300,6 +345,15 @@ void sr_ctx_destroy(sr_ctx *c) {
     dfree(c->d_stats);
     dfree(c->d_ring);
     dfree(c->d_pipe_flags);
+    for (sr_ctx::Lane &L : c->lanes) {
+        if (L.stream) cudaStreamSynchronize(L.stream);
+        dfree(L.d_rays);
+        dfree(L.d_taps);
+        dfree(L.d_weights);
+        if (L.done) cudaEventDestroy(L.done);
+        if (L.stream) cudaStreamDestroy(L.stream);
+    }
+    if (c->ev_fork) cudaEventDestroy(c->ev_fork);
     if (c->d_scratch) cudaFree(c->d_scratch);
     cudaStreamDestroy(c->own_stream);
     delete c;
@@ -314,6 +368,10 @@ void sr_clear_cancel(sr_ctx *c) {
 }
 int sr_set_stream(sr_ctx *c, void *s) {
     if (!c) return SR_ERR_INVALID;
+    {
+        sr_ctx *ctx = c;
+        JOIN();  // views still running on the lanes are ordered before whatever follows on the old stream
+    }
     c->stream = s ? (cudaStream_t)s : c->own_stream;
     return SR_OK;
 }
@@ -347,6 +405,7 @@ int sr_set_views(sr_ctx *ctx, int V, const sr_camera *cams, const uint8_t *const
     if (V <= 0 || !cams || !rgba8 || w <= 0 || h <= 0 || w > 16384 || h > 16384)
         return fail(ctx, SR_ERR_INVALID, "sr_set_views: bad arguments (1 <= w,h <= 16384)");
     CK(cudaSetDevice(ctx->device));
+    JOIN();
     const size_t n = (size_t)w * h;
     if (V != ctx->V || w != ctx->w || h != ctx->h) {
         CK(cudaStreamSynchronize(ctx->stream));
@@ -427,6 +486,7 @@ int sr_set_params(sr_ctx *ctx, const sr_params *p) {
     ctx->depth_table.resize(p->num_levels);
     for (int d = 0; d < p->num_levels; ++d) ctx->depth_table[d] = depth_from_label(*p, d);
     CK(cudaSetDevice(ctx->device));
+    JOIN();
     if (p->num_levels > ctx->depth_table_cap) {
         CK(cudaStreamSynchronize(ctx->stream));
         dfree(ctx->d_depth_table);
@@ -602,7 +662,6 @@ int sr_run_view(sr_ctx *ctx, int ref, const int32_t *nbrs, int nn) {
     if (P.select_kind == SR_SELECT_TWOVIEW && nn != 1)
         return fail(ctx, SR_ERR_INVALID, "two-view selection takes exactly one neighbour");
     CK(cudaSetDevice(ctx->device));
-    cudaStream_t st = ctx->stream;
     const int w = ctx->w, h = ctx->h, D = P.num_levels;
     const int r0 = std::max(P.row_begin, 0);
     const int r1 = (P.row_end > 0 && P.row_end < h) ? P.row_end : h;
@@ -610,15 +669,51 @@ int sr_run_view(sr_ctx *ctx, int ref, const int32_t *nbrs, int nn) {
     const size_t n = (size_t)w * h;
     ViewDev &A = ctx->views[ref];
 
-    rays_kernel<<<(unsigned)(((size_t)(r1 - r0) * w + 127) / 128), 128, 0, st>>>(ctx->cams[ref], w, h, r0, r1 - r0, P.image_scale, ctx->d_rays);
-    CKL();
-
     {   // MultiViewStereo label path with refractive neighbours: build and screen as one launch
         bool pipe = ctx->use_pipeline && ctx->use_screen && ctx->use_refr_build && P.select_kind == SR_SELECT_MVS &&
                     P.cost_kind == SR_COST_NCC_MVS && !P.keep_cost_volume && pipeline_supported(P.radius);
         for (int j = 0; j < nn; ++j) pipe = pipe && ctx->cams[nbrs[j]].is_refractive;
-        if (pipe) return run_view_pipeline(ctx, ref, nbrs, nn, r0, r1);
+        if (pipe) {
+            JOIN();
+            rays_kernel<<<(unsigned)(((size_t)(r1 - r0) * w + 127) / 128), 128, 0, ctx->stream>>>(ctx->cams[ref], w, h, r0, r1 - r0,
+                                                                                                   P.image_scale, ctx->d_rays);
+            CKL();
+            return run_view_pipeline(ctx, ref, nbrs, nn, r0, r1);
+        }
     }
+
+    // Where this view runs: one of the two lanes (its own stream and scratch), or the context stream when
+    // something context-wide is written (kept volume, peak lists, statistics, per-stage timing).
+    const bool on_lane = ctx->num_lanes > 1 && !ctx->profiling && !P.keep_cost_volume && !ctx->d_stats;
+    if (!on_lane) JOIN();
+    sr_ctx::Lane *L = on_lane ? &ctx->lanes[ctx->next_lane] : nullptr;
+    cudaStream_t st = on_lane ? L->stream : ctx->stream;
+    double *&d_rays = on_lane ? L->d_rays : ctx->d_rays;
+    int32_t *&d_taps = on_lane ? L->d_taps : ctx->d_taps;
+    size_t &taps_cap = on_lane ? L->taps_cap : ctx->taps_cap;
+    double *&d_weights = on_lane ? L->d_weights : ctx->d_weights;
+    size_t &weights_cap = on_lane ? L->weights_cap : ctx->weights_cap;
+    if (on_lane) {
+        const int li = ctx->next_lane;
+        ctx->next_lane = (ctx->next_lane + 1) % ctx->num_lanes;
+        CK(cudaEventRecord(ctx->ev_fork, ctx->stream));  // inputs uploaded on the context stream are visible
+        CK(cudaStreamWaitEvent(st, ctx->ev_fork, 0));
+        // the same view still in flight on the other lane (it writes the same output maps): order them
+        if ((int)ctx->view_lane.size() != ctx->V) ctx->view_lane.assign(ctx->V, -1);
+        const int prev = ctx->view_lane[ref];
+        if (prev >= 0 && prev != li && ctx->lanes[prev].pending) CK(cudaStreamWaitEvent(st, ctx->lanes[prev].done, 0));
+        ctx->view_lane[ref] = li;
+        if (n * 6 * 8 > L->rays_cap) {
+            CK(cudaStreamSynchronize(st));
+            dfree(L->d_rays);
+            L->rays_cap = 0;
+            CK(cudaMalloc(&L->d_rays, n * 6 * 8));
+            L->rays_cap = n * 6 * 8;
+        }
+    }
+
+    rays_kernel<<<(unsigned)(((size_t)(r1 - r0) * w + 127) / 128), 128, 0, st>>>(ctx->cams[ref], w, h, r0, r1 - r0, P.image_scale, d_rays);
+    CKL();
 
     // Row bands bound the scratch (tap volume nn*D*rows*w*4 bytes + support weights
     // WN*rows*w*8 bytes); a kept cost volume needs one band.
@@ -629,19 +724,19 @@ int sr_run_view(sr_ctx *ctx, int ref, const int32_t *nbrs, int nn) {
     if (P.keep_cost_volume & 1) band = r1 - r0;
     const size_t need = per_row * band;
     const size_t need_w = per_row_w * band;
-    if (need_w > ctx->weights_cap) {
+    if (need_w > weights_cap) {
         CK(cudaStreamSynchronize(st));
-        dfree(ctx->d_weights);
-        ctx->weights_cap = 0;
-        CK(cudaMalloc(&ctx->d_weights, need_w));
-        ctx->weights_cap = need_w;
+        dfree(d_weights);
+        weights_cap = 0;
+        CK(cudaMalloc(&d_weights, need_w));
+        weights_cap = need_w;
     }
-    if (need > ctx->taps_cap) {
+    if (need > taps_cap) {
         CK(cudaStreamSynchronize(st));
-        dfree(ctx->d_taps);
-        ctx->taps_cap = 0;
-        CK(cudaMalloc(&ctx->d_taps, need));
-        ctx->taps_cap = need;
+        dfree(d_taps);
+        taps_cap = 0;
+        CK(cudaMalloc(&d_taps, need));
+        taps_cap = need;
     }
     rc = init_peaks(ctx, ref);
     if (rc) return rc;
@@ -679,11 +774,11 @@ int sr_run_view(sr_ctx *ctx, int ref, const int32_t *nbrs, int nn) {
                 refr_pixel_map(nb, mvs, P.image_scale, ra.Kn, ra.fxs, ra.cxs, ra.fys, ra.cys);
                 memcpy(ra.prin, ctx->cams[ref].prin_dir, sizeof(ra.prin));
                 memcpy(ra.C, ctx->cams[ref].C, sizeof(ra.C));
-                ra.rays = ctx->d_rays;
+                ra.rays = d_rays;
                 ra.depth_table = ctx->d_depth_table;
                 ra.ref_mask = A.mask;
                 ra.nbr_mask = ctx->views[nbrs[j]].all_white ? nullptr : ctx->views[nbrs[j]].mask;
-                ra.taps = ctx->d_taps + (size_t)j * D * plane;
+                ra.taps = d_taps + (size_t)j * D * plane;
                 ra.w = w;
                 ra.h = h;
                 ra.row0 = b0;
@@ -703,11 +798,11 @@ int sr_run_view(sr_ctx *ctx, int ref, const int32_t *nbrs, int nn) {
             ba.nbr = nb;
             memcpy(ba.prin, ctx->cams[ref].prin_dir, sizeof(ba.prin));
             memcpy(ba.C, ctx->cams[ref].C, sizeof(ba.C));
-            ba.rays = ctx->d_rays;
+            ba.rays = d_rays;
             ba.depth_table = ctx->d_depth_table;
             ba.ref_mask = A.mask;
             ba.nbr_mask = ctx->views[nbrs[j]].mask;
-            ba.taps = ctx->d_taps + (size_t)j * D * plane;
+            ba.taps = d_taps + (size_t)j * D * plane;
             ba.w = w;
             ba.h = h;
             ba.row0 = b0;
@@ -726,7 +821,7 @@ int sr_run_view(sr_ctx *ctx, int ref, const int32_t *nbrs, int nn) {
             wa.rgba = A.rgba;
             wa.mask = A.mask;
             wa.edges = A.edges;
-            wa.W = ctx->d_weights;
+            wa.W = d_weights;
             wa.w = w;
             wa.h = h;
             wa.row0 = b0;
@@ -740,7 +835,7 @@ int sr_run_view(sr_ctx *ctx, int ref, const int32_t *nbrs, int nn) {
         }
         MatchArgs ma;
         memset(&ma, 0, sizeof(ma));
-        ma.W = ctx->d_weights;
+        ma.W = d_weights;
         ma.maskL = A.mask;
         ma.grayL = (P.cost_kind == SR_COST_NCC_MVS) ? A.gray_pix : A.gray_two;
         for (int j = 0; j < nn; ++j) {
@@ -750,7 +845,7 @@ int sr_run_view(sr_ctx *ctx, int ref, const int32_t *nbrs, int nn) {
             ma.grayRf[j] = B.gray_pix_f;
         }
         ma.pitch_f = screen_pitch(w);
-        ma.taps = ctx->d_taps;
+        ma.taps = d_taps;
         ma.depth_table = ctx->d_depth_table;
         ma.out_index = A.index;
         ma.out_depth = A.depth;
@@ -779,6 +874,10 @@ int sr_run_view(sr_ctx *ctx, int ref, const int32_t *nbrs, int nn) {
             for (int k = 0; k < 3; ++k) ctx->prof_events.push_back(ev[k]);
         }
     }
+    if (on_lane) {
+        CK(cudaEventRecord(L->done, st));
+        L->pending = true;
+    }
     return SR_OK;
 }
 
@@ -793,6 +892,7 @@ int sr_set_profiling(sr_ctx *ctx, int on) {
 int sr_get_stage_ms(sr_ctx *ctx, double *out4) {
     if (!ctx || !out4) return SR_ERR_INVALID;
     CK(cudaSetDevice(ctx->device));
+    JOIN();
     CK(cudaStreamSynchronize(ctx->stream));
     out4[0] = out4[1] = out4[2] = out4[3] = 0;
     for (size_t i = 0; i + 2 < ctx->prof_events.size(); i += 3) {
@@ -861,6 +961,7 @@ int sr_run_view_curve(sr_ctx *ctx, int ref, const int32_t *nbrs, int nn) {
     if (P.keep_cost_volume & 1) return fail(ctx, SR_ERR_INVALID, "curve mode keeps no cost volume (candidates are not labels)");
     if (mvs && P.cost_kind != SR_COST_NCC_MVS) return fail(ctx, SR_ERR_INVALID, "multi-view curve search uses SR_COST_NCC_MVS");
     CK(cudaSetDevice(ctx->device));
+    JOIN();
     cudaStream_t st = ctx->stream;
     const int w = ctx->w, h = ctx->h, D = P.num_levels;
     const int r0 = std::max(P.row_begin, 0);
@@ -1065,6 +1166,7 @@ int sr_cross_check(sr_ctx *ctx, int two_view, double threshold) {
     if (ctx->V == 0 || !ctx->have_params) return fail(ctx, SR_ERR_STATE, "views/params not set");
     if (two_view && ctx->V != 2) return fail(ctx, SR_ERR_INVALID, "two-view cross-check needs exactly 2 views");
     CK(cudaSetDevice(ctx->device));
+    JOIN();
     const size_t n = (size_t)ctx->w * ctx->h;
     // View by view, in place, in index order: view v sees the already-updated maps of views < v,
     // exactly as twoviewstereo.cpp:604-670 / multiviewstereo.cpp:427-431 do.
@@ -1086,15 +1188,23 @@ int sr_cross_check(sr_ctx *ctx, int two_view, double threshold) {
     return SR_OK;
 }
 
+int sr_flush(sr_ctx *ctx) {
+    if (!ctx) return SR_ERR_INVALID;
+    CK(cudaSetDevice(ctx->device));
+    JOIN();
+    return SR_OK;
+}
 int sr_synchronize(sr_ctx *ctx) {
     if (!ctx) return SR_ERR_INVALID;
     CK(cudaSetDevice(ctx->device));
+    JOIN();
     CK(cudaStreamSynchronize(ctx->stream));
     return SR_OK;
 }
 
 static int d2h(sr_ctx *ctx, void *dst, const void *src, size_t bytes) {
     CK(cudaSetDevice(ctx->device));
+    JOIN();
     CK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     return SR_OK;
@@ -1138,6 +1248,7 @@ int sr_set_depth(sr_ctx *ctx, int view, const double *depth) {
     int rc = check_view(ctx, view);
     if (rc) return rc;
     CK(cudaSetDevice(ctx->device));
+    JOIN();
     CK(cudaMemcpyAsync(ctx->views[view].depth, depth, (size_t)ctx->w * ctx->h * 8, cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     return SR_OK;
@@ -1161,6 +1272,7 @@ int sr_unproject_grid(sr_ctx *ctx, int view, double *out) {
     int rc = check_view(ctx, view);
     if (rc) return rc;
     CK(cudaSetDevice(ctx->device));
+    JOIN();
     const size_t n = (size_t)ctx->w * ctx->h;
     const double scale = ctx->have_params ? ctx->params.image_scale : 1.0;
     rays_kernel<<<(unsigned)((n + 127) / 128), 128, 0, ctx->stream>>>(ctx->cams[view], ctx->w, ctx->h, 0, ctx->h, scale, ctx->d_rays);
@@ -1297,6 +1409,7 @@ int sr_comm_allgather_views(sr_ctx *ctx, const int32_t *owner) {
     for (int v = 0; v < ctx->V; ++v)
         if (owner[v] < 0 || owner[v] >= ctx->nranks) return fail(ctx, SR_ERR_INVALID, "sr_comm_allgather_views: owner rank out of range");
     CK(cudaSetDevice(ctx->device));
+    JOIN();
     const size_t n = (size_t)ctx->w * ctx->h;
     int r = g_nccl.GroupStart();
     for (int v = 0; v < ctx->V && r == 0; ++v) {
@@ -1320,6 +1433,7 @@ int sr_comm_allgather_rows(sr_ctx *ctx, int view, const int32_t *row_begin, cons
         if (row_begin[k] < 0 || row_begin[k] > row_end[k] || row_end[k] > ctx->h)
             return fail(ctx, SR_ERR_INVALID, "sr_comm_allgather_rows: need 0 <= row_begin <= row_end <= height for every rank");
     CK(cudaSetDevice(ctx->device));
+    JOIN();
     ViewDev &d = ctx->views[view];
     int r = g_nccl.GroupStart();
     for (int k = 0; k < ctx->nranks && r == 0; ++k) {
