@@ -377,6 +377,10 @@ __device__ __noinline__ double slow_cost(const MatchArgs &a, const double *__res
     constexpr bool NCC = (COST != SR_COST_SAD_TWOVIEW);
     const int w = a.w, h = a.h;
     const size_t npix = (size_t)a.rows * w;
+    // A window that lies entirely outside the neighbour image has no valid tap: the filter below would find
+    // cnt = 0, tw = 0.  (Rectified pairs: every label whose disparity exceeds the pixel's column by more than
+    // the radius — a tenth of cfg3's evaluations, each of which walked all (2R+1)^2 taps to learn that.)
+    if (tx + R < 0 || ty + R < 0 || tx - R >= w || ty - R >= h) return (COST == SR_COST_NCC_MVS) ? 0.0 : 1000.0;
     double mL = 0.0, mR = 0.0, tw = 0.0;
     int cnt = 0;
 #pragma unroll 1

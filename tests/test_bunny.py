@@ -37,7 +37,7 @@ def test_oracle_reconstructs_the_bunny():
     cams, imgs, masks, scale = load()
     sc = O.Scene(cams, imgs, masks)
     nb = sc.select_neighbours(3)
-    P = T.default_params(True, 300.0, 800.0, 100, image_scale=scale)
+    P = T.default_params(True, 30.0, 55.0, 100, image_scale=scale)
     od, oi, ob, _, _ = sc.mvs_view(P, 0, nb[0])
     obj = masks[0] == 255
     have = obj & (oi >= 0)
@@ -73,7 +73,7 @@ def test_cfg1_bunny_two_view(gpu_ctx, refractive):
     two, im2, ms2 = cams[:2], imgs[:2], masks[:2]
     sc = O.Scene(two, im2, ms2)
     gpu_ctx.set_views(two, im2, ms2)
-    P = T.default_params(False, 300.0, 800.0, 100, image_scale=scale)
+    P = T.default_params(False, 30.0, 55.0, 100, image_scale=scale)
     gpu_ctx.set_params(P)
     depths = []
     for (a, b) in ((0, 1), (1, 0)):
@@ -96,7 +96,7 @@ def test_cfg2_bunny_multi_view(gpu_ctx, weight):
     cams, imgs, masks, scale = load(refractive=True)
     sc = O.Scene(cams, imgs, masks)
     gpu_ctx.set_views(cams, imgs, masks)
-    P = T.default_params(True, 300.0, 800.0, 100, image_scale=scale, weight_kind=weight)
+    P = T.default_params(True, 30.0, 55.0, 100, image_scale=scale, weight_kind=weight)
     gpu_ctx.set_params(P)
     nb = gpu_ctx.select_neighbours(3)
     assert nb == [[int(v) for v in r] for r in sc.select_neighbours(3)]
