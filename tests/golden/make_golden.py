@@ -152,14 +152,23 @@ def ref_mvs():
         after, nb = ref.run()
         out[f"{name}_cams"] = G.cams_to_bytes(cams)
         out[f"{name}_neighbours"] = np.array([r + [-1] * (3 - len(r)) for r in nb], np.int32)
-        out[f"{name}_after"] = after
+        keep = G.ref_mvs_kept_views(name, len(cams))
         before = []
         for v in range(len(cams)):
             d, pk = ref.initial_estimate(v)
             before.append(d)
             if v == 1:
-                out[f"{name}_peaks_v1"] = pk
-        out[f"{name}_before"] = np.array(before)
+                r0, r1 = G.ref_mvs_peak_rows(name, d.shape[0])
+                out[f"{name}_peaks_v1"] = pk[r0:r1]
+        before = np.array(before)
+        out[f"{name}_views"] = np.array(keep, np.int32)
+        out[f"{name}_before"] = before[keep]
+        if len(keep) == len(cams):
+            # the cross-check only ever replaces a depth by NaN: the mask of those pixels IS the map after it
+            nan_after = np.isnan(after)
+            rebuilt = np.where(nan_after, np.nan, before)
+            assert ((rebuilt == after) | (np.isnan(rebuilt) & np.isnan(after))).all()
+            out[f"{name}_after_nan"] = np.packbits(nan_after)
         ref.close()
     return out
 

@@ -152,12 +152,32 @@ def cams_from_bytes(buf):
 REF_MVS_CASES = {
     # name: (min depth, max depth, levels, cross-check threshold)
     "arc": (420.0, 580.0, 40, 12.0),
-    "bunny": (30.0, 55.0, 100, 5.0),        # README.md:103-112 / SURVEY 8d cfg2
-    "bunny_refr": (30.0, 55.0, 100, 5.0),   # ... with the injected interface
+    "bunny_refr": (30.0, 55.0, 100, 5.0),   # SURVEY 8d cfg2 with the injected interface (depth range: see above)
     # the same reference file built with `typedef AdaptiveWeight WeightFunc` (BASELINE configs[1]: adaptive-weight aggregation)
     "arc_ada": (420.0, 580.0, 40, 12.0),
     "bunny_refr_ada": (30.0, 55.0, 100, 5.0),
 }
+
+
+def ref_mvs_kept_views(name, V):
+    """Views whose depth maps before the cross-check are kept in ref_mvs.npz.  (With a depth range that finds
+    the object the maps are real-valued and do not compress: the AdaptiveWeight bunny case keeps two views.)"""
+    return [1, 2] if name == "bunny_refr_ada" else list(range(V))
+
+
+def ref_mvs_peak_rows(name, h):
+    """Rows of view 1 whose K = 9 peak lists are kept."""
+    return (0, h) if name.startswith("arc") else (h // 2 - 16, h // 2 + 16)
+
+
+def ref_mvs_after(g, name, shape):
+    """The depth maps after the cross-check, rebuilt from the maps before it and the mask of the pixels it
+    invalidated (None when the case keeps a subset of the views)."""
+    if f"{name}_after_nan" not in g:
+        return None
+    before = g[f"{name}_before"]
+    nan_after = np.unpackbits(g[f"{name}_after_nan"])[:before.size].reshape(before.shape).astype(bool)
+    return np.where(nan_after, np.nan, before)
 
 
 def ref_mvs_adaptive(name):

@@ -32,8 +32,9 @@ def test_bunny_fixture_and_cameras():
 
 
 def test_oracle_reconstructs_the_bunny():
-    """Label-mode MVS of one view with the reference's parameters (README: depth 300-800, 100 levels):
-    a sizeable part of the object gets a depth, and the depths lie where the object is."""
+    """Label-mode MVS of one view (100 levels over the depth range that brackets the object for the cameras of
+    example/project.xml, see golden_cases.py): nearly all of the object gets a depth, and the depths lie where
+    the object is (the cameras sit on a semi-circle of radius ~42 around it)."""
     cams, imgs, masks, scale = load()
     sc = O.Scene(cams, imgs, masks)
     nb = sc.select_neighbours(3)
@@ -41,8 +42,8 @@ def test_oracle_reconstructs_the_bunny():
     od, oi, ob, _, _ = sc.mvs_view(P, 0, nb[0])
     obj = masks[0] == 255
     have = obj & (oi >= 0)
-    assert have.sum() > 0.15 * obj.sum()  # 24 % at this reduced size (ncc > 0.95 is a strict bar)
-    assert 300 <= np.median(od[have]) <= 800
+    assert have.sum() > 0.9 * obj.sum()
+    assert 35 <= np.median(od[have]) <= 50
     assert np.isinf(od[~obj]).all()
 
 

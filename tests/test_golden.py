@@ -163,20 +163,24 @@ def test_oracle_matches_reference_mvs_golden(ref_mvs_gold, name):
     nb = [[int(v) for v in r if v >= 0] for r in g[f"{name}_neighbours"]]
     assert nb == [[int(v) for v in r] for r in sc.select_neighbours(3)]
     rel = 0.0 if name.startswith("arc") else 1e-12
-    before = []
-    for v in range(len(cams)):
+    views = [int(v) for v in g[f"{name}_views"]]
+    found = 0
+    for k, v in enumerate(views):
         od, _, _, _, op = sc.mvs_view(P, v, nb[v], curve_mode=True, root_mode=0, want_peaks=(v == 1))
-        before.append(od)
-        ok = _depth_close(od, g[f"{name}_before"][v], rel)
+        found += int((np.isfinite(od) & (od > 0)).sum())
+        ok = _depth_close(od, g[f"{name}_before"][k], rel)
         assert ok.mean() >= 1 - 1e-4, (v, 1 - ok.mean())
         if v == 1:
-            white = ms[v] == 255
-            assert _depth_close(op[white], g[f"{name}_peaks_v1"][white], rel).mean() >= 1 - 1e-4
+            r0, r1 = G.ref_mvs_peak_rows(name, od.shape[0])
+            white = ms[v][r0:r1] == 255
+            assert _depth_close(op[r0:r1][white], g[f"{name}_peaks_v1"][white], rel).mean() >= 1 - 1e-4
+    assert found > 1000  # not vacuous: the reference found depths
     # the cross-check of the reference's own depths: bit for bit in every case
-    want = sc.crosscheck_mvs(P, [g[f"{name}_before"][v].copy() for v in range(len(cams))], cross)
-    for v in range(len(cams)):
-        assert _same(want[v], g[f"{name}_after"][v])
-    assert sum((np.isfinite(b) & (b > 0)).sum() for b in before) > 1000
+    after = G.ref_mvs_after(g, name, None)
+    if after is not None:
+        want = sc.crosscheck_mvs(P, [g[f"{name}_before"][v].copy() for v in range(len(cams))], cross)
+        for v in range(len(cams)):
+            assert _same(want[v], after[v])
 
 
 @pytest.mark.gpu
@@ -194,13 +198,14 @@ def test_gpu_curve_mode_matches_reference_mvs_golden(ref_mvs_gold, gpu_ctx, name
     gpu_ctx.set_params(P)
     nb = gpu_ctx.select_neighbours(3)
     assert nb == [[int(v) for v in r if v >= 0] for r in g[f"{name}_neighbours"]]
+    after = G.ref_mvs_after(g, name, None)
     for v in range(len(cams)):
         gpu_ctx.run_view_curve(v, nb[v])
         ok = _depth_close(gpu_ctx.depth(v), g[f"{name}_before"][v], 1e-9)
         assert ok.mean() >= 1 - 1e-4, (v, 1 - ok.mean())
     gpu_ctx.cross_check(False, cross)
     for v in range(len(cams)):
-        ok = _depth_close(gpu_ctx.depth(v), g[f"{name}_after"][v], 1e-9)
+        ok = _depth_close(gpu_ctx.depth(v), after[v], 1e-9)
         assert ok.mean() >= 1 - 2e-4, (v, 1 - ok.mean())
 
 
