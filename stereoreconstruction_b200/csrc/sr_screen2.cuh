@@ -44,6 +44,9 @@ namespace sr {
 #ifndef SR_SCREEN2_ABL
 #define SR_SCREEN2_ABL 0  // 1-4: timing ablations of the label loop (wrong results; profiling only)
 #endif
+#ifndef SR_SCREEN2_LV
+#define SR_SCREEN2_LV 1  // NL = 2: FFMA2 vectorised across the two labels (scalar weight operand) instead of two taps
+#endif
 #ifndef SR_SCREEN2_PRE
 #define SR_SCREEN2_PRE 0  // 1: two-level sweep (subset bound first, full window for the survivors)
 #endif
@@ -524,6 +527,52 @@ struct Screener {
 #endif
     }
 
+    // Two windows at once, vectorised ACROSS the two labels: every FFMA2 carries tap i of both windows in its
+    // two halves and the tap's weight as a scalar (broadcast) operand.  The sums of a label live in one half
+    // of an accumulator, so there is no horizontal reduction, the 25th tap is not a scalar straggler, and the
+    // whole tail (mean, s3, s1, kappa, error bar, bounds) is packed as well: ~58 FMA-pipe instructions per
+    // label instead of ~77 (the loop's time is additive in them).
+    __device__ __forceinline__ void eval_window2(const float (&gA)[WN], const float (&gB)[WN], float (&ub)[2], float (&lb)[2],
+                                                 float (&eps_out)[2]) const {
+        const float2 zero = make_float2(0.0f, 0.0f);
+        float2 S1 = zero, Q = zero, X = zero;
+#pragma unroll
+        for (int i = 0; i < WN; ++i) {
+            const float2 gv = make_float2(gA[i], gB[i]);
+            const float2 wv = make_float2(wtf[i], wtf[i]);
+            S1 = fma2(gv, wv, S1);
+#if SR_SCREEN2_ABL != 2
+            const float2 pv = fma2(gv, wv, zero);
+            Q = fma2(pv, pv, Q);
+            X = fma2(gv, make_float2(c1f[i], c1f[i]), X);
+#endif
+        }
+        const float2 mR = fma2(S1, make_float2(inv_totWf, inv_totWf), zero);
+        const float2 mR2 = fma2(mR, mR, zero);
+        const float2 s3 = fma2(mR2, make_float2(-k0, -k0), Q);
+        const float2 s1 = fma2(mR, make_float2(-k1, -k1), X);
+        float2 rs;
+        asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(rs.x) : "f"(s3.x));
+        asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(rs.y) : "f"(s3.y));
+        const float2 c32 = fma2(s1, rs, zero);
+        const float2 kappa = fma2(Q, fma2(rs, rs, zero), zero);
+        const float2 eps = fma2(kappa, make_float2(e1, e1), make_float2(e0, e0));  // e0 + e1 * kappa
+        const float2 up = fma2(eps, make_float2(1.0f, 1.0f), c32), lo = fma2(eps, make_float2(-1.0f, -1.0f), c32);
+        const bool okx = (s3.x >= (float)WN) && (eps.x <= SCREEN_EPS_MAX), oky = (s3.y >= (float)WN) && (eps.y <= SCREEN_EPS_MAX);
+        eps_out[0] = eps.x;
+        eps_out[1] = eps.y;
+#if SR_SCREEN2_ABL
+        lb[0] = lb[1] = SCREEN_SKIP;
+        ub[0] = (okx && c32.x > 1e30f) ? up.x : SCREEN_SKIP;
+        ub[1] = (oky && c32.y > 1e30f) ? up.y : SCREEN_SKIP;
+#else
+        lb[0] = okx ? lo.x : SCREEN_SKIP;
+        lb[1] = oky ? lo.y : SCREEN_SKIP;
+        ub[0] = okx ? up.x : SCREEN_FORCE;
+        ub[1] = oky ? up.y : SCREEN_FORCE;
+#endif
+    }
+
     // NL windows at once: independent chains of one basic block.
     template <int NL>
     __device__ __forceinline__ void screen_n(const float *__restrict__ gplane, const int (&idx)[NL], float (&ub)[NL], float (&lb)[NL],
@@ -531,6 +580,17 @@ struct Screener {
         float g[NL][WN];
 #pragma unroll
         for (int n = 0; n < NL; ++n) load_window(gplane, idx[n], g[n]);
+        if (NL == 2 && ONEPASS && SR_SCREEN2_LV) {
+            float ub2[2], lb2[2], ep2[2];
+            eval_window2(g[0], g[NL - 1], ub2, lb2, ep2);
+#pragma unroll
+            for (int n = 0; n < NL; ++n) {
+                ub[n] = ub2[n];
+                lb[n] = lb2[n];
+                eps_out[n] = ep2[n];
+            }
+            return;
+        }
 #pragma unroll
         for (int n = 0; n < NL; ++n) eval_window(g[n], ub[n], lb[n], eps_out[n]);
     }
