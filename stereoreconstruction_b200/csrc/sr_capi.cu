@@ -143,6 +143,10 @@ struct sr_ctx {
     int num_lanes = 2, next_lane = 0;
     cudaEvent_t ev_fork = nullptr;
     std::vector<int> view_lane;  // lane that last ran each reference view (-1: none pending)
+    // Downloads of a view that is still on a lane wait for THAT view only (its own event) and run on a copy
+    // stream: sr_get_depth(v) overlaps the views enqueued after v instead of joining all of them.
+    std::vector<cudaEvent_t> view_done;
+    cudaStream_t copy_stream = nullptr;
     bool use_pipeline = false;  // SR_PIPELINE=1: build and screen as roles of ONE launch (sr_pipeline.cuh; measured slower: DESIGN.md)
     int pipe_lag = 128;        // tiles between a tile's build and its screen (SR_PIPE_LAG)
     size_t pipe_ring_bytes = (size_t)1 << 30;  // tap ring of the pipeline kernel (SR_PIPE_RING_MB)
@@ -203,6 +207,10 @@ void free_views(sr_ctx *c) {
         dfree(v.best);
     }
     c->views.clear();
+    for (cudaEvent_t e : c->view_done)
+        if (e) cudaEventDestroy(e);
+    c->view_done.clear();
+    c->view_lane.clear();
     c->peaks_view = -1;  // peak lists belong to the image size they were computed at
     dfree(c->d_cams);
     dfree(c->d_depth_ptrs);
@@ -316,6 +324,7 @@ int sr_ctx_create(int device, sr_ctx **out) {
         for (int i = 0; i < c->num_lanes && ok; ++i)
             ok = cudaStreamCreateWithFlags(&c->lanes[i].stream, cudaStreamNonBlocking) == cudaSuccess &&
                  cudaEventCreateWithFlags(&c->lanes[i].done, cudaEventDisableTiming) == cudaSuccess;
+        ok = ok && cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking) == cudaSuccess;
         if (!ok) c->num_lanes = 1;
     }
     if (const char *sl = getenv("SR_PIPE_LAG")) c->pipe_lag = std::max(1, atoi(sl));
@@ -354,6 +363,7 @@ void sr_ctx_destroy(sr_ctx *c) {
         if (L.stream) cudaStreamDestroy(L.stream);
     }
     if (c->ev_fork) cudaEventDestroy(c->ev_fork);
+    if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
     if (c->d_scratch) cudaFree(c->d_scratch);
     cudaStreamDestroy(c->own_stream);
     delete c;
@@ -877,6 +887,13 @@ int sr_run_view(sr_ctx *ctx, int ref, const int32_t *nbrs, int nn) {
     if (on_lane) {
         CK(cudaEventRecord(L->done, st));
         L->pending = true;
+        if ((int)ctx->view_done.size() != ctx->V) {
+            for (cudaEvent_t e : ctx->view_done)
+                if (e) cudaEventDestroy(e);
+            ctx->view_done.assign(ctx->V, nullptr);
+        }
+        if (!ctx->view_done[ref]) CK(cudaEventCreateWithFlags(&ctx->view_done[ref], cudaEventDisableTiming));
+        CK(cudaEventRecord(ctx->view_done[ref], st));
     }
     return SR_OK;
 }
@@ -1202,8 +1219,17 @@ int sr_synchronize(sr_ctx *ctx) {
     return SR_OK;
 }
 
-static int d2h(sr_ctx *ctx, void *dst, const void *src, size_t bytes) {
+static int d2h(sr_ctx *ctx, void *dst, const void *src, size_t bytes, int view = -1) {
     CK(cudaSetDevice(ctx->device));
+    if (view >= 0 && view < (int)ctx->view_lane.size() && ctx->view_lane[view] >= 0 && view < (int)ctx->view_done.size() &&
+        ctx->view_done[view] && ctx->copy_stream) {
+        // the view is still on a lane: nothing on the context stream has touched its maps since (that would
+        // have joined the lanes), so its own event is all this copy has to wait for
+        CK(cudaStreamWaitEvent(ctx->copy_stream, ctx->view_done[view], 0));
+        CK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, ctx->copy_stream));
+        CK(cudaStreamSynchronize(ctx->copy_stream));
+        return SR_OK;
+    }
     JOIN();
     CK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
@@ -1213,17 +1239,17 @@ static int d2h(sr_ctx *ctx, void *dst, const void *src, size_t bytes) {
 int sr_get_depth_index(sr_ctx *ctx, int view, int32_t *out) {
     int rc = check_view(ctx, view);
     if (rc) return rc;
-    return d2h(ctx, out, ctx->views[view].index, (size_t)ctx->w * ctx->h * 4);
+    return d2h(ctx, out, ctx->views[view].index, (size_t)ctx->w * ctx->h * 4, view);
 }
 int sr_get_depth(sr_ctx *ctx, int view, double *out) {
     int rc = check_view(ctx, view);
     if (rc) return rc;
-    return d2h(ctx, out, ctx->views[view].depth, (size_t)ctx->w * ctx->h * 8);
+    return d2h(ctx, out, ctx->views[view].depth, (size_t)ctx->w * ctx->h * 8, view);
 }
 int sr_get_best_cost(sr_ctx *ctx, int view, double *out) {
     int rc = check_view(ctx, view);
     if (rc) return rc;
-    return d2h(ctx, out, ctx->views[view].best, (size_t)ctx->w * ctx->h * 8);
+    return d2h(ctx, out, ctx->views[view].best, (size_t)ctx->w * ctx->h * 8, view);
 }
 int sr_get_cost_volume(sr_ctx *ctx, float *out, size_t out_elems) {
     if (!ctx || !out) return SR_ERR_INVALID;

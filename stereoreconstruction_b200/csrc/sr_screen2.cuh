@@ -589,10 +589,10 @@ struct Screener {
                 lb[n] = lb2[n];
                 eps_out[n] = ep2[n];
             }
-            return;
-        }
+        } else {
 #pragma unroll
-        for (int n = 0; n < NL; ++n) eval_window(g[n], ub[n], lb[n], eps_out[n]);
+            for (int n = 0; n < NL; ++n) eval_window(g[n], ub[n], lb[n], eps_out[n]);
+        }
     }
 
     // A ring entry -> is its window interior to the neighbour image (then idx = its element index, else a
