@@ -1032,9 +1032,14 @@ int sr_run_view_curve(sr_ctx *ctx, int ref, const int32_t *nbrs, int nn) {
         ca.mvs = mvs;
         return ca;
     };
-    auto launch_curve = [&](const CurveArgs &ca, unsigned gx) {
-        if (ca.nbr.is_refractive) curve_build_kernel<true><<<gx, 128, 0, st>>>(ca);
-        else curve_build_kernel<false><<<gx, 128, 0, st>>>(ca);
+    auto launch_curve = [&](const CurveArgs &ca, unsigned gx, bool masked) {
+        if (ca.nbr.is_refractive) {
+            if (masked) curve_build_kernel<true, true><<<gx, 128, 0, st>>>(ca);
+            else curve_build_kernel<true, false><<<gx, 128, 0, st>>>(ca);
+        } else {
+            if (masked) curve_build_kernel<false, true><<<gx, 128, 0, st>>>(ca);
+            else curve_build_kernel<false, false><<<gx, 128, 0, st>>>(ca);
+        }
     };
 
     int cap = 2 * D + 64;  // planes per neighbour: curves are rarely longer than the label count
@@ -1043,6 +1048,11 @@ int sr_run_view_curve(sr_ctx *ctx, int ref, const int32_t *nbrs, int nn) {
         if (ctx->cancel.load()) return fail(ctx, SR_ERR_CANCELLED, "cancelled");
         int rows = std::min(band, r1 - b0);
         int L = 1;
+        cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
+        if (ctx->profiling) {
+            for (int k = 0; k < 3; ++k) CK(cudaEventCreate(&ev[k]));
+            CK(cudaEventRecord(ev[0], st));
+        }
         for (int attempt = 0;; ++attempt) {
             const size_t plane = (size_t)rows * w;
             const size_t need = (size_t)nn * cap * plane * 4, need_w = per_row_w * rows;
@@ -1070,7 +1080,7 @@ int sr_run_view_curve(sr_ctx *ctx, int ref, const int32_t *nbrs, int nn) {
                 ca.taps = ctx->d_taps + (size_t)j * cap * plane;
                 ca.capacity = cap;
                 ca.max_count = d_max;
-                launch_curve(ca, gx);
+                launch_curve(ca, gx, !ctx->views[nbrs[j]].all_white);
                 CKL();
             }
             int32_t hmax = 0;
@@ -1086,6 +1096,7 @@ int sr_run_view_curve(sr_ctx *ctx, int ref, const int32_t *nbrs, int nn) {
         }
         const size_t plane = (size_t)rows * w;
         const unsigned gx = (unsigned)((plane + 127) / 128);
+        if (ctx->profiling) CK(cudaEventRecord(ev[1], st));
         {
             WeightArgs wa;
             memset(&wa, 0, sizeof(wa));
@@ -1145,6 +1156,10 @@ int sr_run_view_curve(sr_ctx *ctx, int ref, const int32_t *nbrs, int nn) {
         cudaError_t e = launch_match(P.radius, P.cost_kind, ma, st);
         ++ctx->launches;
         if (e != cudaSuccess) return fail(ctx, SR_ERR_CUDA, std::string("match kernel: ") + cudaGetErrorString(e));
+        if (ctx->profiling) {
+            CK(cudaEventRecord(ev[2], st));
+            for (int k = 0; k < 3; ++k) ctx->prof_events.push_back(ev[k]);
+        }
         b0 += rows;
     }
     return SR_OK;

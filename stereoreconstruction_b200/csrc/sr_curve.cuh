@@ -29,7 +29,7 @@ struct CurveArgs {
     const double *rays;          // [6][h][w] of the reference view
     const double *depth_table;   // [D]
     const uint8_t *ref_mask;
-    const uint8_t *nbr_mask;     // never null here (a null mask is a plane of 255)
+    const uint8_t *nbr_mask;     // a plane of 255 when the view was given no mask (then the launch uses HAS_MASK = false)
     int32_t *taps;               // [capacity][rows][w] for this neighbour (null: only measure the curve lengths)
     int32_t *max_count;          // device scalar, atomicMax of the curve lengths over all pixels
     int w, h, row0, rows, D, capacity;
@@ -91,7 +91,9 @@ __device__ inline bool clip_line(int &x0, int &y0, int &x1, int &y1, int w, int 
     }
 }
 
-template <bool REFR>
+// HAS_MASK = false: the neighbour was given no mask (every pixel WHITE): the rasteriser's per-step mask
+// gather — a dependent global load in a serial loop, the latency that bounds this kernel — is compiled out.
+template <bool REFR, bool HAS_MASK>
 __global__ void __launch_bounds__(128) curve_build_kernel(const __grid_constant__ CurveArgs a) {
     const int pid = blockIdx.x * blockDim.x + threadIdx.x;
     if (pid >= a.rows * a.w) return;
@@ -177,7 +179,7 @@ __global__ void __launch_bounds__(128) curve_build_kernel(const __grid_constant_
             long long guard = 0;
             for (int lx = ax0; lx <= ax1; ++lx) {
                 const int tx = steep ? ly : lx, ty = steep ? lx : ly;
-                if (tx >= 0 && ty >= 0 && tx < a.w && ty < a.h && a.nbr_mask[(size_t)ty * a.w + tx] == 255) {
+                if (tx >= 0 && ty >= 0 && tx < a.w && ty < a.h && (!HAS_MASK || a.nbr_mask[(size_t)ty * a.w + tx] == 255)) {
                     const int32_t tap = (int32_t)(((uint32_t)ty << 16) | (uint32_t)tx);
                     if (!(a.mvs && tap == last)) {  // multiviewstereo.cpp:800-807
                         if (count < cap) a.taps[(size_t)count * plane + pid] = tap;
