@@ -801,10 +801,10 @@ struct Screener {
 };
 
 #ifndef SR_SCREEN2_TILE_ROWS
-#define SR_SCREEN2_TILE_ROWS 8  // warps per block: a block owns a 32 x TILE_ROWS tile of reference pixels
+#define SR_SCREEN2_TILE_ROWS 4  // warps per block: a block owns a 32 x TILE_ROWS tile of reference pixels (measured: 4 < 8 < 1)
 #endif
 #ifndef SR_SCREEN2_MINBLOCKS
-#define SR_SCREEN2_MINBLOCKS 2  // resident blocks per SM the register allocation must allow
+#define SR_SCREEN2_MINBLOCKS 4  // resident blocks per SM the register allocation must allow (x TILE_ROWS = 16 warps)
 #endif
 constexpr int SCREEN2_TILE_ROWS = SR_SCREEN2_TILE_ROWS;
 
