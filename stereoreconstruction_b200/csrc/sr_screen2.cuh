@@ -44,6 +44,9 @@ namespace sr {
 #ifndef SR_SCREEN2_ABL
 #define SR_SCREEN2_ABL 0  // 1-4: timing ablations of the label loop (wrong results; profiling only)
 #endif
+#ifndef SR_SCREEN2_STAGE
+#define SR_SCREEN2_STAGE 0  // 1: the chunk's neighbour band staged in shared memory by bulk async copies (TMA engine), windows by LDS
+#endif
 #ifndef SR_SCREEN2_LV
 #define SR_SCREEN2_LV 1  // NL = 2: FFMA2 vectorised across the two labels (scalar weight operand) instead of two taps
 #endif
@@ -67,8 +70,14 @@ constexpr float SCREEN_EPS_MAX = 5e-3f;    // one-pass form: a wider error bar m
 constexpr float SCREEN_SKIP = -2.0f;       // "no value": below every possible lower bound
 
 // Shared memory of one screening warp.
+constexpr int STAGE_BW = 64, STAGE_BH = 16;  // staged band: floats per row (multiple of 4), rows
 template <bool STATS>
-struct Screen2Smem {
+struct alignas(16) Screen2Smem {
+#if SR_SCREEN2_STAGE
+    float box[STAGE_BH][STAGE_BW];       // rows [y0, y0 + bh) x columns [x0, x0 + bw) of the neighbour's FP32 plane
+    unsigned long long mbar;             // completion barrier of the bulk copies
+    unsigned long long pad_;
+#endif
     int32_t tap_ring[2][TAP_CHUNK][32];
     float ub_ring[TAP_CHUNK][32];    // ncc32 + eps of the chunk's labels (SCREEN_FORCE: FP64 decides)
     int32_t q_lab[SCREEN_QCAP][32];  // (neighbour << 16) | label
@@ -101,6 +110,33 @@ __device__ __forceinline__ int32_t lds_b32(unsigned addr) {
     return v;
 }
 __device__ __forceinline__ void sts_f32(unsigned addr, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v)); }
+
+// Bulk asynchronous copy (TMA engine, no tensor map: one contiguous run of bytes) and its mbarrier.
+__device__ __forceinline__ void mbar_init(unsigned mbar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(mbar), "r"(count));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned mbar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(unsigned dst, const void *src, unsigned bytes, unsigned mbar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
+                 "r"(bytes), "r"(mbar)
+                 : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(unsigned mbar, unsigned parity) {
+    unsigned ok;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok)
+                 : "r"(mbar), "r"(parity)
+                 : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ float lds_f32(unsigned addr) {
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
+    return v;
+}
 
 // ---- the rare paths: free functions with by-value arguments, so that the screening warp's register
 // arrays (weights, dl) never have to be addressable ------------------------------------------------
@@ -290,6 +326,10 @@ struct Screener {
     float inv_totWf, k0, k1, e0, e1, lower32;
     float pre_sdl_n, pre_inv_n, pre_E;  // pre-screen: sum_A dl / n_A, 1 / n_A, centred energy of dl on A
     int n_prerej, n_prebad;              // STATS only
+    // SR_SCREEN2_STAGE: the staged band of this chunk (warp-uniform)
+    unsigned box_addr, stage_phase;
+    int box_x0, box_y0;
+    bool use_box;
     int qn, my_win_w, first_pid;
     unsigned pend;
     bool alive;
@@ -408,6 +448,14 @@ struct Screener {
         pend = 0u;
         lower32 = (float)a.ncc_threshold - 1e-6f;
         n_forced = n_screened = n_prerej = n_prebad = 0;
+        use_box = false;
+        stage_phase = 0u;
+        box_addr = 0u;
+        box_x0 = box_y0 = 0;
+#if SR_SCREEN2_STAGE
+        box_addr = (unsigned)__cvta_generic_to_shared(&sm.box[0][0]);
+        if (lane == 0) mbar_init((unsigned)__cvta_generic_to_shared(&sm.mbar), 1u);
+#endif
         if (STATS && alive && all_slow && a.stats) atomicAdd(a.stats + 4, 1ull);
         __syncwarp();
     }
@@ -726,6 +774,92 @@ struct Screener {
         }
     }
 
+#if SR_SCREEN2_STAGE
+    // north_star stage (1): "neighbour views staged in shared memory via TMA".  The warp's interior taps of a
+    // chunk span a band of the neighbour image; its bounding box (+ the window radius) is copied row by row
+    // with cp.async.bulk (the TMA engine; a row is one contiguous run, so no tensor map is needed), completion
+    // on an mbarrier, and the windows are read with LDS at immediate offsets.  A band that does not fit
+    // STAGE_BH x STAGE_BW falls back to the global loads for that chunk.
+    __device__ __forceinline__ void stage_chunk(const float *__restrict__ gplane, unsigned ra, int nl) {
+        const int fp = PITCH ? PITCH : a.pitch_f;
+        int xmin = 1 << 20, xmax = -1, ymin = 1 << 20, ymax = -1;
+#pragma unroll 4
+        for (int l = 0; l < nl; ++l) {
+            const int32_t tap = lds_b32(ra + 128u * l);
+            const int tx = tap & 0xffff, ty = (int)((uint32_t)tap >> 16);
+            if ((unsigned)(tx - R) < (unsigned)my_win_w && (unsigned)(ty - R) < (unsigned)a.win_h) {
+                xmin = min(xmin, tx);
+                xmax = max(xmax, tx);
+                ymin = min(ymin, ty);
+                ymax = max(ymax, ty);
+            }
+        }
+        xmin = __reduce_min_sync(FULL, xmin);
+        xmax = __reduce_max_sync(FULL, xmax);
+        ymin = __reduce_min_sync(FULL, ymin);
+        ymax = __reduce_max_sync(FULL, ymax);
+        use_box = false;
+        if (xmax < 0) return;
+        const int x0 = (xmin - R) & ~3, y0 = ymin - R;
+        const int bw = min(((xmax + R + 1 - x0) + 3) & ~3, fp - x0), bh = ymax + R + 1 - y0;
+        if (xmax + R + 1 - x0 > bw || bw > STAGE_BW || bh > STAGE_BH) return;
+        const unsigned mbar = (unsigned)__cvta_generic_to_shared(&sm.mbar);
+        // the box was last read through the generic proxy, the copies write it through the async proxy
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        if (lane == 0) mbar_expect_tx(mbar, (unsigned)(bh * bw * 4));
+        __syncwarp();
+        if (lane < bh) bulk_g2s(box_addr + (unsigned)(lane * STAGE_BW * 4), gplane + ((size_t)(y0 + lane) * fp + x0), (unsigned)(bw * 4), mbar);
+        while (!mbar_try_wait(mbar, stage_phase)) {
+        }
+        stage_phase ^= 1u;
+        use_box = true;
+        box_x0 = x0;
+        box_y0 = y0;
+    }
+    __device__ __forceinline__ void load_window_box(unsigned addr, float (&g)[WN]) const {
+#pragma unroll
+        for (int i = 0; i < WN; ++i) {
+            const int k = screen2_slot_tap<R>(i);
+            g[i] = lds_f32(addr + (unsigned)(((k / WS - R) * STAGE_BW + (k % WS - R)) * 4));
+        }
+    }
+    // labels<NL> with the windows read from the staged band
+    template <int NL>
+    __device__ __forceinline__ void labels_box(unsigned ra, unsigned ca, unsigned bit, int l) {
+        int32_t tap[NL];
+        unsigned addr[NL];
+        bool interior[NL], any = false;
+#pragma unroll
+        for (int n = 0; n < NL; ++n) {
+            tap[n] = lds_b32(ra + 128u * n);
+            const int tx = tap[n] & 0xffff, ty = (int)((uint32_t)tap[n] >> 16);
+            interior[n] = (unsigned)(tx - R) < (unsigned)my_win_w && (unsigned)(ty - R) < (unsigned)a.win_h;
+            const int off = interior[n] ? (ty - box_y0) * STAGE_BW + (tx - box_x0) : R * STAGE_BW + R;
+            addr[n] = box_addr + (unsigned)(off * 4);
+            any = any || interior[n];
+        }
+        float ub[NL], lb[NL], eps[NL];
+#pragma unroll
+        for (int n = 0; n < NL; ++n) ub[n] = lb[n] = eps[n] = 0.0f;
+        if (any) {
+            float g[NL][WN];
+#pragma unroll
+            for (int n = 0; n < NL; ++n) load_window_box(addr[n], g[n]);
+            if (NL == 2 && ONEPASS && SR_SCREEN2_LV) {
+                float ub2[2], lb2[2], ep2[2];
+                eval_window2(g[0], g[NL - 1], ub2, lb2, ep2);
+#pragma unroll
+                for (int n = 0; n < NL; ++n) ub[n] = ub2[n], lb[n] = lb2[n], eps[n] = ep2[n];
+            } else {
+#pragma unroll
+                for (int n = 0; n < NL; ++n) eval_window(g[n], ub[n], lb[n], eps[n]);
+            }
+        }
+#pragma unroll
+        for (int n = 0; n < NL; ++n) commit_label(interior[n], tap[n], ub[n], lb[n], eps[n], ca + 128u * n, bit << n, l + n);
+    }
+#endif
+
     // NL consecutive labels of a chunk: ring entries at shared addresses ra, ra + 128, ...; `bit` = mask bit
     // of the first.  A lane with at least one interior label evaluates all NL (the others at a safe address,
     // result discarded).
@@ -760,6 +894,15 @@ struct Screener {
             unsigned bit = 1u;
             constexpr int NL = SR_SCREEN2_NL;
             int l = 0;
+#if SR_SCREEN2_STAGE
+            stage_chunk(gplane, ra, nl);
+            if (use_box) {
+#pragma unroll 1
+                for (; l + NL <= nl; l += NL, ra += 128u * NL, ca += 128u * NL, bit <<= NL) labels_box<NL>(ra, ca, bit, l);
+#pragma unroll 1
+                for (; l < nl; ++l, ra += 128u, ca += 128u, bit <<= 1) labels_box<1>(ra, ca, bit, l);
+            }
+#endif
 #pragma unroll 1
             for (; l + NL <= nl; l += NL, ra += 128u * NL, ca += 128u * NL, bit <<= NL) labels<NL>(gplane, ra, ca, bit, l);
             if (NL > 1) {
