@@ -631,7 +631,9 @@ def main():
             cpu["parity"] = {
                 "pixels": int(mism.size), "index_mismatch_rate": float(mism.mean()),
                 "depth_equal_where_index_equal": bool(same_maps(gd, o["depth"])[~mism].all()),
-                "max_rel_cost_diff": float(rel.max()) if rel.size else None, "labelled_fraction": float(lab.mean()),
+                "max_rel_cost_diff": float(rel.max()) if rel.size else None,
+                "max_abs_cost_diff": float(np.abs(gb[lab] - o["best"][lab]).max()) if rel.size else None,  # (two-view costs can be ~0)
+                "labelled_fraction": float(lab.mean()),
             }
         # ... and the reference's own MultiViewStereo (oracle/_ref, when the prebuilt library is there) on a band
         # of the same view: its live curve formulation, timed beside the port, and the checker of the GPU's curve

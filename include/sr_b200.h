@@ -144,8 +144,10 @@ int sr_get_build_stats(sr_ctx *ctx, uint64_t *out4);
  * one mask byte per pixel (255 == WHITE, anything else is not).  mask8[i] may be
  * NULL (all WHITE).  rgba8[i] may be NULL for a view this context only needs the
  * camera of (multi-GPU: a view another rank computes and that is no neighbour of this
- * rank's views); using such a view as reference or neighbour is an error.  Copies to the device (async on the context stream from pinned
- * staging) and runs the per-view preparation kernels. */
+ * rank's views); using such a view as reference or neighbour is an error.  Copies straight from the caller's
+ * buffers to the device on the context stream (cudaMemcpyAsync: truly asynchronous when the caller's memory is
+ * pinned, staged by the driver when it is pageable; the buffers may be reused when the call returns only in the
+ * pageable case — keep pinned buffers alive until sr_synchronize) and runs the per-view preparation kernels. */
 int sr_set_views(sr_ctx *ctx, int num_views, const sr_camera *cams,
                  const uint8_t *const *rgba8, const uint8_t *const *mask8, int w, int h);
 int sr_set_params(sr_ctx *ctx, const sr_params *p);

@@ -1,3 +1,7 @@
-timeout 1500 python -m pytest tests -m gpu -x -q > gpurun_out/c_pytest.log 2>&1; echo "pytest rc=$?"; tail -3 gpurun_out/c_pytest.log
-PYTHONPATH=. python tools/curve_time.py 2>&1 | tail -4
-SR_CURVE_INTERP=0 PYTHONPATH=. python tools/curve_time.py 2>&1 | tail -4 | head -2
+timeout 1500 python bench.py --workload cfg3 --steps 1 --warmup 1 > gpurun_out/r2_bench_cfg3.json 2> gpurun_out/r2_bench_cfg3.err; echo rc=$?
+python - <<'PY'
+import json
+d=json.loads([l for l in open('gpurun_out/r2_bench_cfg3.json') if l.startswith('{')][-1])
+print('cfg3 value',round(d['value'],1),'e2e',round(d['e2e']['value'],1),'ms/step',round(d['ms_per_step'],1))
+print(d['cpu_baseline']); print(d['like_for_like'])
+PY
