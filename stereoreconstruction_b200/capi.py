@@ -18,8 +18,7 @@ _LIB = None
 NVCC_FLAGS = ["-std=c++17", "-O3", "-fmad=false", "-DSR_FEW_RADII", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
               "--shared", "-Xcompiler", "-fPIC"]
 SOURCES = ["csrc/sr_capi.cu"]
-HEADERS = ["csrc/sr_geometry.cuh", "csrc/sr_kernels.cuh", "csrc/sr_match_dispatch.cuh", "csrc/sr_match_screen.cuh", "csrc/sr_build_refr.cuh", "csrc/sr_curve.cuh",
-           "../include/sr_b200.h"]
+HEADERS = ["csrc/" + f for f in sorted(os.listdir(os.path.join(_PKG, "csrc"))) if f.endswith(".cuh")] + ["../include/sr_b200.h"]
 
 EXPORTS = [
     "sr_ctx_create", "sr_ctx_destroy", "sr_last_error", "sr_request_cancel", "sr_clear_cancel",
