@@ -39,6 +39,19 @@ struct BuildRefrArgs {
                                  // interpolated labels whose tap differs from the exact projection (must be 0)
 };
 
+// fmin(fmax(v, lo), hi) with the same results (a NaN comes out as lo) as two compare+select pairs.
+// max.f64/min.f64 expand to 7 instructions each on sm_100a (NaN canonicalisation), and the compiler
+// turns the C++ `v > lo ? v : lo` back into max.f64: hence PTX.  3 instructions per bound.
+__device__ __forceinline__ double clamp_sel(double v, double lo, double hi) {
+    double r;
+    asm("{\n\t.reg .pred p;\n\t"
+        "setp.gt.f64 p, %1, %2;\n\tselp.f64 %0, %1, %2, p;\n\t"
+        "setp.lt.f64 p, %0, %3;\n\tselp.f64 %0, %0, %3, p;\n\t}"
+        : "=&d"(r)
+        : "d"(v), "d"(lo), "d"(hi));
+    return r;
+}
+
 __device__ __forceinline__ double rcp_approx(double a) {  // ~2^-20 relative (MUFU.RCP64H)
     double r;
     asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(a));
@@ -67,6 +80,10 @@ struct RefrProjector {
         const double nC = dot(nrm, ld3(C_)), npn = dot(nrm, prin), nn = dot(nrm, nrm), ns = dot(nrm, src);
         tA = npn * nn * inv_nd;
         tB = (nC * nn - ns) * inv_nd;
+        if (!ray_ok) {  // a ray parallel to the depth planes has no point at any label: t = -1 fails the test in project()
+            tA = 0.0;
+            tB = -1.0;
+        }
         // camera-local ray and its decomposition about the interface normal
         const d3 Ls = fmul3(nbr.R, src) + ld3(nbr.t), Ld = fmul3(nbr.R, dir);
         const d3 N = ld3(nbr.plane_n);
@@ -133,14 +150,14 @@ struct RefrProjector {
             n2_ = n2;
         }
         const double t = fma(depth_table[d], tA, tB);
-        if (!ray_ok || t < 1e-10) return false;
+        if (t < 1e-10) return false;  // (also every label of a ray with !ray_ok, see init)
         const d3 radv = faxpy(t, R1, R0);
         const double rr = fdot(radv, radv);
         if (!(rr > 0.0)) return false;  // on the axis dir = radv/r is NaN in the reference: no root is accepted
         const double av = fma(t, a1, a0);
         const double h = fabs(av) - pd_, hh = h * h;
         double rho = (rho_guess >= 0.0) ? rho_guess : n1_ * fabs(pd_) / (fabs(h) + n1_ * fabs(pd_) + 1e-300);
-        rho = fmin(fmax(rho, 0.0), 1.0);
+        rho = clamp_sel(rho, 0.0, 1.0);
         bool conv = false;
 #pragma unroll 1
         for (int it = 0; it < 8; ++it) {
@@ -157,7 +174,7 @@ struct RefrProjector {
                 conv = true;
                 break;
             }
-            rho = fmin(fmax(rho, 0.0), 1.0);
+            rho = clamp_sel(rho, 0.0, 1.0);
         }
         if (!conv || !(rho >= 0.0 && rho <= 1.0)) {
             const double r = sqrt(rr);
@@ -250,8 +267,8 @@ struct BuildSweep {
 // MVS: the multi-view tap rule (tap inside the image and WHITE in the neighbour's mask);
 // HAS_MASK: the neighbour has a mask plane (a.nbr_mask != null).  Compile-time so that the other
 // variant's clamps, mask address arithmetic and loads do not occupy (predicated-off) issue slots.
-// Labels [d0, d1) of reference pixel (x, y), d0 a multiple of BUILD_STRIDE; sink(d, tap) receives them
-// in increasing d.
+// Labels [d0, d1) of reference pixel (x, y), d0 a multiple of BUILD_STRIDE; sink(d, tap) receives every
+// one of them exactly once, in increasing d.
 template <bool MVS, bool HAS_MASK, bool UC, class Sink>
 __device__ __forceinline__ void build_refr_sweep(const BuildSweep &a, int x, int y, int d0, int d1, Sink sink) {
     const size_t pix = (size_t)y * a.w + x;
@@ -282,19 +299,21 @@ __device__ __forceinline__ void build_refr_sweep(const BuildSweep &a, int x, int
     constexpr int S = BUILD_STRIDE;
     // anchor window: labels (k-1)S, kS, (k+1)S, (k+2)S for the interval [kS, (k+1)S)
     double au[4], av_[4], ar[4];
-    bool aok[4], asane[4];
+    unsigned aok = 0, asane = 0;  // bit = slot: the anchor projected / is usable as a node of the cubic
     auto anchor = [&](int slot, int d, double guess) {
-        aok[slot] = false;
+        bool ok = false;
         au[slot] = av_[slot] = ar[slot] = 0.0;
-        if (d >= 0 && d < D) aok[slot] = project_label(d, guess, au[slot], av_[slot], ar[slot]);
+        if (d >= 0 && d < D) ok = project_label(d, guess, au[slot], av_[slot], ar[slot]);
         // an anchor far outside any image (a projection near the camera plane) is not interpolated
         // through: the labels around it are projected exactly, and the cubic never leaves 2^31
-        asane[slot] = aok[slot] && fabs(au[slot]) + fabs(av_[slot]) < 1.0e6;
+        const bool sane = ok && fabs(au[slot]) + fabs(av_[slot]) < 1.0e6;
+        aok = (aok & ~(1u << slot)) | ((unsigned)ok << slot);
+        asane = (asane & ~(1u << slot)) | ((unsigned)sane << slot);
     };
     const int kfirst = d0 / S;
     anchor(0, (kfirst - 1) * S, -1.0);
-    anchor(1, kfirst * S, aok[0] ? ar[0] : -1.0);
-    anchor(2, (kfirst + 1) * S, (aok[0] && aok[1]) ? fma(2.0, ar[1], -ar[0]) : (aok[1] ? ar[1] : -1.0));
+    anchor(1, kfirst * S, (aok & 1) ? ar[0] : -1.0);
+    anchor(2, (kfirst + 1) * S, ((aok & 3) == 3) ? fma(2.0, ar[1], -ar[0]) : ((aok & 2) ? ar[1] : -1.0));
     // Lagrange weights of the cubic through nodes -1,0,1,2 at x = s/S and of its top term L2(x)
     double lw[S][4], l2[S];
 #pragma unroll
@@ -313,13 +332,13 @@ __device__ __forceinline__ void build_refr_sweep(const BuildSweep &a, int x, int
     for (int kk = kfirst; kk * S < d1; ++kk) {
         {
             double g = -1.0;
-            if (aok[0] && aok[1] && aok[2]) g = fma(3.0, ar[2] - ar[1], ar[0]);
-            else if (aok[1] && aok[2]) g = fma(2.0, ar[2], -ar[1]);
-            else if (aok[2]) g = ar[2];
+            if ((aok & 7) == 7) g = fma(3.0, ar[2] - ar[1], ar[0]);
+            else if ((aok & 6) == 6) g = fma(2.0, ar[2], -ar[1]);
+            else if (aok & 4) g = ar[2];
             anchor(3, (kk + 2) * S, g);
         }
         const int db = kk * S;
-        const bool full = asane[0] && asane[1] && asane[2] && asane[3];
+        const bool full = (asane & 15) == 15;
         double d3u = 0.0, d3v = 0.0, d4u = 0.0, d4v = 0.0;
         if (full) {
             const double su = (au[3] - au[0]) - 3.0 * (au[2] - au[1]);  // signed third differences
@@ -341,9 +360,9 @@ __device__ __forceinline__ void build_refr_sweep(const BuildSweep &a, int x, int
         unsigned need_exact = 0;  // bit s: label must be projected exactly
         {
             double du, dv;
-            tx[0] = trunc_magic(fmin(fmax(au[1], -CL), CL), du);
-            ty[0] = trunc_magic(fmin(fmax(av_[1], -CL), CL), dv);
-            ok[0] = aok[1];
+            tx[0] = trunc_magic(clamp_sel(au[1], -CL, CL), du);
+            ty[0] = trunc_magic(clamp_sel(av_[1], -CL, CL), dv);
+            ok[0] = (aok & 2) != 0;
         }
 #pragma unroll
         for (int s = 1; s < S; ++s) {
@@ -368,7 +387,7 @@ __device__ __forceinline__ void build_refr_sweep(const BuildSweep &a, int x, int
                 double Ue, Ve, re, du;
                 const bool oke = project_label(db + s, fma((double)s / S, ar[2] - ar[1], ar[1]), Ue, Ve, re);
                 atomicAdd(a.check + 0, 1ull);
-                if (!oke || trunc_magic(fmin(fmax(Ue, -CL), CL), du) != tx[s] || trunc_magic(fmin(fmax(Ve, -CL), CL), du) != ty[s])
+                if (!oke || trunc_magic(clamp_sel(Ue, -CL, CL), du) != tx[s] || trunc_magic(clamp_sel(Ve, -CL, CL), du) != ty[s])
                     atomicAdd(a.check + 2, 1ull);
             }
         }
@@ -378,10 +397,10 @@ __device__ __forceinline__ void build_refr_sweep(const BuildSweep &a, int x, int
                 if (need_exact & (1u << s)) {
                     double U = 0.0, V = 0.0, rho, du;
                     double g = -1.0;
-                    if (aok[1] && aok[2]) g = fma((double)s / S, ar[2] - ar[1], ar[1]);
+                    if ((aok & 6) == 6) g = fma((double)s / S, ar[2] - ar[1], ar[1]);
                     ok[s] = project_label(db + s, g, U, V, rho);
-                    tx[s] = trunc_magic(fmin(fmax(U, -CL), CL), du);
-                    ty[s] = trunc_magic(fmin(fmax(V, -CL), CL), du);
+                    tx[s] = trunc_magic(clamp_sel(U, -CL, CL), du);
+                    ty[s] = trunc_magic(clamp_sel(V, -CL, CL), du);
                 }
             }
         }
@@ -417,9 +436,9 @@ __device__ __forceinline__ void build_refr_sweep(const BuildSweep &a, int x, int
             au[i] = au[i + 1];
             av_[i] = av_[i + 1];
             ar[i] = ar[i + 1];
-            aok[i] = aok[i + 1];
-            asane[i] = asane[i + 1];
         }
+        aok >>= 1;
+        asane >>= 1;
     }
 }
 
@@ -455,8 +474,12 @@ __global__ void SR_BUILD_BOUNDS build_refr_kernel(const __grid_constant__ BuildR
     const size_t plane = (size_t)a.rows * a.w;
     const int d0 = blockIdx.y * a.d_chunk;  // d_chunk is a multiple of BUILD_STRIDE
     const int d1 = min(d0 + a.d_chunk, a.D);
-    int32_t *__restrict__ out = a.taps + pid;
-    build_refr_sweep<MVS, HAS_MASK, false>(build_sweep_of(a), x, y, d0, d1, [&](int d, int32_t tap) { out[(size_t)d * plane] = tap; });
+    // the sweep hands over labels d0, d0+1, ... in order: a running pointer instead of a 64-bit multiply per label
+    build_refr_sweep<MVS, HAS_MASK, false>(build_sweep_of(a), x, y, d0, d1,
+                                           [p = a.taps + pid + (size_t)d0 * plane, plane](int, int32_t tap) mutable {
+                                               *p = tap;
+                                               p += plane;
+                                           });
 }
 
 }  // namespace sr

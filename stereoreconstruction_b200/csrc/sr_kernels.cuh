@@ -256,6 +256,15 @@ __global__ void __launch_bounds__(128) weights_adaptive_kernel(const WeightArgs 
 // SMEM: the grid lives in shared memory ([cell][thread], conflict-free) during the sweeps and is
 // written to W once at the end — used when (2R+1)^2 * 128 doubles fit (R <= 2); otherwise the grid
 // is the thread's column of W itself.
+// fmin(a, b) for operands that are never NaN (distances: finite or +INF, never negative zero) as
+// compare + select: min.f64 expands to 7 instructions on sm_100a (NaN canonicalisation), and the
+// compiler turns `b < a ? b : a` back into min.f64, hence PTX.
+__device__ __forceinline__ double min_sel(double a, double b) {
+    double r;
+    asm("{\n\t.reg .pred p;\n\tsetp.lt.f64 p, %2, %1;\n\tselp.f64 %0, %2, %1, p;\n\t}" : "=d"(r) : "d"(a), "d"(b));
+    return r;
+}
+
 template <bool SMEM>
 __global__ void __launch_bounds__(128) weights_geodesic_kernel(const WeightArgs a) {
     extern __shared__ double grid_s[];
@@ -288,11 +297,11 @@ __global__ void __launch_bounds__(128) weights_geodesic_kernel(const WeightArgs 
                 const size_t k = (size_t)((y + R) * WS + (x + R));
                 double wt = c[k * npix];
                 if (y > -R && py >= 1) {  // row above (inside the image): edges stored at the upper pixel
-                    if (x > -R && px >= 1) wt = fmin(wt, c[(k - WS - 1) * npix] + eSE[p - w - 1]);
-                    wt = fmin(wt, c[(k - WS) * npix] + eS[p - w]);
-                    if (x < R && px + 1 < w) wt = fmin(wt, c[(k - WS + 1) * npix] + eSW[p - w + 1]);
+                    if (x > -R && px >= 1) wt = min_sel(wt, c[(k - WS - 1) * npix] + eSE[p - w - 1]);
+                    wt = min_sel(wt, c[(k - WS) * npix] + eS[p - w]);
+                    if (x < R && px + 1 < w) wt = min_sel(wt, c[(k - WS + 1) * npix] + eSW[p - w + 1]);
                 }
-                if (x > -R && px >= 1) wt = fmin(wt, c[(k - 1) * npix] + eE[p - 1]);
+                if (x > -R && px >= 1) wt = min_sel(wt, c[(k - 1) * npix] + eE[p - 1]);
                 c[k * npix] = wt;
             }
         }
@@ -309,11 +318,11 @@ __global__ void __launch_bounds__(128) weights_geodesic_kernel(const WeightArgs 
                 const size_t k = (size_t)((y + R) * WS + (x + R));
                 double wt = c[k * npix];
                 if (y < R) {  // row below: edges stored at this pixel
-                    if (x > -R) wt = fmin(wt, c[(k + WS - 1) * npix] + eSW[p]);
-                    wt = fmin(wt, c[(k + WS) * npix] + eS[p]);
-                    if (x < R) wt = fmin(wt, c[(k + WS + 1) * npix] + eSE[p]);
+                    if (x > -R) wt = min_sel(wt, c[(k + WS - 1) * npix] + eSW[p]);
+                    wt = min_sel(wt, c[(k + WS) * npix] + eS[p]);
+                    if (x < R) wt = min_sel(wt, c[(k + WS + 1) * npix] + eSE[p]);
                 }
-                if (x < R) wt = fmin(wt, c[(k + 1) * npix] + eE[p]);
+                if (x < R) wt = min_sel(wt, c[(k + 1) * npix] + eE[p]);
                 c[k * npix] = wt;
             }
         }
