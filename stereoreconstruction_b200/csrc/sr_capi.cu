@@ -229,10 +229,15 @@ int ensure_scratch(sr_ctx *ctx, size_t bytes) {
 
 void launch_geodesic(const WeightArgs &wa, unsigned gx, cudaStream_t st) {
     const size_t cells = (size_t)(2 * wa.radius + 1) * (2 * wa.radius + 1);
-    if (cells * 128 * sizeof(double) <= 48 * 1024)
-        weights_geodesic_kernel<true><<<gx, 128, cells * 128 * sizeof(double), st>>>(wa);
+    const size_t smem = cells * 128 * sizeof(double);
+    if (wa.radius == 2)  // MultiViewStereo's window (multiviewstereo.cpp:91): sweeps unrolled
+        weights_geodesic_kernel<true, 2><<<gx, 128, smem, st>>>(wa);
+    else if (wa.radius == 1)
+        weights_geodesic_kernel<true, 1><<<gx, 128, smem, st>>>(wa);
+    else if (smem <= 48 * 1024)
+        weights_geodesic_kernel<true, 0><<<gx, 128, smem, st>>>(wa);
     else
-        weights_geodesic_kernel<false><<<gx, 128, 0, st>>>(wa);
+        weights_geodesic_kernel<false, 0><<<gx, 128, 0, st>>>(wa);
 }
 
 double depth_from_label(const sr_params &p, int label) {

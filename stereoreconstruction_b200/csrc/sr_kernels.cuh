@@ -265,10 +265,16 @@ __device__ __forceinline__ double min_sel(double a, double b) {
     return r;
 }
 
-template <bool SMEM>
-__global__ void __launch_bounds__(128) weights_geodesic_kernel(const WeightArgs a) {
+// RT > 0: the radius as a compile-time constant (the sweeps are unrolled: every cell index, shared-memory
+// offset and window-edge test folds away); RT = 0: a.radius.  Same updates in the same order either way.
+#ifndef SR_GEO_MINBLOCKS  // resident blocks per SM the register allocation must allow (6: 80 registers, no spills;
+#define SR_GEO_MINBLOCKS 6  // unbounded the unrolled sweeps take 96, bounded to 8 blocks they spill)
+#endif
+#define SR_GEO_BOUNDS __launch_bounds__(128, SR_GEO_MINBLOCKS)
+template <bool SMEM, int RT>
+__global__ void SR_GEO_BOUNDS weights_geodesic_kernel(const WeightArgs a) {
     extern __shared__ double grid_s[];
-    const int R = a.radius, WS = 2 * R + 1;
+    const int R = RT > 0 ? RT : a.radius, WS = 2 * R + 1;
     const int pid = blockIdx.x * blockDim.x + threadIdx.x;
     size_t npix;
     int cx, cy;
@@ -282,49 +288,56 @@ __global__ void __launch_bounds__(128) weights_geodesic_kernel(const WeightArgs 
     const size_t n = (size_t)a.w * a.h;
     const double *eE = a.edges, *eS = a.edges + n, *eSE = a.edges + 2 * n, *eSW = a.edges + 3 * n;
     const int w = a.w, h = a.h;
+    // forward pass: neighbours (-1,-1), (0,-1), (1,-1), (-1,0)
+    auto forward = [&](int y, int x) {
+        const int py = cy + y, px = cx + x;
+        if (py < 0 || py >= h || px < 0 || px >= w) return;
+        const size_t p = (size_t)py * w + px;
+        const int k = (y + R) * WS + (x + R);
+        double wt = c[(size_t)k * npix];
+        if (y > -R && py >= 1) {  // row above (inside the image): edges stored at the upper pixel
+            if (x > -R && px >= 1) wt = min_sel(wt, c[(size_t)(k - WS - 1) * npix] + eSE[p - w - 1]);
+            wt = min_sel(wt, c[(size_t)(k - WS) * npix] + eS[p - w]);
+            if (x < R && px + 1 < w) wt = min_sel(wt, c[(size_t)(k - WS + 1) * npix] + eSW[p - w + 1]);
+        }
+        if (x > -R && px >= 1) wt = min_sel(wt, c[(size_t)(k - 1) * npix] + eE[p - 1]);
+        c[(size_t)k * npix] = wt;
+    };
+    // backward pass: neighbours (-1,1), (0,1), (1,1), (1,0)
+    auto backward = [&](int y, int x) {
+        const int py = cy + y, px = cx + x;
+        if (py < 0 || py >= h || px < 0 || px >= w) return;
+        const size_t p = (size_t)py * w + px;
+        const int k = (y + R) * WS + (x + R);
+        double wt = c[(size_t)k * npix];
+        if (y < R) {  // row below: edges stored at this pixel
+            if (x > -R) wt = min_sel(wt, c[(size_t)(k + WS - 1) * npix] + eSW[p]);
+            wt = min_sel(wt, c[(size_t)(k + WS) * npix] + eS[p]);
+            if (x < R) wt = min_sel(wt, c[(size_t)(k + WS + 1) * npix] + eSE[p]);
+        }
+        if (x < R) wt = min_sel(wt, c[(size_t)(k + 1) * npix] + eE[p]);
+        c[(size_t)k * npix] = wt;
+    };
 #pragma unroll 1
     for (int iter = 0; iter < 3; ++iter) {
-        // forward pass: neighbours (-1,-1), (0,-1), (1,-1), (-1,0)
+        if (RT > 0) {
+#pragma unroll
+            for (int y = -RT; y <= RT; ++y)
+#pragma unroll
+                for (int x = -RT; x <= RT; ++x) forward(y, x);
+#pragma unroll
+            for (int y = RT; y >= -RT; --y)
+#pragma unroll
+                for (int x = RT; x >= -RT; --x) backward(y, x);
+        } else {
 #pragma unroll 1
-        for (int y = -R; y <= R; ++y) {
-            const int py = cy + y;
-            if (py < 0 || py >= h) continue;
+            for (int y = -R; y <= R; ++y)
 #pragma unroll 1
-            for (int x = -R; x <= R; ++x) {
-                const int px = cx + x;
-                if (px < 0 || px >= w) continue;
-                const size_t p = (size_t)py * w + px;
-                const size_t k = (size_t)((y + R) * WS + (x + R));
-                double wt = c[k * npix];
-                if (y > -R && py >= 1) {  // row above (inside the image): edges stored at the upper pixel
-                    if (x > -R && px >= 1) wt = min_sel(wt, c[(k - WS - 1) * npix] + eSE[p - w - 1]);
-                    wt = min_sel(wt, c[(k - WS) * npix] + eS[p - w]);
-                    if (x < R && px + 1 < w) wt = min_sel(wt, c[(k - WS + 1) * npix] + eSW[p - w + 1]);
-                }
-                if (x > -R && px >= 1) wt = min_sel(wt, c[(k - 1) * npix] + eE[p - 1]);
-                c[k * npix] = wt;
-            }
-        }
-        // backward pass: neighbours (-1,1), (0,1), (1,1), (1,0)
+                for (int x = -R; x <= R; ++x) forward(y, x);
 #pragma unroll 1
-        for (int y = R; y >= -R; --y) {
-            const int py = cy + y;
-            if (py < 0 || py >= h) continue;
+            for (int y = R; y >= -R; --y)
 #pragma unroll 1
-            for (int x = R; x >= -R; --x) {
-                const int px = cx + x;
-                if (px < 0 || px >= w) continue;
-                const size_t p = (size_t)py * w + px;
-                const size_t k = (size_t)((y + R) * WS + (x + R));
-                double wt = c[k * npix];
-                if (y < R) {  // row below: edges stored at this pixel
-                    if (x > -R) wt = min_sel(wt, c[(k + WS - 1) * npix] + eSW[p]);
-                    wt = min_sel(wt, c[(k + WS) * npix] + eS[p]);
-                    if (x < R) wt = min_sel(wt, c[(k + WS + 1) * npix] + eSE[p]);
-                }
-                if (x < R) wt = min_sel(wt, c[(k + 1) * npix] + eE[p]);
-                c[k * npix] = wt;
-            }
+                for (int x = R; x >= -R; --x) backward(y, x);
         }
     }
     for (int k = 0; k < WS * WS; ++k) out[(size_t)k * out_stride] = exp(-c[(size_t)k * npix] / 50.0);
