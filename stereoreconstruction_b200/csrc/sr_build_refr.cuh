@@ -158,23 +158,51 @@ struct RefrProjector {
         const double h = fabs(av) - pd_, hh = h * h;
         double rho = (rho_guess >= 0.0) ? rho_guess : n1_ * fabs(pd_) / (fabs(h) + n1_ * fabs(pd_) + 1e-300);
         rho = clamp_sel(rho, 0.0, 1.0);
+        // One Newton step on G: G/2 and G'/2 = rho*B + n^2 s A - rho s rr (rho + n^2 s) at rho; returns the
+        // step and leaves the reciprocal of G'/2 in rinv.
+        double rinv = 0.0;
+        auto half_G = [&](double rho_, double &A, double &B, double &s) {
+            s = 1.0 - rho_;
+            const double p2 = rho_ * rho_, s2 = s * s;
+            A = fma(p2, rr, dd_);
+            B = fma(s2, rr, hh);
+            return 0.5 * fma(p2, B, -((n2_ * s2) * A));
+        };
+        auto newton_step = [&](double rho_) {
+            double A, B, s;
+            const double hG = half_G(rho_, A, B, s);
+            const double u = fma(n2_, s, rho_);
+            const double g2 = fma(n2_ * s, A, fma(rho_, B, -(((rho_ * s) * rr) * u)));
+            rinv = rcp_approx(g2);
+            return hG * rinv;
+        };
         bool conv = false;
-#pragma unroll 1
-        for (int it = 0; it < 8; ++it) {
-            const double s = 1.0 - rho;
-            const double p2 = rho * rho, s2 = s * s;
-            const double A = fma(p2, rr, dd_), B = fma(s2, rr, hh);
-            const double G = fma(p2, B, -((n2_ * s2) * A));
-            const double u = fma(n2_, s, rho);
-            // G'/2 = rho*B + n^2 s A - rho s rr (rho + n^2 s)
-            const double g2 = fma(n2_ * s, A, fma(rho, B, -(((rho * s) * rr) * u)));
-            const double step = (0.5 * G) * rcp_approx(g2);
+        double step = newton_step(rho);
+        rho -= step;
+        if (fabs(step) <= 3e-8) {
+            conv = true;
+#if SR_BUILD_CHORD
+        } else if (fabs(step) <= 1e-5) {
+            // The usual case between anchors (the extrapolated start is ~1e-6 off): the error is now
+            // ~1e-12, and a chord step with the SAME derivative takes it to ~1e-12 * (|step| + 2^-20),
+            // below the rounding of rho, for half the FP64 instructions of a second full step.
+            double A, B, s;
+            step = half_G(rho, A, B, s) * rinv;
             rho -= step;
-            if (fabs(step) <= 3e-8) {
-                conv = true;
-                break;
+            conv = fabs(step) <= 3e-8;
+#endif
+        }
+        if (!conv) {
+#pragma unroll 1
+            for (int it = 0; it < 7; ++it) {
+                rho = clamp_sel(rho, 0.0, 1.0);
+                step = newton_step(rho);
+                rho -= step;
+                if (fabs(step) <= 3e-8) {
+                    conv = true;
+                    break;
+                }
             }
-            rho = clamp_sel(rho, 0.0, 1.0);
         }
         if (!conv || !(rho >= 0.0 && rho <= 1.0)) {
             const double r = sqrt(rr);
@@ -241,6 +269,12 @@ struct RefrProjector {
 // ~1e-4 px a label falls back with probability ~4e-4.
 #ifndef SR_BUILD_STRIDE
 #define SR_BUILD_STRIDE 4
+#endif
+#ifndef SR_BUILD_CHORD  // second solver step between anchors as a chord step (A/B)
+#define SR_BUILD_CHORD 1
+#endif
+#ifndef SR_BUILD_ONEGUARD  // one guard threshold per interval (the largest L2) instead of one per label (A/B)
+#define SR_BUILD_ONEGUARD 1
 #endif
 constexpr int BUILD_STRIDE = SR_BUILD_STRIDE;
 #ifdef SR_BUILD_MINBLOCKS  // A/B: resident 128-thread blocks per SM the register allocation must allow
@@ -354,6 +388,9 @@ __device__ __forceinline__ void build_refr_sweep(const BuildSweep &a, int x, int
         }
         have_d3 = full;
         const double g0u = fma(0.1, d4u, 1e-6), g0v = fma(0.1, d4v, 1e-6);  // label-independent part of the guard
+#if SR_BUILD_ONEGUARD
+        const double gmaxu = fma(0.0625, d3u, g0u), gmaxv = fma(0.0625, d3v, g0v);  // L2(x) <= L2(1/2) = 1/16
+#endif
         // ---- stage 1: coordinates of the S labels of this interval (branch-free) ----
         int tx[S], ty[S];
         bool ok[S];
@@ -368,11 +405,18 @@ __device__ __forceinline__ void build_refr_sweep(const BuildSweep &a, int x, int
         for (int s = 1; s < S; ++s) {
             const double U = fma(lw[s][0], au[0], fma(lw[s][1], au[1], fma(lw[s][2], au[2], lw[s][3] * au[3])));
             const double V = fma(lw[s][0], av_[0], fma(lw[s][1], av_[1], fma(lw[s][2], av_[2], lw[s][3] * av_[3])));
+            ok[s] = true;
+#if SR_BUILD_ONEGUARD
             double du, dv;
             tx[s] = trunc_magic(U, du);  // |U|,|V| < 2^31 when `full`; otherwise recomputed below
             ty[s] = trunc_magic(V, dv);
-            ok[s] = true;
+            const bool safe = full && du > gmaxu && dv > gmaxv;
+#else
+            double du, dv;
+            tx[s] = trunc_magic(U, du);
+            ty[s] = trunc_magic(V, dv);
             const bool safe = full && du > fma(l2[s], d3u, g0u) && dv > fma(l2[s], d3v, g0v);
+#endif
             if (!safe && db + s < d1) need_exact |= 1u << s;
         }
         // ---- stage 2 (rare): labels too close to a pixel boundary, or without a full stencil ----
