@@ -405,13 +405,7 @@ __device__ __noinline__ double slow_cost(const MatchArgs &a, const double *__res
     if (tx + R < 0 || ty + R < 0 || tx - R >= w || ty - R >= h) return (COST == SR_COST_NCC_MVS) ? 0.0 : 1000.0;
     double mL = 0.0, mR = 0.0, tw = 0.0;
     int cnt = 0;
-#pragma unroll 1
-    for (int k = sub; k < WN; k += G) {
-        const int row = k / WS - R, col = k % WS - R;
-        const int xr = tx + col, yr = ty + row, xl = x + col, yl = y + row;
-        if (xr < 0 || yr < 0 || xr >= w || yr >= h || xl < 0 || yl < 0 || xl >= w || yl >= h) continue;
-        const double gl = a.grayL[(size_t)yl * w + xl], gr = gR[(size_t)yr * w + xr];
-        const double wt = a.W[(size_t)k * npix + pid];
+    auto first = [&](double gl, double gr, double wt) {
         if (gl == gl && gr == gr && wt > 1e-10) {
             if (NCC) {
                 mL += wt * gl;
@@ -421,6 +415,32 @@ __device__ __noinline__ double slow_cost(const MatchArgs &a, const double *__res
             }
             tw += wt;
             ++cnt;
+        }
+    };
+    // One lane per window (G = 1, the thread-per-pixel screen's verifications): the taps with both pixels
+    // inside their images are a sub-rectangle of the window, walked in the reference's row-major order with
+    // running pointers instead of eight bound tests and three 64-bit index products per tap.
+    const int row_lo = max(-R, max(-ty, -y)), row_hi = min(R, min(h - 1 - ty, h - 1 - y));
+    const int col_lo = max(-R, max(-tx, -x)), col_hi = min(R, min(w - 1 - tx, w - 1 - x));
+    auto walk = [&](auto &&body) {
+#pragma unroll 1
+        for (int row = row_lo; row <= row_hi; ++row) {
+            const double *__restrict__ pl = a.grayL + ((size_t)(y + row) * w + (x + col_lo));
+            const double *__restrict__ pr = gR + ((size_t)(ty + row) * w + (tx + col_lo));
+            const double *__restrict__ pw = a.W + ((size_t)((row + R) * WS + (col_lo + R)) * npix + pid);
+#pragma unroll 1
+            for (int col = col_lo; col <= col_hi; ++col, ++pl, ++pr, pw += npix) body(*pl, *pr, *pw);
+        }
+    };
+    if (G == 1) {
+        walk(first);
+    } else {
+#pragma unroll 1
+        for (int k = sub; k < WN; k += G) {
+            const int row = k / WS - R, col = k % WS - R;
+            const int xr = tx + col, yr = ty + row, xl = x + col, yl = y + row;
+            if (xr < 0 || yr < 0 || xr >= w || yr >= h || xl < 0 || yl < 0 || xl >= w || yl >= h) continue;
+            first(a.grayL[(size_t)yl * w + xl], gR[(size_t)yr * w + xr], a.W[(size_t)k * npix + pid]);
         }
     }
     mL = group_sum<G>(mL, gmask);
@@ -432,18 +452,23 @@ __device__ __noinline__ double slow_cost(const MatchArgs &a, const double *__res
     mL /= tw;
     mR /= tw;
     double q1 = 0.0, q2 = 0.0, q3 = 0.0;
-#pragma unroll 1
-    for (int k = sub; k < WN; k += G) {
-        const int row = k / WS - R, col = k % WS - R;
-        const int xr = tx + col, yr = ty + row, xl = x + col, yl = y + row;
-        if (xr < 0 || yr < 0 || xr >= w || yr >= h || xl < 0 || yl < 0 || xl >= w || yl >= h) continue;
-        const double gl = a.grayL[(size_t)yl * w + xl], gr = gR[(size_t)yr * w + xr];
-        const double wt = a.W[(size_t)k * npix + pid];
+    auto second = [&](double gl, double gr, double wt) {
         if (gl == gl && gr == gr && wt > 1e-10) {
             const double pl = wt * gl - mL, pr = wt * gr - mR;
             q1 += pl * pr;
             q2 += pl * pl;
             q3 += pr * pr;
+        }
+    };
+    if (G == 1) {
+        walk(second);
+    } else {
+#pragma unroll 1
+        for (int k = sub; k < WN; k += G) {
+            const int row = k / WS - R, col = k % WS - R;
+            const int xr = tx + col, yr = ty + row, xl = x + col, yl = y + row;
+            if (xr < 0 || yr < 0 || xr >= w || yr >= h || xl < 0 || yl < 0 || xl >= w || yl >= h) continue;
+            second(a.grayL[(size_t)yl * w + xl], gR[(size_t)yr * w + xr], a.W[(size_t)k * npix + pid]);
         }
     }
     q1 = group_sum<G>(q1, gmask);
