@@ -501,6 +501,10 @@ __device__ __forceinline__ void cp_async4(void *smem_dst, const void *gmem_src, 
     asm volatile("cp.async.ca.shared.global.L2::cache_hint [%0], [%1], 4, %2;" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)),
                  "l"(gmem_src), "l"(pol));
 }
+// (shared-window address already converted: callers that issue many copies convert the base once)
+__device__ __forceinline__ void cp_async4_saddr(unsigned smem_addr, const void *gmem_src, uint64_t pol) {
+    asm volatile("cp.async.ca.shared.global.L2::cache_hint [%0], [%1], 4, %2;" ::"r"(smem_addr), "l"(gmem_src), "l"(pol));
+}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;"); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() {

@@ -955,9 +955,13 @@ constexpr int SCREEN2_TILE_ROWS = SR_SCREEN2_TILE_ROWS;
 // rasteriser) through the two-stage cp.async ring.  The warps of a block are independent (nothing is
 // block-wide); they own the rows of a 32-pixel-wide tile so that their neighbour-image footprints overlap
 // in L1 (adjacent reference rows project to adjacent neighbour rows).  grid = (ceil(w/32), ceil(rows/TR)).
+#ifdef SR_SCREEN2_MAXNREG  // A/B: an explicit register cap instead of the one MINBLOCKS implies
+#define SR_SCREEN2_BOUNDS __maxnreg__(SR_SCREEN2_MAXNREG)
+#else
+#define SR_SCREEN2_BOUNDS __launch_bounds__(32 * SCREEN2_TILE_ROWS, SR_SCREEN2_MINBLOCKS)
+#endif
 template <int R, bool STATS, int PITCH>
-__global__ void __launch_bounds__(32 * SCREEN2_TILE_ROWS, SR_SCREEN2_MINBLOCKS)
-    match_mvs_screen2_kernel(const __grid_constant__ MatchArgs a) {
+__global__ void SR_SCREEN2_BOUNDS match_mvs_screen2_kernel(const __grid_constant__ MatchArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     Screen2Smem<STATS> &sm = reinterpret_cast<Screen2Smem<STATS> *>(smem_raw)[warp];
@@ -979,7 +983,13 @@ __global__ void __launch_bounds__(32 * SCREEN2_TILE_ROWS, SR_SCREEN2_MINBLOCKS)
         if (jn < a.num_nbrs && S.alive) {
             const int32_t *src = a.taps + ((size_t)jn * (a.tap_planes ? a.tap_planes : D) + dn) * npix + pid;
             const int nl = min(TAP_CHUNK, D - dn);
-            for (int l = 0; l < nl; ++l) cp_async4(&sm.tap_ring[bufn][l][lane], src + (size_t)l * npix, pol);
+            const unsigned dst = (unsigned)__cvta_generic_to_shared(&sm.tap_ring[bufn][0][lane]);
+            if (nl == TAP_CHUNK) {  // whole chunk: ring offsets are immediates, the source a running pointer
+#pragma unroll
+                for (int l = 0; l < TAP_CHUNK; ++l, src += npix) cp_async4_saddr(dst + 128u * l, src, pol);
+            } else {
+                for (int l = 0; l < nl; ++l, src += npix) cp_async4_saddr(dst + 128u * l, src, pol);
+            }
         }
         cp_async_commit();
         bufn ^= 1;
