@@ -393,8 +393,11 @@ __device__ __forceinline__ int group_sum_i(int v, unsigned gmask) {
 // weight exceeds 1e-10), used for the few windows that touch an image border or an invalid
 // (masked) pixel.  Runtime loops, weights re-read from W: small code, no register arrays.
 template <int R, int G, int COST>
+// wloc: this pixel's support weights by tap index in shared memory (match_kernel with G > 1 lanes per pixel
+// stages them there: in the [tap][pixel] layout of W the G lanes of a pixel read G different planes, 32 sectors
+// per request, for every border label again), or null: read W.
 __device__ __noinline__ double slow_cost(const MatchArgs &a, const double *__restrict__ gR, int x, int y, int tx, int ty,
-                                         int pid, int sub, unsigned gmask) {
+                                         int pid, int sub, unsigned gmask, const double *wloc = nullptr) {
     constexpr int WS = 2 * R + 1, WN = WS * WS;
     constexpr bool NCC = (COST != SR_COST_SAD_TWOVIEW);
     const int w = a.w, h = a.h;
@@ -432,17 +435,35 @@ __device__ __noinline__ double slow_cost(const MatchArgs &a, const double *__res
             for (int col = col_lo; col <= col_hi; ++col, ++pl, ++pr, pw += npix) body(*pl, *pr, *pw);
         }
     };
-    if (G == 1) {
-        walk(first);
-    } else {
+    // G lanes per window (taps dealt round-robin): four of the lane's taps per step, their loads issued
+    // together (a tap outside either image reads as NaN, which the filter skips) and consumed in tap order —
+    // the loop used to wait for each tap's three loads in turn, at 8 warps per SM (cfg3: 70 % of the kernel).
+    constexpr int UNR = 4;
+    auto strided = [&](auto &&body) {
+        // (`a` arrives by reference: its pointers are read once here, not for every tap)
+        const double *__restrict__ const gLp = a.grayL;
+        const double *__restrict__ const Wp = a.W;
 #pragma unroll 1
-        for (int k = sub; k < WN; k += G) {
-            const int row = k / WS - R, col = k % WS - R;
-            const int xr = tx + col, yr = ty + row, xl = x + col, yl = y + row;
-            if (xr < 0 || yr < 0 || xr >= w || yr >= h || xl < 0 || yl < 0 || xl >= w || yl >= h) continue;
-            first(a.grayL[(size_t)yl * w + xl], gR[(size_t)yr * w + xr], a.W[(size_t)k * npix + pid]);
+        for (int k0 = sub; k0 < WN; k0 += UNR * G) {
+            double gl[UNR], gr[UNR], wt[UNR];
+            bool in[UNR];
+#pragma unroll
+            for (int u = 0; u < UNR; ++u) {  // unconditional loads from clamped addresses: nothing to branch around
+                const int k = min(k0 + u * G, WN - 1);
+                const int row = k / WS - R, col = k % WS - R;
+                const int xr = tx + col, yr = ty + row, xl = x + col, yl = y + row;
+                in[u] = k0 + u * G < WN && !(xr < 0 || yr < 0 || xr >= w || yr >= h || xl < 0 || yl < 0 || xl >= w || yl >= h);
+                const size_t il = in[u] ? (size_t)yl * w + xl : 0, ir = in[u] ? (size_t)yr * w + xr : 0;
+                gl[u] = gLp[il];
+                gr[u] = gR[ir];
+                wt[u] = wloc ? wloc[k] : Wp[(size_t)k * npix + pid];
+            }
+#pragma unroll
+            for (int u = 0; u < UNR; ++u) body(in[u] ? gl[u] : __longlong_as_double(0x7ff8000000000000ll), gr[u], wt[u]);
         }
-    }
+    };
+    if (G == 1) walk(first);
+    else strided(first);
     mL = group_sum<G>(mL, gmask);
     mR = group_sum<G>(mR, gmask);
     tw = group_sum<G>(tw, gmask);
@@ -460,17 +481,8 @@ __device__ __noinline__ double slow_cost(const MatchArgs &a, const double *__res
             q3 += pr * pr;
         }
     };
-    if (G == 1) {
-        walk(second);
-    } else {
-#pragma unroll 1
-        for (int k = sub; k < WN; k += G) {
-            const int row = k / WS - R, col = k % WS - R;
-            const int xr = tx + col, yr = ty + row, xl = x + col, yl = y + row;
-            if (xr < 0 || yr < 0 || xr >= w || yr >= h || xl < 0 || yl < 0 || xl >= w || yl >= h) continue;
-            second(a.grayL[(size_t)yl * w + xl], gR[(size_t)yr * w + xr], a.W[(size_t)k * npix + pid]);
-        }
-    }
+    if (G == 1) walk(second);
+    else strided(second);
     q1 = group_sum<G>(q1, gmask);
     q2 = group_sum<G>(q2, gmask);
     q3 = group_sum<G>(q3, gmask);
@@ -533,6 +545,10 @@ __global__ void __launch_bounds__(128, (R <= 2) ? SR_MATCH_MINBLOCKS : 2) match_
     // 4 blocks (16 warps) share an SM, which is what hides the FP64 issue latency.
     constexpr bool SMEM_C1 = (G == 1) && (SR_MATCH_SMEM_C1 != 0);
     __shared__ double c1s[SMEM_C1 ? TPL : 1][128];
+    // G > 1: the pixel's raw support weights by tap index, for slow_cost (dynamic: PIX_PER_BLOCK * WN doubles);
+    // every lane reads back only what it wrote (tap k belongs to lane k % G in both places)
+    extern __shared__ double wstage[];
+    double *const wloc = (G > 1) ? wstage + (size_t)(threadIdx.x / G) * WN : nullptr;
 
     const int lane = threadIdx.x & 31;
     const int sub = threadIdx.x % G;
@@ -570,6 +586,7 @@ __global__ void __launch_bounds__(128, (R <= 2) ? SR_MATCH_MINBLOCKS : 2) match_
             gl = a.grayL[(size_t)yl * w + xl];
             wv = a.W[(size_t)k * npix + pid];
         }
+        if (G > 1 && k < WN) wloc[k] = wv;
         const bool active = (gl == gl) && (wv > 1e-10);
         wt[i] = active ? wv : 0.0;
         c1[i] = active ? gl : 0.0;
@@ -724,7 +741,7 @@ __global__ void __launch_bounds__(128, (R <= 2) ? SR_MATCH_MINBLOCKS : 2) match_
                 const int tx = (int)(short)(tap & 0xffff), ty = (int)(short)((uint32_t)tap >> 16);
                 if (tx >= R && ty >= R && tx < w - R && ty < h - R) cost = fast_one(gR + ((size_t)ty * w + tx));
                 // windows touching a border / an invalid pixel: the reference's exact tap filter
-                if (cost != cost) cost = slow_cost<R, G, COST>(a, gR, x, y, tx, ty, pid, sub, gmask);
+                if (cost != cost) cost = slow_cost<R, G, COST>(a, gR, x, y, tx, ty, pid, sub, gmask, wloc);
                 // ---- stage (3): winner-take-all, fused ----
                 const int d = d0 + l;
                 // curve mode (multiviewstereo.cpp:583-588): a candidate's depth is the camera-space z of

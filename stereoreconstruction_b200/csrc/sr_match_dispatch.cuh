@@ -30,7 +30,12 @@ cudaError_t launch_match_rc(const MatchArgs &a, cudaStream_t st) {
     constexpr int PPB = 128 / G;
     const size_t npix = (size_t)a.rows * a.w;
     const unsigned grid = (unsigned)((npix + PPB - 1) / PPB);
-    match_kernel<R, G, COST><<<grid, 128, 0, st>>>(a);
+    constexpr size_t smem = (G > 1) ? (size_t)PPB * (2 * R + 1) * (2 * R + 1) * sizeof(double) : 0;  // wstage
+    if (smem > 0) {  // with the static tap ring the block can exceed 48 KB (r = 16): opt in
+        const cudaError_t e = cudaFuncSetAttribute(match_kernel<R, G, COST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+    }
+    match_kernel<R, G, COST><<<grid, 128, smem, st>>>(a);
     return cudaGetLastError();
 }
 

@@ -16,3 +16,5 @@ CMD3="python bench.py --workload cfg3 --steps 1 --warmup 0 --no-cpu --no-extras"
 $CMD3 > gpurun_out/r2_plain_cfg3.log 2>&1 &&
 ncu --set full --clock-control none --import-source on -k regex:'match_kernel' -s 0 -c 1 -f -o gpurun_out/prof_r2_cfg3 $CMD3 > gpurun_out/r2_ncu_cfg3.log 2>&1
 tail -2 gpurun_out/r2_ncu_cfg3.log | cut -c1-200
+python bench.py --workload cfg3 --steps 1 --warmup 1 > gpurun_out/r2_bench_cfg3.json 2> gpurun_out/r2_bench_cfg3.err; tail -c 300 gpurun_out/r2_bench_cfg3.json
+timeout 1500 python -m pytest tests -m gpu -x -q 2>&1 | tail -3
